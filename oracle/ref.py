@@ -1,0 +1,130 @@
+"""oracle/ref.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes client of ``oracle/_ref/libcalclens_ref.so`` = the UNMODIFIED CALCLENS reference functions compiled from
+/root/reference by ``oracle/Makefile`` (single-rank MPI stub, FP64-internal float FFT shim).  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this module; the product package
+``calclens_b200`` never does.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_ref", "libcalclens_ref.so")
+
+# HEALPixRay, raytrace.h:284-293 (176 bytes)
+RAY_DTYPE = np.dtype([("nest", "<i8"), ("n", "<f8", 3), ("beta", "<f8", 3), ("alpha", "<f8", 2),
+                      ("A", "<f8", 4), ("Aprev", "<f8", 4), ("U", "<f8", 4), ("phi", "<f8")], align=False)
+assert RAY_DTYPE.itemsize == 176
+
+_lib = None
+
+
+def available():
+    return os.path.exists(_SO)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError("oracle/_ref/libcalclens_ref.so missing: run `make -C oracle ref` where /root/reference exists")
+        L = C.CDLL(_SO)
+        dp, fp, lp = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_long)
+        L.ref_nmapvec.restype = C.c_long; L.ref_nmapvec.argtypes = [C.c_long]
+        L.ref_nlm.restype = C.c_long; L.ref_nlm.argtypes = [C.c_long]
+        L.ref_map2alm.restype = None; L.ref_map2alm.argtypes = [C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_poisson_filter.restype = None; L.ref_poisson_filter.argtypes = [C.c_long, C.c_void_p, C.c_void_p]
+        L.ref_alm2allmaps.restype = None; L.ref_alm2allmaps.argtypes = [C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_rayprop.restype = None; L.ref_rayprop.argtypes = [C.c_void_p, C.c_long, C.c_double, C.c_double, C.c_double]
+        L.ref_shearinterp.restype = C.c_long; L.ref_shearinterp.argtypes = [C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_long]
+        L.ref_read_ring_weights.restype = C.c_long; L.ref_read_ring_weights.argtypes = [C.c_char_p, C.c_long, C.c_void_p]
+        L.ref_plmgen.restype = C.c_long; L.ref_plmgen.argtypes = [C.c_long, C.c_double, C.c_double, C.c_long, C.c_void_p]
+        L.ref_sizeof_ray.restype = C.c_long
+        assert L.ref_sizeof_ray() == 176
+        # HEALPix helpers straight from healpix_utils.c
+        L.ring2nest.restype = C.c_long; L.ring2nest.argtypes = [C.c_long, C.c_long]
+        L.nest2ring.restype = C.c_long; L.nest2ring.argtypes = [C.c_long, C.c_long]
+        L.ang2nest.restype = C.c_long; L.ang2nest.argtypes = [C.c_double, C.c_double, C.c_long]
+        L.ang2ring.restype = C.c_long; L.ang2ring.argtypes = [C.c_double, C.c_double, C.c_long]
+        L.nest2peano.restype = C.c_long; L.nest2peano.argtypes = [C.c_long, C.c_long]
+        L.peano2nest.restype = C.c_long; L.peano2nest.argtypes = [C.c_long, C.c_long]
+        L.nest2vec.restype = None; L.nest2vec.argtypes = [C.c_long, dp, C.c_long]
+        L.vec2ang.restype = None; L.vec2ang.argtypes = [dp, dp, dp]
+        L.get_interpol.restype = None; L.get_interpol.argtypes = [C.c_double, C.c_double, lp, dp, C.c_long]
+        L.get_ring_info2.restype = None; L.get_ring_info2.argtypes = [C.c_long, lp, lp, dp, dp, lp, C.c_long]
+        L.get_lmin_ylm.restype = C.c_long; L.get_lmin_ylm.argtypes = [C.c_long, C.c_double]
+        _lib = L
+    return _lib
+
+
+def nlm(lmax):
+    return (lmax + 1) * (lmax + 2) // 2
+
+
+def map2alm(order, lmax, ringmap, ring_weights=None):
+    """map2alm_mpi on a RING-ordered float32 map -> (alm_re, alm_im), m-major."""
+    m = np.ascontiguousarray(ringmap, dtype=np.float32)
+    assert m.size == 12 << (2 * order)
+    are = np.zeros(nlm(lmax)); aim = np.zeros(nlm(lmax))
+    w = None if ring_weights is None else np.ascontiguousarray(ring_weights, dtype=np.float64)
+    lib().ref_map2alm(order, lmax, None if w is None else w.ctypes.data, m.ctypes.data, are.ctypes.data, aim.ctypes.data)
+    return are, aim
+
+
+def poisson_filter(lmax, are, aim):
+    are = np.array(are, dtype=np.float64); aim = np.array(aim, dtype=np.float64)
+    lib().ref_poisson_filter(lmax, are.ctypes.data, aim.ctypes.data)
+    return are, aim
+
+
+def alm2allmaps(order, lmax, are, aim):
+    """alm2allmaps_mpi -> float32 array [6, Npix] RING-ordered (phi, gt, gp, gtt, gtp, gpp)."""
+    are = np.ascontiguousarray(are, dtype=np.float64).copy(); aim = np.ascontiguousarray(aim, dtype=np.float64).copy()
+    maps = np.zeros((6, 12 << (2 * order)), dtype=np.float32)
+    lib().ref_alm2allmaps(order, lmax, are.ctypes.data, aim.ctypes.data, maps.ctypes.data)
+    return maps
+
+
+def rayprop(rays, wp, wpm1, wpm2):
+    assert rays.dtype == RAY_DTYPE and rays.flags.c_contiguous
+    lib().ref_rayprop(rays.ctypes.data, rays.size, wp, wpm1, wpm2)
+
+
+def shearinterp(poisson_order, bundle_order, maps, rays):
+    maps = np.ascontiguousarray(maps, dtype=np.float32)
+    assert rays.dtype == RAY_DTYPE and rays.flags.c_contiguous
+    bad = lib().ref_shearinterp(poisson_order, bundle_order, maps.ctypes.data, rays.ctypes.data, rays.size)
+    if bad:
+        raise RuntimeError("reference shearinterp_comp reported %d rays without map cells" % bad)
+
+
+def read_ring_weights(path, order):
+    out = np.zeros(2 << order)
+    n = lib().ref_read_ring_weights(path.encode(), order, out.ctypes.data)
+    if n != out.size:
+        raise RuntimeError("ring weights not read from %s" % path)
+    return out
+
+
+def plmgen(lmax, cth, sth, m):
+    vec = np.zeros(lmax + 1)
+    firstl = lib().ref_plmgen(lmax, cth, sth, m, vec.ctypes.data)
+    return firstl, vec
+
+
+def init_rays(ray_order, binL_2, nest_ids=None):
+    """Ray initialisation as raytrace_utils.c:302-347 (beta = pixel centre, n = beta*binL/2, A = Aprev = I)."""
+    L = lib()
+    npix = 12 << (2 * ray_order)
+    ids = np.arange(npix, dtype=np.int64) if nest_ids is None else np.asarray(nest_ids, dtype=np.int64)
+    rays = np.zeros(ids.size, dtype=RAY_DTYPE)
+    v = (C.c_double * 3)()
+    for i, nest in enumerate(ids):
+        L.nest2vec(int(nest), v, ray_order)
+        rays["beta"][i] = (v[0], v[1], v[2])
+    rays["nest"] = ids
+    rays["n"] = rays["beta"] * binL_2
+    rays["A"][:, 0] = 1.0; rays["A"][:, 3] = 1.0
+    rays["Aprev"][:, 0] = 1.0; rays["Aprev"][:, 3] = 1.0
+    return rays
