@@ -1,0 +1,296 @@
+// calclens_b200/csrc/api.cu -- extern "C" boundary of libcalclens_b200.so (see include/calclens_b200.h).
+#include "sht_internal.cuh"
+#include "raymath.cuh"
+#include "../../include/calclens_b200.h"
+#include <string.h>
+
+namespace clb {
+ShtPlan *sht_plan_create(long order, long lmax, const double *ring_weights, int nranks, int rank, const int *rp_owner,
+                         const int *m_owner);
+void sht_plan_destroy(ShtPlan *p);
+int launch_ring_analysis(const ShtPlan *p, const float *d_map, double2 *d_g_send, cudaStream_t st);
+int launch_ring_synthesis(const ShtPlan *p, const double2 *d_b_recv, float *const d_maps[6], cudaStream_t st);
+int launch_legendre_analysis(ShtPlan *p, const double2 *d_g_recv, double *d_alm_re, double *d_alm_im, int apply_filter,
+                             cudaStream_t st);
+int launch_legendre_synthesis(ShtPlan *p, const double *d_alm_re, const double *d_alm_im, double2 *d_b_send, cudaStream_t st);
+int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long order, double wp, double wpm1, double wpm2,
+                    int mode, cudaStream_t st);
+void launch_healpix_index(int what, long order, long n, const long *in, const double *th, const double *ph, long *out, cudaStream_t st);
+void launch_healpix_interpol(long order, long n, const double *vec, long *pix, double *wgt, cudaStream_t st);
+extern int g_syn_rings_per_thread;
+
+static long g_launches = 0;
+
+__global__ void scale_density_kernel(float *__restrict__ map, long npix, float premul, float densmul, float backdens)
+{
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i < npix; i += stride) {
+    float v = map[i];
+    v = __fmul_rn(v, premul);       // mapvec[i] *= (float)(partMass/MASS_SCALE)             shtpoissonsolve.c:426
+    v = __fmul_rn(v, densmul);      // mapvec[i] *= (float)(densfact/area*MASS_SCALE)        shtpoissonsolve.c:468
+    v = __fsub_rn(v, backdens);     // mapvec[i] -= (float) backdens                          shtpoissonsolve.c:478
+    map[i] = v;
+  }
+}
+}  // namespace clb
+
+using namespace clb;
+
+struct clb_sht_plan { ShtPlan *p; };
+
+static ShtPlan *P(const clb_sht_plan *plan)
+{
+  if (!plan || !plan->p) { fprintf(stderr, "calclens_b200: NULL plan\n"); abort(); }
+  return plan->p;
+}
+
+extern "C" {
+
+int clb_abi_version(void) { return 1; }
+
+int clb_device_count(void)
+{
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    fprintf(stderr, "calclens_b200: no CUDA device available (%s); this library has no CPU fallback\n",
+            e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    abort();
+  }
+  return n;
+}
+void clb_set_device(int device) { CLB_CUDA_CHECK(cudaSetDevice(device)); }
+long clb_launch_count(void) { return g_launches; }
+void clb_set_tuning(int what, int value)
+{
+  if (what == 0 && (value == 1 || value == 2 || value == 4)) g_syn_rings_per_thread = value;
+}
+
+clb_sht_plan *clb_sht_plan_create(long order, long lmax, const double *ring_weights, int nranks, int rank,
+                                  const int *rp_owner, const int *m_owner)
+{
+  clb_device_count();
+  if (order < 0 || order > 13 || lmax < 0 || nranks < 1 || rank < 0 || rank >= nranks) {
+    fprintf(stderr, "calclens_b200: bad plan arguments order=%ld lmax=%ld nranks=%d rank=%d\n", order, lmax, nranks, rank);
+    abort();
+  }
+  clb_sht_plan *h = new clb_sht_plan();
+  h->p = sht_plan_create(order, lmax, ring_weights, nranks, rank, rp_owner, m_owner);
+  return h;
+}
+void clb_sht_plan_destroy(clb_sht_plan *plan)
+{
+  if (!plan) return;
+  sht_plan_destroy(plan->p);
+  delete plan;
+}
+long clb_sht_plan_query(const clb_sht_plan *plan, int what)
+{
+  const ShtPlan *p = P(plan);
+  switch (what) {
+    case 0: return p->npix;
+    case 1: return p->lmax;
+    case 2: return p->alm_total;
+    case 3: return p->nrp_loc;
+    case 4: return p->nm_loc;
+    case 5: return p->g_send_total;
+    case 6: return p->g_recv_total;
+    case 7: return p->b_send_total;
+    case 8: return p->b_recv_total;
+    case 9: return p->nranks;
+    case 10: return p->rank;
+    default: return -1;
+  }
+}
+void clb_sht_plan_counts(const clb_sht_plan *plan, int which, long *counts)
+{
+  const ShtPlan *p = P(plan);
+  const std::vector<long> *v = which == 0 ? &p->g_send_count : which == 1 ? &p->g_recv_count
+                             : which == 2 ? &p->b_send_count : &p->b_recv_count;
+  for (int q = 0; q < p->nranks; ++q) counts[q] = (*v)[q];
+}
+void clb_sht_plan_local_m(const clb_sht_plan *plan, int *m_list)
+{
+  const ShtPlan *p = P(plan);
+  for (int i = 0; i < p->nm_loc; ++i) m_list[i] = p->m_loc[i];
+}
+void clb_sht_plan_local_ring_pairs(const clb_sht_plan *plan, int *rp_list)
+{
+  const ShtPlan *p = P(plan);
+  for (int i = 0; i < p->nrp_loc; ++i) rp_list[i] = p->rp_loc[i];
+}
+
+int clb_ring_analysis_dev(const clb_sht_plan *plan, const float *map, double *g_send, void *stream)
+{
+  int n = launch_ring_analysis(P(plan), map, reinterpret_cast<double2 *>(g_send), (cudaStream_t)stream);
+  g_launches += n; return n;
+}
+int clb_legendre_analysis_dev(clb_sht_plan *plan, const double *g_recv, double *alm_re, double *alm_im,
+                              int apply_poisson_filter, void *stream)
+{
+  int n = launch_legendre_analysis(P(plan), reinterpret_cast<const double2 *>(g_recv), alm_re, alm_im,
+                                   apply_poisson_filter, (cudaStream_t)stream);
+  g_launches += n; return n;
+}
+int clb_legendre_synthesis_dev(clb_sht_plan *plan, const double *alm_re, const double *alm_im, double *b_send, void *stream)
+{
+  int n = launch_legendre_synthesis(P(plan), alm_re, alm_im, reinterpret_cast<double2 *>(b_send), (cudaStream_t)stream);
+  g_launches += n; return n;
+}
+int clb_ring_synthesis_dev(const clb_sht_plan *plan, const double *b_recv, float *const maps[6], void *stream)
+{
+  int n = launch_ring_synthesis(P(plan), reinterpret_cast<const double2 *>(b_recv), maps, (cudaStream_t)stream);
+  g_launches += n; return n;
+}
+int clb_scale_density_dev(float *map, long npix, float premul, float densmul, float backdens, void *stream)
+{
+  if (npix <= 0) return 0;
+  scale_density_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(map, npix, premul, densmul, backdens);
+  CLB_CUDA_CHECK(cudaGetLastError());
+  g_launches += 1; return 1;
+}
+int clb_ray_step_dev(void *rays, long nrays, const float *const maps[6], long map_order, double wp, double wpm1,
+                     double wpm2, int mode, void *stream)
+{
+  if ((mode & 2) && !maps) { fprintf(stderr, "calclens_b200: clb_ray_step_dev mode 2 needs maps\n"); abort(); }
+  int n = launch_ray_step(reinterpret_cast<Ray *>(rays), nrays, maps, map_order, wp, wpm1, wpm2, mode, (cudaStream_t)stream);
+  g_launches += n; return n;
+}
+void clb_healpix_index_dev(int what, long order, long n, const long *in, const double *theta, const double *phi,
+                           long *out, void *stream)
+{
+  launch_healpix_index(what, order, n, in, theta, phi, out, (cudaStream_t)stream);
+  g_launches += 1;
+}
+void clb_healpix_interpol_dev(long order, long n, const double *vec, long *pix, double *wgt, void *stream)
+{
+  launch_healpix_interpol(order, n, vec, pix, wgt, (cudaStream_t)stream);
+  g_launches += 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host-pointer entry points (single rank)
+// ---------------------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+static void require_single(const ShtPlan *p, const char *who)
+{
+  if (p->nranks != 1) { fprintf(stderr, "calclens_b200: %s needs a single-rank plan (use the _dev stages)\n", who); abort(); }
+}
+
+struct DevBuf {
+  void *p = nullptr;
+  explicit DevBuf(size_t bytes) { CLB_CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 16)); }
+  ~DevBuf() { cudaFree(p); }
+  template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+extern "C" {
+
+void clb_map2alm(clb_sht_plan *plan, const float *ringmap, double *alm_re, double *alm_im, int apply_poisson_filter)
+{
+  ShtPlan *p = P(plan);
+  require_single(p, "clb_map2alm");
+  DevBuf map(sizeof(float) * p->npix), g(sizeof(double2) * p->g_send_total), are(sizeof(double) * p->alm_total),
+      aim(sizeof(double) * p->alm_total);
+  CLB_CUDA_CHECK(cudaMemcpy(map.p, ringmap, sizeof(float) * p->npix, cudaMemcpyHostToDevice));
+  clb_ring_analysis_dev(plan, map.as<float>(), g.as<double>(), nullptr);
+  clb_legendre_analysis_dev(plan, g.as<double>(), are.as<double>(), aim.as<double>(), apply_poisson_filter, nullptr);
+  CLB_CUDA_CHECK(cudaMemcpy(alm_re, are.p, sizeof(double) * p->alm_total, cudaMemcpyDeviceToHost));
+  CLB_CUDA_CHECK(cudaMemcpy(alm_im, aim.p, sizeof(double) * p->alm_total, cudaMemcpyDeviceToHost));
+}
+
+void clb_alm2allmaps(clb_sht_plan *plan, const double *alm_re, const double *alm_im, float *maps)
+{
+  ShtPlan *p = P(plan);
+  require_single(p, "clb_alm2allmaps");
+  DevBuf dm(sizeof(float) * 6 * p->npix), b(sizeof(double2) * p->b_send_total), are(sizeof(double) * p->alm_total),
+      aim(sizeof(double) * p->alm_total);
+  CLB_CUDA_CHECK(cudaMemcpy(are.p, alm_re, sizeof(double) * p->alm_total, cudaMemcpyHostToDevice));
+  CLB_CUDA_CHECK(cudaMemcpy(aim.p, alm_im, sizeof(double) * p->alm_total, cudaMemcpyHostToDevice));
+  float *mp[6];
+  for (int k = 0; k < 6; ++k) mp[k] = dm.as<float>() + (size_t)k * p->npix;
+  clb_legendre_synthesis_dev(plan, are.as<double>(), aim.as<double>(), b.as<double>(), nullptr);
+  clb_ring_synthesis_dev(plan, b.as<double>(), mp, nullptr);
+  CLB_CUDA_CHECK(cudaMemcpy(maps, dm.p, sizeof(float) * 6 * p->npix, cudaMemcpyDeviceToHost));
+}
+
+}  // extern "C"
+
+static void mapvec_to_ring(const ShtPlan *p, const float *mapvec, const long *ns, const long *ss, float *ring)
+{
+  for (int rp = 0; rp < p->nrp; ++rp) {
+    const size_t n = (size_t)p->h_nphi[rp];
+    memcpy(ring + p->h_startN[rp], mapvec + 2 * ns[rp], sizeof(float) * n);
+    if (p->h_startS[rp] >= 0) memcpy(ring + p->h_startS[rp], mapvec + 2 * ss[rp], sizeof(float) * n);
+  }
+}
+static void ring_to_mapvec(const ShtPlan *p, const float *ring, const long *ns, const long *ss, float *mapvec)
+{
+  for (int rp = 0; rp < p->nrp; ++rp) {
+    const size_t n = (size_t)p->h_nphi[rp];
+    memcpy(mapvec + 2 * ns[rp], ring + p->h_startN[rp], sizeof(float) * n);
+    if (p->h_startS[rp] >= 0) memcpy(mapvec + 2 * ss[rp], ring + p->h_startS[rp], sizeof(float) * n);
+  }
+}
+
+extern "C" {
+
+void clb_map2alm_mapvec(clb_sht_plan *plan, float *mapvec, const long *north_start, const long *south_start,
+                        double *alm_re, double *alm_im)
+{
+  ShtPlan *p = P(plan);
+  require_single(p, "clb_map2alm_mapvec");
+  std::vector<float> ring(p->npix);
+  mapvec_to_ring(p, mapvec, north_start, south_start, ring.data());
+  clb_map2alm(plan, ring.data(), alm_re, alm_im, 0);
+}
+
+void clb_alm2allmaps_mapvec(clb_sht_plan *plan, const double *alm_re, const double *alm_im, float *const mapvec[6],
+                            const long *north_start, const long *south_start)
+{
+  ShtPlan *p = P(plan);
+  require_single(p, "clb_alm2allmaps_mapvec");
+  std::vector<float> maps((size_t)6 * p->npix);
+  clb_alm2allmaps(plan, alm_re, alm_im, maps.data());
+  for (int k = 0; k < 6; ++k) ring_to_mapvec(p, maps.data() + (size_t)k * p->npix, north_start, south_start, mapvec[k]);
+}
+
+void clb_ray_step(void *rays, long nrays, const float *maps, long map_order, double wp, double wpm1, double wpm2, int mode)
+{
+  clb_device_count();
+  const long npix = 12L << (2 * map_order);
+  DevBuf dr(sizeof(Ray) * nrays), dm((mode & 2) ? sizeof(float) * 6 * npix : 16);
+  CLB_CUDA_CHECK(cudaMemcpy(dr.p, rays, sizeof(Ray) * nrays, cudaMemcpyHostToDevice));
+  const float *mp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (mode & 2) {
+    if (!maps) { fprintf(stderr, "calclens_b200: clb_ray_step mode 2 needs maps\n"); abort(); }
+    CLB_CUDA_CHECK(cudaMemcpy(dm.p, maps, sizeof(float) * 6 * npix, cudaMemcpyHostToDevice));
+    for (int k = 0; k < 6; ++k) mp[k] = dm.as<float>() + (size_t)k * npix;
+  }
+  clb_ray_step_dev(dr.p, nrays, mp, map_order, wp, wpm1, wpm2, mode, nullptr);
+  CLB_CUDA_CHECK(cudaMemcpy(rays, dr.p, sizeof(Ray) * nrays, cudaMemcpyDeviceToHost));
+}
+
+void clb_lens_plane(clb_sht_plan *plan, const float *ringmap, float premul, float densmul, float backdens, void *rays,
+                    long nrays, double wp, double wpm1, double wpm2)
+{
+  ShtPlan *p = P(plan);
+  require_single(p, "clb_lens_plane");
+  DevBuf dm(sizeof(float) * 6 * p->npix), g(sizeof(double2) * p->g_send_total), b(sizeof(double2) * p->b_send_total),
+      are(sizeof(double) * p->alm_total), aim(sizeof(double) * p->alm_total), dr(sizeof(Ray) * nrays);
+  float *mp[6];
+  for (int k = 0; k < 6; ++k) mp[k] = dm.as<float>() + (size_t)k * p->npix;
+  CLB_CUDA_CHECK(cudaMemcpyAsync(mp[0], ringmap, sizeof(float) * p->npix, cudaMemcpyHostToDevice, nullptr));
+  CLB_CUDA_CHECK(cudaMemcpyAsync(dr.p, rays, sizeof(Ray) * nrays, cudaMemcpyHostToDevice, nullptr));
+  clb_scale_density_dev(mp[0], p->npix, premul, densmul, backdens, nullptr);
+  clb_ring_analysis_dev(plan, mp[0], g.as<double>(), nullptr);
+  clb_legendre_analysis_dev(plan, g.as<double>(), are.as<double>(), aim.as<double>(), 1, nullptr);
+  clb_legendre_synthesis_dev(plan, are.as<double>(), aim.as<double>(), b.as<double>(), nullptr);
+  clb_ring_synthesis_dev(plan, b.as<double>(), mp, nullptr);
+  clb_ray_step_dev(dr.p, nrays, mp, p->order, wp, wpm1, wpm2, 1 | 2 | 4, nullptr);
+  CLB_CUDA_CHECK(cudaMemcpy(rays, dr.p, sizeof(Ray) * nrays, cudaMemcpyDeviceToHost));
+}
+
+}  // extern "C"

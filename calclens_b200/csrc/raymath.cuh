@@ -1,0 +1,190 @@
+// calclens_b200/csrc/raymath.cuh
+// Per-ray arithmetic of the lens-plane step, host and device: parallel transport of tangent vectors/tensors
+// along great circles, 4-point interpolation of the derivative maps at the ray position, and the plane-to-plane
+// propagation (deflect beta, advance n, A-matrix recursion).  All FP64; the translation unit that includes this
+// for the device is compiled with -fmad=false so that products and sums round exactly like the reference's
+// plain C (oracle built without FP contraction).
+#pragma once
+#include "healpix.cuh"
+
+namespace clb {
+
+// HEALPixRay, 176 bytes, identical field order to raytrace.h:284-293 so host arrays can be copied verbatim.
+struct Ray {
+  long nest;
+  double n[3];
+  double beta[3];
+  double alpha[2];
+  double A[4];
+  double Aprev[4];
+  double U[4];
+  double phi;
+};
+static_assert(sizeof(Ray) == 176, "Ray must match HEALPixRay");
+
+// Rodrigues rotation of vec about a unit axis by (cos, sin)            [rot_paratrans.c:78-92]
+CLB_HD void rot_vec_axis_trig(const double vec[3], double rvec[3], const double axis[3], double cosangle, double sinangle)
+{
+  double axisdotvec = axis[0] * vec[0] + axis[1] * vec[1] + axis[2] * vec[2];
+  double c0 = axis[1] * vec[2] - axis[2] * vec[1];
+  double c1 = axis[2] * vec[0] - axis[0] * vec[2];
+  double c2 = axis[0] * vec[1] - axis[1] * vec[0];
+  rvec[0] = vec[0] * cosangle + axis[0] * axisdotvec * (1.0 - cosangle) + c0 * sinangle;
+  rvec[1] = vec[1] * cosangle + axis[1] * axisdotvec * (1.0 - cosangle) + c1 * sinangle;
+  rvec[2] = vec[2] * cosangle + axis[2] * axisdotvec * (1.0 - cosangle) + c2 * sinangle;
+}
+
+// rotation angle psi of the (e_theta, e_phi) frame when transported from _vec to _rvec along their great circle.
+// Shared front half of paratrans_tangvec / paratrans_tangtensor.        [rot_paratrans.c:101-150, :179-233]
+CLB_HD void paratrans_angle(const double _vec[3], const double _rvec[3], double &cospsi, double &sinpsi)
+{
+  double vec[3], rvec[3], axis[3], p[3], rephi[3], ephi[3], etheta[3];
+  double norm_vec = sqrt(_vec[0] * _vec[0] + _vec[1] * _vec[1] + _vec[2] * _vec[2]);
+  vec[0] = _vec[0] / norm_vec; vec[1] = _vec[1] / norm_vec; vec[2] = _vec[2] / norm_vec;
+  double norm_rvec = sqrt(_rvec[0] * _rvec[0] + _rvec[1] * _rvec[1] + _rvec[2] * _rvec[2]);
+  rvec[0] = _rvec[0] / norm_rvec; rvec[1] = _rvec[1] / norm_rvec; rvec[2] = _rvec[2] / norm_rvec;
+  axis[0] = vec[1] * rvec[2] - vec[2] * rvec[1];
+  axis[1] = vec[2] * rvec[0] - vec[0] * rvec[2];
+  axis[2] = vec[0] * rvec[1] - vec[1] * rvec[0];
+  double cosangle = vec[0] * rvec[0] + vec[1] * rvec[1] + vec[2] * rvec[2];
+  double sinangle = sqrt(axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2]);
+  if (sinangle != 0.0) { axis[0] /= sinangle; axis[1] /= sinangle; axis[2] /= sinangle; }
+  else { axis[0] = 1.0; axis[1] = 0.0; axis[2] = 0.0; }
+  p[0] = -vec[1]; p[1] = vec[0]; p[2] = 0.0;
+  rot_vec_axis_trig(p, rephi, axis, cosangle, sinangle);
+  ephi[0] = -rvec[1]; ephi[1] = rvec[0]; ephi[2] = 0.0;
+  etheta[0] = rvec[2] * rvec[0]; etheta[1] = rvec[2] * rvec[1];
+  etheta[2] = -1.0 * (rvec[0] * rvec[0] + rvec[1] * rvec[1]);
+  double norm = sqrt((1.0 - rvec[2]) * (1.0 + rvec[2]) * (1.0 - vec[2]) * (1.0 + vec[2]));
+  sinpsi = (rephi[0] * etheta[0] + rephi[1] * etheta[1] + rephi[2] * etheta[2]) / norm;
+  cospsi = (rephi[0] * ephi[0] + rephi[1] * ephi[1] + rephi[2] * ephi[2]) / norm;
+}
+
+CLB_HD void transport_vec(const double t[2], double cospsi, double sinpsi, double rt[2])   // [rot_paratrans.c:168-169]
+{
+  rt[0] = t[0] * cospsi + t[1] * sinpsi;
+  rt[1] = -1.0 * t[0] * sinpsi + t[1] * cospsi;
+}
+// T' = R^T T R with R = [[c, -s], [s, c]]                              [rot_paratrans.c:251-270]
+CLB_HD void transport_tensor(const double T[2][2], double c, double s, double RT[2][2])
+{
+  double r[2][2] = {{c, -1.0 * s}, {s, c}};
+  double rt[2][2] = {{r[0][0], r[1][0]}, {r[0][1], r[1][1]}};
+  double t1[2][2];
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) t1[i][j] = T[i][0] * r[0][j] + T[i][1] * r[1][j];
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) RT[i][j] = rt[i][0] * t1[0][j] + rt[i][1] * t1[1][j];
+}
+
+// Interpolate phi, grad phi, grad grad phi at the ray position from six RING-ordered float maps and accumulate
+// into the ray exactly as the reference's caller does: phi = ., alpha -= grad, U += hessian.
+//                                        [shtpoissonsolve.c:1122-1204 shearinterp_comp, :666-702 caller]
+// maps: m_phi, m_gt, m_gp, m_gtt, m_gtp, m_gpp (same argument order as alm2allmaps_mpi, healpix_shtrans.h:70-72)
+CLB_HD void ray_interp_accumulate(Ray &ray, long order, const float *m_phi, const float *m_gt, const float *m_gp,
+                                  const float *m_gtt, const float *m_gtp, const float *m_gpp)
+{
+  double theta, phi, wgt[4];
+  long pix[4];
+  vec2ang(ray.n, theta, phi);
+  get_interpol(theta, phi, pix, wgt, order);
+  double pot = 0.0, gtheta = 0.0, gphi = 0.0;
+  double ti[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  for (int k = 0; k < 4; ++k) {
+    long p = pix[k];
+    double vec[3], z, ph, c, s, tvec[2], rtvec[2], T[2][2], RT[2][2];
+    pot += m_phi[p] * wgt[k];
+    ringpix2zphi(p, order, z, ph);
+    zphi2vec(z, ph, vec);
+    paratrans_angle(vec, ray.n, c, s);   // the reference evaluates the same angle twice (vector, then tensor)
+    tvec[0] = m_gt[p]; tvec[1] = m_gp[p];
+    transport_vec(tvec, c, s, rtvec);
+    gtheta += rtvec[0] * wgt[k];
+    gphi += rtvec[1] * wgt[k];
+    T[0][0] = m_gtt[p]; T[0][1] = m_gtp[p]; T[1][0] = m_gtp[p]; T[1][1] = m_gpp[p];
+    transport_tensor(T, c, s, RT);
+    ti[0][0] += RT[0][0] * wgt[k]; ti[0][1] += RT[0][1] * wgt[k];
+    ti[1][0] += RT[1][0] * wgt[k]; ti[1][1] += RT[1][1] * wgt[k];
+  }
+  ray.phi = pot;
+  ray.alpha[0] += -1.0 * gtheta;
+  ray.alpha[1] += -1.0 * gphi;
+  ray.U[0] += ti[0][0]; ray.U[1] += ti[0][1]; ray.U[2] += ti[1][0]; ray.U[3] += ti[1][1];
+}
+
+// One lens-plane step of one ray: wp = w_{p+1}, wpm1 = w_p, wpm2 = w_{p-1} (the reference's argument names).
+//                                        [rayprop.c:18-189 rayprop_sphere (non-BORNAPPRX branch),
+//                                         rot_paratrans.c:17-45 generate_rotmat_axis_angle_countercw]
+CLB_HD void ray_propagate(Ray &ray, double wp, double wpm1, double wpm2)
+{
+  double np[3], betap[3], Ap[4];
+  double alpha = sqrt(ray.alpha[0] * ray.alpha[0] + ray.alpha[1] * ray.alpha[1]);
+  if (alpha > 0.0) {
+    double phihat[3], thetahat[3], a[3], nxa[3], R[3][3], norm;
+    phihat[0] = -1.0 * ray.n[1]; phihat[1] = ray.n[0]; phihat[2] = 0.0;
+    norm = sqrt(phihat[0] * phihat[0] + phihat[1] * phihat[1]);
+    phihat[0] /= norm; phihat[1] /= norm;
+    thetahat[0] = ray.n[2] * ray.n[0];
+    thetahat[1] = ray.n[2] * ray.n[1];
+    thetahat[2] = -1.0 * (ray.n[0] * ray.n[0] + ray.n[1] * ray.n[1]);
+    norm = sqrt(thetahat[0] * thetahat[0] + thetahat[1] * thetahat[1] + thetahat[2] * thetahat[2]);
+    thetahat[0] /= norm; thetahat[1] /= norm; thetahat[2] /= norm;
+    a[0] = ray.alpha[0] * thetahat[0] + ray.alpha[1] * phihat[0];
+    a[1] = ray.alpha[0] * thetahat[1] + ray.alpha[1] * phihat[1];
+    a[2] = ray.alpha[0] * thetahat[2] + ray.alpha[1] * phihat[2];
+    nxa[0] = ray.n[1] * a[2] - ray.n[2] * a[1];
+    nxa[1] = ray.n[2] * a[0] - ray.n[0] * a[2];
+    nxa[2] = ray.n[0] * a[1] - ray.n[1] * a[0];
+    norm = sqrt(nxa[0] * nxa[0] + nxa[1] * nxa[1] + nxa[2] * nxa[2]);
+    nxa[0] /= norm; nxa[1] /= norm; nxa[2] /= norm;
+    // rotation matrix about nxa by alpha, counter-clockwise
+    double sinangle = sin(alpha), cosangle = cos(alpha);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) R[i][j] = 0.0;
+    R[0][0] = cosangle; R[1][1] = cosangle; R[2][2] = cosangle;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) R[i][j] += nxa[i] * nxa[j] * (1.0 - cosangle);
+    R[0][1] -= nxa[2] * sinangle; R[0][2] += nxa[1] * sinangle; R[1][2] -= nxa[0] * sinangle;
+    R[1][0] += nxa[2] * sinangle; R[2][0] -= nxa[1] * sinangle; R[2][1] += nxa[0] * sinangle;
+    for (int i = 0; i < 3; ++i) {
+      betap[i] = R[i][0] * ray.beta[0];
+      betap[i] += R[i][1] * ray.beta[1];
+      betap[i] += R[i][2] * ray.beta[2];
+    }
+    double qa = 1.0;
+    double qb = 2.0 * (ray.n[0] * betap[0] + ray.n[1] * betap[1] + ray.n[2] * betap[2]);
+    double qc = wpm1 * wpm1 - wp * wp;
+    double q = -0.5 * (qb + qb / fabs(qb) * sqrt(qb * qb - 4.0 * qa * qc));
+    double lambda = qc / q;
+    if (lambda < 0.0) lambda = q / qa;
+    np[0] = ray.n[0] + betap[0] * lambda;
+    np[1] = ray.n[1] + betap[1] * lambda;
+    np[2] = ray.n[2] + betap[2] * lambda;
+  } else {
+    betap[0] = ray.beta[0]; betap[1] = ray.beta[1]; betap[2] = ray.beta[2];
+    np[0] = ray.n[0] / wpm1 * wp;
+    np[1] = ray.n[1] / wpm1 * wp;
+    np[2] = ray.n[2] / wpm1 * wp;
+  }
+  for (int n = 0; n < 2; ++n)
+    for (int m = 0; m < 2; ++m)
+      Ap[m + 2 * n] = (1.0 - wpm1 * (wp - wpm2) / wp / (wpm1 - wpm2)) * ray.Aprev[m + 2 * n]
+                      + (wpm1 * (wp - wpm2) / wp / (wpm1 - wpm2)) * ray.A[m + 2 * n]
+                      - ((wp - wpm1) / wp) * (ray.U[0 + 2 * n] * ray.A[m + 2 * 0] + ray.U[1 + 2 * n] * ray.A[m + 2 * 1]);
+  double c, s, T[2][2], RT[2][2];
+  paratrans_angle(ray.n, np, c, s);
+  // Aprev <- transport(A), A <- transport(Ap)
+  T[0][0] = ray.A[0]; T[0][1] = ray.A[1]; T[1][0] = ray.A[2]; T[1][1] = ray.A[3];
+  transport_tensor(T, c, s, RT);
+  ray.Aprev[0] = RT[0][0]; ray.Aprev[1] = RT[0][1]; ray.Aprev[2] = RT[1][0]; ray.Aprev[3] = RT[1][1];
+  T[0][0] = Ap[0]; T[0][1] = Ap[1]; T[1][0] = Ap[2]; T[1][1] = Ap[3];
+  transport_tensor(T, c, s, RT);
+  ray.A[0] = RT[0][0]; ray.A[1] = RT[0][1]; ray.A[2] = RT[1][0]; ray.A[3] = RT[1][1];
+  ray.n[0] = np[0]; ray.n[1] = np[1]; ray.n[2] = np[2];
+  ray.beta[0] = betap[0]; ray.beta[1] = betap[1]; ray.beta[2] = betap[2];
+  double r = sqrt(ray.n[0] * ray.n[0] + ray.n[1] * ray.n[1] + ray.n[2] * ray.n[2]);
+  r = wp / r;
+  ray.n[0] *= r; ray.n[1] *= r; ray.n[2] *= r;
+}
+
+}  // namespace clb

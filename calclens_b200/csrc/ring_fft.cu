@@ -1,0 +1,699 @@
+// calclens_b200/csrc/ring_fft.cu
+// Batched HEALPix ring FFTs for sm_100a: one CTA per ring, everything between the HBM read and the HBM write stays
+// in shared memory.  Replaces the per-ring FFTW calls and the pack/unpack loops of the reference:
+//   analysis : ring weights, r2c, alias pick + conjugate, half-pixel phase, write g_m
+//              [map2alm_transpose_mpi.c:151-191 (weights + ring_analysis), :219-315 (pack); healpix_shtrans.c:549-571]
+//   synthesis: alias fold of b_m into float half-complex bins, half-pixel phase, c2r, 1/sin(theta) scalings,
+//              cot(theta) cross terms
+//              [alm2allmaps_transpose_mpi.c:818-947 (unpack), :1034-1089 (FFT + scale), :1097-1147 (cot terms);
+//               healpix_shtrans.c:168-205 ring_synthesis]
+//
+// Precision contract (SURVEY.md App. A.6 / DESIGN.md): the reference stores ring spectra as float and the FFT
+// library it links is third-party, so the oracle uses an exactly-rounded float FFT.  Here the transform itself
+// runs in FP64 and is rounded to float exactly where the reference stores a float; every other float rounding
+// point of the reference is reproduced explicitly with __double2float_rn-style casts and un-contracted
+// arithmetic (__dmul_rn/__dadd_rn) so that results agree to the last float bit except for FP64-level noise.
+//
+// Algorithm: a real ring has n = 4r pixels.  Radix-4 split into four real length-r sequences, packed pairwise
+// into two complex length-r DFTs.  DFT_r: r a power of two -> in-place radix-4 DIF (bit-reversed read-out);
+// otherwise Bluestein with M = pow2 >= 2r-1: DIF forward, product with a precomputed bit-reversed chirp spectrum,
+// DIT inverse (no bit reversal anywhere).  (Index math prototyped in tools/fft_proto.py.)
+#include "sht_internal.cuh"
+#include "healpix.cuh"
+#include <algorithm>
+#include <math.h>
+
+namespace clb {
+
+struct FftClass {
+  int logM;          // work length M = 1 << logM
+  int bluestein;     // 0: r == M direct power-of-two path
+  int rmax;          // largest r in the class (sizes shared memory)
+  int count;         // ring pairs in the class (local ones only)
+  int *d_rp = nullptr;   // [count] global ring-pair indices
+  int threads;
+  size_t smem_ana, smem_syn;
+};
+
+struct FftTables {
+  int logTW = 0;                 // twiddle table: exp(-2 pi i k / TW), k < TW/2
+  double2 *d_tw = nullptr;
+  // Bluestein tables, indexed by r (only non-power-of-two r < Nside are filled)
+  long *d_chirp_off = nullptr;   // [nside+1] offset of chirp_r (r entries)
+  long *d_bhat_off = nullptr;    // [nside+1] offset of bhat_r (M(r) entries, bit-reversed order, includes 1/M)
+  double2 *d_chirp = nullptr;
+  double2 *d_bhat = nullptr;
+  std::vector<FftClass> classes;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// complex helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b)
+{
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b)   // a * conj(b)
+{
+  return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ double2 mul_mi(double2 a) { return make_double2(a.y, -a.x); }   // a * (-i)
+__device__ __forceinline__ double2 mul_pi(double2 a) { return make_double2(-a.y, a.x); }   // a * (+i)
+
+// exp(i * pi * num / den) for integers, exact argument reduction
+__device__ __forceinline__ double2 unit_pi(long num, long den)
+{
+  long twoden = 2 * den;
+  num %= twoden;
+  if (num < 0) num += twoden;
+  double s, c;
+  sincospi((double)num / (double)den, &s, &c);
+  return make_double2(c, s);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-cooperative in-place FFTs on shared memory (all threads of the block must call)
+// ---------------------------------------------------------------------------------------------------------------
+// forward, sign -1, natural order in -> bit-reversed order out
+__device__ void cta_fft_dif(double2 *a, int logM, const double2 *__restrict__ tw, int logTW)
+{
+  const int M = 1 << logM;
+  int lg = logM;
+  if (lg & 1) {   // one radix-2 stage first so the rest is radix-4
+    const int span = M >> 1;
+    const int sh = logTW - lg;   // TW / (2*span)
+    for (int idx = threadIdx.x; idx < span; idx += blockDim.x) {
+      double2 u = a[idx], v = a[idx + span];
+      double2 w = __ldg(&tw[(size_t)idx << sh]);
+      a[idx] = cadd(u, v);
+      a[idx + span] = cmul(csub(u, v), w);
+    }
+    __syncthreads();
+    lg -= 1;
+  }
+  // now blocks of length 1<<lg, processed by fused radix-2x2 stages
+  for (; lg >= 2; lg -= 2) {
+    const int s = 1 << (lg - 2);        // quarter length
+    const int sh1 = logTW - lg;         // W_{4s}^j  = tw[j << sh1]
+    for (int idx = threadIdx.x; idx < (M >> 2); idx += blockDim.x) {
+      const int j = idx & (s - 1);
+      const int base = ((idx >> (lg - 2)) << lg) + j;
+      double2 a0 = a[base], a1 = a[base + s], a2 = a[base + 2 * s], a3 = a[base + 3 * s];
+      double2 w1 = __ldg(&tw[(size_t)j << sh1]);
+      double2 w2 = __ldg(&tw[(size_t)j << (sh1 + 1)]);
+      double2 b0 = cadd(a0, a2), b2 = cmul(csub(a0, a2), w1);
+      double2 b1 = cadd(a1, a3), b3 = cmul(mul_mi(csub(a1, a3)), w1);
+      a[base] = cadd(b0, b1);
+      a[base + s] = cmul(csub(b0, b1), w2);
+      a[base + 2 * s] = cadd(b2, b3);
+      a[base + 3 * s] = cmul(csub(b2, b3), w2);
+    }
+    __syncthreads();
+  }
+}
+
+// inverse (unnormalised), sign +1, bit-reversed order in -> natural order out
+__device__ void cta_fft_dit_inv(double2 *a, int logM, const double2 *__restrict__ tw, int logTW)
+{
+  const int M = 1 << logM;
+  int lg = 2;
+  for (; lg <= logM; lg += 2) {
+    const int s = 1 << (lg - 2);
+    const int sh1 = logTW - lg;
+    for (int idx = threadIdx.x; idx < (M >> 2); idx += blockDim.x) {
+      const int j = idx & (s - 1);
+      const int base = ((idx >> (lg - 2)) << lg) + j;
+      double2 a0 = a[base], a1 = a[base + s], a2 = a[base + 2 * s], a3 = a[base + 3 * s];
+      double2 w1 = __ldg(&tw[(size_t)j << sh1]);
+      double2 w2 = __ldg(&tw[(size_t)j << (sh1 + 1)]);
+      double2 t1 = cmulc(a1, w2), t3 = cmulc(a3, w2);
+      double2 b0 = cadd(a0, t1), b1 = csub(a0, t1), b2 = cadd(a2, t3), b3 = csub(a2, t3);
+      double2 u2 = cmulc(b2, w1), u3 = mul_pi(cmulc(b3, w1));
+      a[base] = cadd(b0, u2);
+      a[base + 2 * s] = csub(b0, u2);
+      a[base + s] = cadd(b1, u3);
+      a[base + 3 * s] = csub(b1, u3);
+    }
+    __syncthreads();
+  }
+  if (logM & 1) {
+    const int span = M >> 1;
+    const int sh = logTW - logM;
+    for (int idx = threadIdx.x; idx < span; idx += blockDim.x) {
+      double2 u = a[idx];
+      double2 v = cmulc(a[idx + span], __ldg(&tw[(size_t)idx << sh]));
+      a[idx] = cadd(u, v);
+      a[idx + span] = csub(u, v);
+    }
+    __syncthreads();
+  }
+}
+
+// block-wide sum of NV doubles per thread; result valid in every thread (red: shared scratch of NV*32 doubles)
+template <int NV>
+__device__ void cta_sum(double (&v)[NV], double *red)
+{
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    for (int o = 16; o; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[i * 32 + w] = v[i];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double t = 0.0;
+    for (int k = 0; k < nw; ++k) t += red[i * 32 + k];
+    v[i] = t;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int bitrev(int v, int bits) { return bits ? (int)(__brev((unsigned)v) >> (32 - bits)) : 0; }
+
+// Forward DFT of length r held in a[0..r) (natural order).  Bluestein path: caller has ALREADY multiplied by the
+// chirp and zero-filled a[r..M).  On return element k of the spectrum is dft_get(a, k, ...).
+__device__ void cta_dft_r(double2 *a, int r, int logM, int bluestein, const double2 *__restrict__ chirp,
+                          const double2 *__restrict__ bhat, const double2 *__restrict__ tw, int logTW)
+{
+  cta_fft_dif(a, logM, tw, logTW);
+  if (!bluestein) return;
+  const int M = 1 << logM;
+  for (int k = threadIdx.x; k < M; k += blockDim.x) a[k] = cmul(a[k], __ldg(&bhat[k]));
+  __syncthreads();
+  cta_fft_dit_inv(a, logM, tw, logTW);
+  for (int k = threadIdx.x; k < r; k += blockDim.x) a[k] = cmul(a[k], __ldg(&chirp[k]));
+  __syncthreads();
+}
+__device__ __forceinline__ double2 dft_get(const double2 *a, int k, int logM, int bluestein)
+{
+  return bluestein ? a[k] : a[bitrev(k, logM)];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// plan-time: Bluestein chirp spectra
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void bluestein_table_kernel(const int *__restrict__ rlist, const long *__restrict__ chirp_off,
+                                       const long *__restrict__ bhat_off, double2 *__restrict__ chirp_all,
+                                       double2 *__restrict__ bhat_all, const double2 *__restrict__ tw, int logTW)
+{
+  extern __shared__ double2 smem[];
+  const int r = rlist[blockIdx.x];
+  int logM = 0;
+  while ((1 << logM) < 2 * r - 1) ++logM;
+  const int M = 1 << logM;
+  double2 *chirp = chirp_all + chirp_off[r];
+  double2 *bhat = bhat_all + bhat_off[r];
+  for (int k = threadIdx.x; k < M; k += blockDim.x) smem[k] = make_double2(0.0, 0.0);
+  __syncthreads();
+  for (int j = threadIdx.x; j < r; j += blockDim.x) {
+    long j2 = ((long)j * j) % (2L * r);
+    double2 w = unit_pi(-j2, r);       // exp(-i pi j^2 / r)
+    chirp[j] = w;
+    double2 c = cconj(w);
+    smem[j] = c;
+    if (j) smem[M - j] = c;
+  }
+  __syncthreads();
+  cta_fft_dif(smem, logM, tw, logTW);
+  const double inv = 1.0 / (double)M;   // fold the inverse-FFT normalisation into the table (exact power of two)
+  for (int k = threadIdx.x; k < M; k += blockDim.x) bhat[k] = make_double2(smem[k].x * inv, smem[k].y * inv);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// analysis kernel: one CTA per (ring pair in class, hemisphere)
+// ---------------------------------------------------------------------------------------------------------------
+struct RingGeomDev {
+  const double *cth, *sth, *weight;
+  const int *nphi, *shifted;
+  const long *startN, *startS;
+};
+
+__global__ void ring_analysis_kernel(const float *__restrict__ map, double2 *__restrict__ g_send, RingGeomDev geo,
+                                     const int *__restrict__ class_rp, const int *__restrict__ rp_to_local,
+                                     const long *__restrict__ m_goff, int lmax, int logM, int bluestein,
+                                     const long *__restrict__ chirp_off, const long *__restrict__ bhat_off,
+                                     const double2 *__restrict__ chirp_all, const double2 *__restrict__ bhat_all,
+                                     const double2 *__restrict__ tw, int logTW)
+{
+  extern __shared__ double2 smem[];
+  const int rp = class_rp[blockIdx.x >> 1];
+  const int hemi = blockIdx.x & 1;
+  const int n = geo.nphi[rp];
+  const int r = n >> 2;
+  const int M = 1 << logM;
+  const long start = hemi ? geo.startS[rp] : geo.startN[rp];
+  const int slot = 2 * rp_to_local[rp] + hemi;
+  if (start < 0) {   // equator has no southern partner: its slot carries zeros
+    for (int m = threadIdx.x; m <= lmax; m += blockDim.x) g_send[m_goff[m] + slot] = make_double2(0.0, 0.0);
+    return;
+  }
+  double2 *bufA = smem;          // [M]
+  double2 *bufB = smem + M;      // [r]  first spectrum, natural order
+  const double w = geo.weight[rp];
+  const double2 *chirp = bluestein ? chirp_all + chirp_off[r] : nullptr;
+  const double2 *bhat = bluestein ? bhat_all + bhat_off[r] : nullptr;
+  const float4 *ring4 = reinterpret_cast<const float4 *>(map + start);   // start is a multiple of 4 for every ring
+
+  // Bins whose twiddles are rational (k = 0, n/4, n/2; real parts of n/6, n/3) are exact sums of floats and sit on
+  // float rounding ties with probability ~1/n, where FFT round-off would flip a coin.  They are formed from the
+  // exact class sums T[c] = sum_{j = c mod 12} x_j instead (the oracle's exactly-rounded FFT does the same).
+  __shared__ double s_red[12 * 32];
+  double T[12];
+  {
+    double t3[3][4];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) t3[a][q] = 0.0;
+    for (int j = threadIdx.x; j < r; j += blockDim.x) {
+      float4 x = __ldg(&ring4[j]);
+      const double xw[4] = {(double)__double2float_rn(__dmul_rn((double)x.x, w)), (double)__double2float_rn(__dmul_rn((double)x.y, w)),
+                            (double)__double2float_rn(__dmul_rn((double)x.z, w)), (double)__double2float_rn(__dmul_rn((double)x.w, w))};
+      const int a = j % 3;   // pixel 4j+q is in class (4j+q) mod 12 = 4*(j mod 3) + q
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (a == 0) t3[0][q] += xw[q];
+        else if (a == 1) t3[1][q] += xw[q];
+        else t3[2][q] += xw[q];
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) T[4 * a + q] = t3[a][q];
+    cta_sum<12>(T, s_red);
+  }
+
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+      double2 z = make_double2(0.0, 0.0);
+      if (j < r) {
+        float4 x = __ldg(&ring4[j]);
+        // map = (float)(map * w_r)                                  [map2alm_transpose_mpi.c:161-162]
+        float xa = __double2float_rn(__dmul_rn((double)(pass ? x.z : x.x), w));
+        float xb = __double2float_rn(__dmul_rn((double)(pass ? x.w : x.y), w));
+        z = make_double2((double)xa, (double)xb);
+        if (bluestein) z = cmul(z, __ldg(&chirp[j]));
+      }
+      bufA[j] = z;
+    }
+    __syncthreads();
+    cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW);
+    if (pass == 0) {
+      for (int k = threadIdx.x; k < r; k += blockDim.x) bufB[k] = dft_get(bufA, k, logM, bluestein);
+      __syncthreads();
+    }
+  }
+  // bufB = Z1 (natural), bufA = Z2 (natural or bit-reversed).  F_k = X0 + W X1 + W^2 X2 + W^3 X3, W = exp(-2 pi i k/n)
+  const int shifted = geo.shifted[rp];
+  for (int m = threadIdx.x; m <= lmax; m += blockDim.x) {
+    int mind = m % n;                                               // [map2alm_transpose_mpi.c:237-252]
+    bool conj_it = false;
+    if (mind > n / 2) { mind = n - mind; conj_it = true; }
+    const int kk = mind % r;
+    const int kc = (r - kk) % r;
+    double2 z1 = bufB[kk], z1c = cconj(bufB[kc]);
+    double2 z2 = dft_get(bufA, kk, logM, bluestein), z2c = cconj(dft_get(bufA, kc, logM, bluestein));
+    double2 X0 = make_double2(0.5 * (z1.x + z1c.x), 0.5 * (z1.y + z1c.y));
+    double2 d1 = csub(z1, z1c);
+    double2 X1 = make_double2(0.5 * d1.y, -0.5 * d1.x);              // -i/2 * (Z - conj Z')
+    double2 X2 = make_double2(0.5 * (z2.x + z2c.x), 0.5 * (z2.y + z2c.y));
+    double2 d2 = csub(z2, z2c);
+    double2 X3 = make_double2(0.5 * d2.y, -0.5 * d2.x);
+    double2 W1 = unit_pi(-2L * mind, n);
+    double2 W2 = cmul(W1, W1);
+    double2 W3 = cmul(W1, W2);
+    double2 F = cadd(cadd(X0, cmul(W1, X1)), cadd(cmul(W2, X2), cmul(W3, X3)));
+    if (mind == 0) {
+      F.x = ((T[0] + T[1]) + (T[2] + T[3])) + ((T[4] + T[5]) + (T[6] + T[7])) + ((T[8] + T[9]) + (T[10] + T[11]));
+      F.y = 0.0;
+    } else if (2 * mind == n) {
+      F.x = ((T[0] + T[2]) + (T[4] + T[6]) + (T[8] + T[10])) - ((T[1] + T[3]) + (T[5] + T[7]) + (T[9] + T[11]));
+      F.y = 0.0;
+    } else if (4 * mind == n) {
+      F.x = (T[0] + T[4] + T[8]) - (T[2] + T[6] + T[10]);
+      F.y = (T[3] + T[7] + T[11]) - (T[1] + T[5] + T[9]);
+    } else if (6 * mind == n) {      // cos(pi j/3) = 1, 1/2, -1/2, -1, -1/2, 1/2
+      F.x = ((T[0] + T[6]) - (T[3] + T[9])) + 0.5 * (((T[1] + T[7]) + (T[5] + T[11])) - ((T[2] + T[8]) + (T[4] + T[10])));
+    } else if (3 * mind == n) {      // cos(2 pi j/3) = 1, -1/2, -1/2
+      F.x = ((T[0] + T[3]) + (T[6] + T[9])) - 0.5 * (((T[1] + T[4]) + (T[7] + T[10])) + ((T[2] + T[5]) + (T[8] + T[11])));
+    }
+    // the reference keeps the spectrum as float                     [healpix_shtrans.c:549-571]
+    double gr = (double)__double2float_rn(F.x);
+    double gi = (double)__double2float_rn(F.y);
+    if (conj_it) gi = -gi;
+    if (shifted) {                                                  // [map2alm_transpose_mpi.c:255-271]
+      double ang = __ddiv_rn(__dmul_rn((double)m, CLB_PI), (double)n);
+      double p0 = cos(ang), p1 = -sin(ang);
+      double t0 = __dsub_rn(__dmul_rn(gr, p0), __dmul_rn(gi, p1));
+      double t1 = __dadd_rn(__dmul_rn(gr, p1), __dmul_rn(gi, p0));
+      gr = t0; gi = t1;
+    }
+    g_send[m_goff[m] + slot] = make_double2(gr, gi);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// synthesis kernel: one CTA per (ring pair in class, hemisphere, field)
+// ---------------------------------------------------------------------------------------------------------------
+// float half-complex bin k of one ring, accumulated exactly like the reference's unpack loop
+// (ascending m; positive-m contribution before the negative-m one; one float rounding per contribution).
+__device__ __forceinline__ float2 fold_bin(const double2 *__restrict__ b_recv, const long *__restrict__ m_boff,
+                                           long fslot, int k, int n, int lmax, int shifted)
+{
+  float re = 0.f, im = 0.f;
+  auto add_pos = [&](long m, long j) {                              // [alm2allmaps_transpose_mpi.c:836-854]
+    double2 b = __ldg(&b_recv[m_boff[m] + fslot]);
+    double sk = (shifted && (j & 1)) ? -1.0 : 1.0;                  // l = (m - mp)/n = j
+    re = __double2float_rn(__dadd_rn((double)re, __dmul_rn(b.x, sk)));
+    im = __double2float_rn(__dadd_rn((double)im, __dmul_rn(b.y, sk)));
+  };
+  auto add_neg = [&](long m, long j) {                              // [alm2allmaps_transpose_mpi.c:857-881]
+    double2 b = __ldg(&b_recv[m_boff[m] + fslot]);
+    double sk = (shifted && ((j + 1) & 1)) ? -1.0 : 1.0;            // l = (-m - mp)/n = -(j+1)
+    re = __double2float_rn(__dadd_rn((double)re, __dmul_rn(b.x, sk)));
+    im = __double2float_rn(__dsub_rn((double)im, __dmul_rn(b.y, sk)));
+  };
+  if (k == 0) {
+    add_pos(0, 0);
+    for (long j = 1; j * n <= lmax; ++j) { add_pos(j * n, j); add_neg(j * n, j - 1); }
+  } else {
+    for (long j = 0;; ++j) {
+      long mp = k + j * n, mn = (j + 1) * n - k;
+      if (mp > lmax) break;
+      add_pos(mp, j);
+      if (mn > lmax) break;
+      add_neg(mn, j);
+    }
+  }
+  return make_float2(re, im);
+}
+
+struct MapPtrs { float *p[6]; };
+
+// Shared memory: bufA[M] | bufB[r+1] | tail.  tail = float2 park[r] (Bluestein) or float2 Y[2r+1] (power of two,
+// reused as park).  On the Bluestein path the bins Y overlay bufA[M/2..M), which is unused until the zero fill.
+__global__ void ring_synthesis_kernel(const double2 *__restrict__ b_recv, MapPtrs maps, RingGeomDev geo,
+                                      const int *__restrict__ class_rp, const int *__restrict__ rp_to_local,
+                                      const long *__restrict__ m_boff, int nslot_loc, int lmax, int logM, int bluestein,
+                                      int rmax, const long *__restrict__ chirp_off, const long *__restrict__ bhat_off,
+                                      const double2 *__restrict__ chirp_all, const double2 *__restrict__ bhat_all,
+                                      const double2 *__restrict__ tw, int logTW)
+{
+  extern __shared__ double2 smem[];
+  const int field = blockIdx.y;
+  const int rp = class_rp[blockIdx.x >> 1];
+  const int hemi = blockIdx.x & 1;
+  const long start = hemi ? geo.startS[rp] : geo.startN[rp];
+  if (start < 0) return;
+  const int n = geo.nphi[rp];
+  const int r = n >> 2;
+  const int M = 1 << logM;
+  const int shifted = geo.shifted[rp];
+  const long fslot = (long)field * nslot_loc + 2 * rp_to_local[rp] + hemi;
+  double2 *bufA = smem;
+  double2 *bufB = smem + M;
+  float2 *tailbuf = reinterpret_cast<float2 *>(smem + M + rmax + 1);
+  float2 *Y = bluestein ? reinterpret_cast<float2 *>(smem + (M >> 1)) : tailbuf;
+  float2 *park = tailbuf;
+  const double2 *chirp = bluestein ? chirp_all + chirp_off[r] : nullptr;
+  const double2 *bhat = bluestein ? bhat_all + bhat_off[r] : nullptr;
+
+  // S1: folded, phased float bins
+  for (int k = threadIdx.x; k <= 2 * r; k += blockDim.x) {
+    float2 y = fold_bin(b_recv, m_boff, fslot, k, n, lmax, shifted);
+    if (shifted) {                                                  // [healpix_shtrans.c:186-197]
+      double ang = __ddiv_rn(__dmul_rn((double)k, CLB_PI), (double)n);
+      double c = cos(ang), s = sin(ang);
+      double t0 = (double)y.x, t1 = (double)y.y;
+      y.x = __double2float_rn(__dsub_rn(__dmul_rn(t0, c), __dmul_rn(t1, s)));
+      y.y = __double2float_rn(__dadd_rn(__dmul_rn(t1, c), __dmul_rn(t0, s)));
+    }
+    Y[k] = y;
+  }
+  __syncthreads();
+  // c2r samples 0, n/4, n/2, 3n/4 have rational twiddles: exact sums of the float bins (same reason and same
+  // formulas as in the oracle's exactly-rounded FFT)
+  __shared__ double s_red[8 * 32];
+  __shared__ float s_special[4];
+  {
+    double cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // R[k&3], I[k&3] over 0 < k < n/2
+    for (int k = 1 + threadIdx.x; k < 2 * r; k += blockDim.x) {
+      const float2 f = Y[k];
+      const int c4 = k & 3;
+      if (c4 == 0) { cs[0] += (double)f.x; cs[4] += (double)f.y; }
+      else if (c4 == 1) { cs[1] += (double)f.x; cs[5] += (double)f.y; }
+      else if (c4 == 2) { cs[2] += (double)f.x; cs[6] += (double)f.y; }
+      else { cs[3] += (double)f.x; cs[7] += (double)f.y; }
+    }
+    cta_sum<8>(cs, s_red);
+    if (threadIdx.x == 0) {
+      const double y0 = (double)Y[0].x, yh = (double)Y[2 * r].x, sr = (r & 1) ? -1.0 : 1.0;
+      s_special[0] = __double2float_rn(y0 + yh + 2.0 * ((cs[0] + cs[1]) + (cs[2] + cs[3])));
+      s_special[1] = __double2float_rn(y0 + sr * yh + 2.0 * ((cs[0] - cs[2]) - (cs[5] - cs[7])));
+      s_special[2] = __double2float_rn(y0 + yh + 2.0 * ((cs[0] + cs[2]) - (cs[1] + cs[3])));
+      s_special[3] = __double2float_rn(y0 + sr * yh + 2.0 * ((cs[0] - cs[2]) + (cs[5] - cs[7])));
+    }
+    __syncthreads();
+  }
+  // S2: x_{4j+q} = IDFT_r(U^(q))_j with U^(q)_{k'} = E^q sum_p i^{qp} Yfull_{k'+p r}, E = exp(2 pi i k'/n).
+  // Two real outputs per complex transform: V1 = U0 + i U1, V2 = U2 + i U3; IDFT(V) = conj(DFT(conj V)).
+  for (int k0 = threadIdx.x; k0 < r; k0 += blockDim.x) {
+    double2 y[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int k = k0 + p * r;
+      float2 f = (k <= 2 * r) ? Y[k] : Y[n - k];
+      y[p] = make_double2((double)f.x, (k <= 2 * r) ? (double)f.y : -(double)f.y);
+      if (k == 0 || k == 2 * r) y[p].y = 0.0;   // c2r ignores the imaginary parts of the DC and Nyquist bins
+    }
+    double2 s02 = cadd(y[0], y[2]), d02 = csub(y[0], y[2]), s13 = cadd(y[1], y[3]), d13 = csub(y[1], y[3]);
+    double2 T0 = cadd(s02, s13), T2 = csub(s02, s13);
+    double2 T1 = cadd(d02, mul_pi(d13)), T3 = csub(d02, mul_pi(d13));
+    double2 E1 = unit_pi(2L * k0, n), E2 = cmul(E1, E1), E3 = cmul(E1, E2);
+    double2 U1 = cmul(T1, E1), U2 = cmul(T2, E2), U3 = cmul(T3, E3);
+    double2 v1 = cconj(cadd(T0, mul_pi(U1)));
+    double2 v2 = cconj(cadd(U2, mul_pi(U3)));
+    bufB[k0] = v2;
+    bufA[k0] = bluestein ? cmul(v1, __ldg(&chirp[k0])) : v1;
+  }
+  __syncthreads();
+  for (int k = r + threadIdx.x; k < M; k += blockDim.x) bufA[k] = make_double2(0.0, 0.0);
+  __syncthreads();
+  cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW);
+  // S5: x^(0)_j = Re(res_j), x^(1)_j = -Im(res_j), rounded to float like the reference's c2r output
+  for (int j = threadIdx.x; j < r; j += blockDim.x) {
+    double2 res = dft_get(bufA, j, logM, bluestein);
+    park[j] = make_float2(__double2float_rn(res.x), __double2float_rn(-res.y));
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    double2 z = make_double2(0.0, 0.0);
+    if (j < r) { z = bufB[j]; if (bluestein) z = cmul(z, __ldg(&chirp[j])); }
+    bufA[j] = z;
+  }
+  __syncthreads();
+  cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW);
+  // S7: float4 of four consecutive pixels, 1/sin(theta) scalings        [alm2allmaps_transpose_mpi.c:1045-1051]
+  const double sth = geo.sth[rp];
+  float4 *out = reinterpret_cast<float4 *>(maps.p[field] + start);
+  for (int j = threadIdx.x; j < r; j += blockDim.x) {
+    double2 res = dft_get(bufA, j, logM, bluestein);
+    float2 a = park[j];
+    float v[4] = {a.x, a.y, __double2float_rn(res.x), __double2float_rn(-res.y)};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int pidx = 4 * j + q;   // pixel index within the ring
+      if (pidx == 0) v[q] = s_special[0];
+      else if (pidx == r) v[q] = s_special[1];
+      else if (pidx == 2 * r) v[q] = s_special[2];
+      else if (pidx == 3 * r) v[q] = s_special[3];
+    }
+    if (field == 2 || field == 4 || field == 5) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = __double2float_rn(__ddiv_rn((double)v[q], sth));
+    }
+    if (field == 5) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = __double2float_rn(__ddiv_rn((double)v[q], sth));
+    }
+    out[j] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// cot(theta) cross terms, one CTA per (local ring pair, hemisphere)    [alm2allmaps_transpose_mpi.c:1097-1147]
+__global__ void ring_cot_terms_kernel(MapPtrs maps, RingGeomDev geo, const int *__restrict__ rp_loc)
+{
+  const int rp = rp_loc[blockIdx.x >> 1];
+  const int hemi = blockIdx.x & 1;
+  const long start = hemi ? geo.startS[rp] : geo.startN[rp];
+  if (start < 0) return;
+  const int n = geo.nphi[rp];
+  const double cot = __ddiv_rn(geo.cth[rp], geo.sth[rp]);   // the north ring's cos(theta); signs flip in the south
+  const float *mvt = maps.p[1] + start, *mvp = maps.p[2] + start;
+  float *mvtp = maps.p[4] + start, *mvpp = maps.p[5] + start;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double a = __dmul_rn(cot, (double)mvp[i]), b = __dmul_rn(cot, (double)mvt[i]);
+    if (!hemi) {
+      mvtp[i] = __double2float_rn(__dsub_rn((double)mvtp[i], a));
+      mvpp[i] = __double2float_rn(__dadd_rn((double)mvpp[i], b));
+    } else {
+      mvtp[i] = __double2float_rn(__dadd_rn((double)mvtp[i], a));
+      mvpp[i] = __double2float_rn(__dsub_rn((double)mvpp[i], b));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static int ilog2_ceil(long v) { int l = 0; while ((1L << l) < v) ++l; return l; }
+
+static RingGeomDev geom_of(const ShtPlan *p)
+{
+  RingGeomDev g;
+  g.cth = p->d_cth; g.sth = p->d_sth; g.weight = p->d_weight; g.nphi = p->d_nphi; g.shifted = p->d_shifted;
+  g.startN = p->d_startN; g.startS = p->d_startS;
+  return g;
+}
+
+void fft_tables_destroy(ShtPlan *p)
+{
+  FftTables *t = p->fft;
+  if (!t) return;
+  for (auto &c : t->classes) cudaFree(c.d_rp);
+  cudaFree(t->d_tw); cudaFree(t->d_chirp_off); cudaFree(t->d_bhat_off); cudaFree(t->d_chirp); cudaFree(t->d_bhat);
+  delete t;
+  p->fft = nullptr;
+}
+
+void fft_tables_create(ShtPlan *p)
+{
+  FftTables *t = new FftTables();
+  p->fft = t;
+  const long nside = p->nside;
+  // classes over the local ring pairs
+  struct Key { int logM, blu; };
+  std::vector<std::vector<int>> members;
+  std::vector<Key> keys;
+  int maxLogM = 1;
+  std::vector<int> need_r;   // distinct non-power-of-two r among local rings
+  std::vector<char> seen(nside + 1, 0);
+  for (int i = 0; i < p->nrp_loc; ++i) {
+    int rp = p->rp_loc[i];
+    int r = p->h_nphi[rp] / 4;
+    int pow2 = (r & (r - 1)) == 0;
+    int logM = pow2 ? ilog2_ceil(r) : ilog2_ceil(2L * r - 1);
+    maxLogM = std::max(maxLogM, logM);
+    size_t k = 0;
+    for (; k < keys.size(); ++k) if (keys[k].logM == logM && keys[k].blu == !pow2) break;
+    if (k == keys.size()) { keys.push_back({logM, !pow2}); members.emplace_back(); }
+    members[k].push_back(rp);
+    if (!pow2 && !seen[r]) { seen[r] = 1; need_r.push_back(r); }
+  }
+  // twiddles exp(-2 pi i k / TW), k < TW/2
+  t->logTW = std::max(maxLogM, 2);
+  const long TW = 1L << t->logTW;
+  std::vector<double2> tw(TW / 2);
+  for (long k = 0; k < TW / 2; ++k) {
+    // octant reduction keeps the argument of sin/cos in [0, pi/4]
+    long q = (8 * k) / TW, r8 = 8 * k - q * TW;
+    double a = (CLB_PI / 4.0) * ((double)r8 / (double)TW);
+    if (q & 1) a = (CLB_PI / 4.0) - a;
+    double c = cos(a), s = sin(a), re, im;
+    switch (q) { case 0: re = c; im = s; break; case 1: re = s; im = c; break; case 2: re = -s; im = c; break;
+                 default: re = -c; im = s; break; }
+    tw[k] = make_double2(re, -im);
+  }
+  CLB_CUDA_CHECK(cudaMalloc(&t->d_tw, sizeof(double2) * tw.size()));
+  CLB_CUDA_CHECK(cudaMemcpy(t->d_tw, tw.data(), sizeof(double2) * tw.size(), cudaMemcpyHostToDevice));
+  // Bluestein tables
+  std::vector<long> coff(nside + 1, -1), boff(nside + 1, -1);
+  long ctot = 0, btot = 0;
+  for (int r : need_r) { coff[r] = ctot; ctot += r; boff[r] = btot; btot += 1L << ilog2_ceil(2L * r - 1); }
+  CLB_CUDA_CHECK(cudaMalloc(&t->d_chirp_off, sizeof(long) * (nside + 1)));
+  CLB_CUDA_CHECK(cudaMalloc(&t->d_bhat_off, sizeof(long) * (nside + 1)));
+  CLB_CUDA_CHECK(cudaMemcpy(t->d_chirp_off, coff.data(), sizeof(long) * (nside + 1), cudaMemcpyHostToDevice));
+  CLB_CUDA_CHECK(cudaMemcpy(t->d_bhat_off, boff.data(), sizeof(long) * (nside + 1), cudaMemcpyHostToDevice));
+  if (!need_r.empty()) {
+    CLB_CUDA_CHECK(cudaMalloc(&t->d_chirp, sizeof(double2) * ctot));
+    CLB_CUDA_CHECK(cudaMalloc(&t->d_bhat, sizeof(double2) * btot));
+    int *d_rlist;
+    CLB_CUDA_CHECK(cudaMalloc(&d_rlist, sizeof(int) * need_r.size()));
+    CLB_CUDA_CHECK(cudaMemcpy(d_rlist, need_r.data(), sizeof(int) * need_r.size(), cudaMemcpyHostToDevice));
+    size_t smem = sizeof(double2) << maxLogM;
+    CLB_CUDA_CHECK(cudaFuncSetAttribute(bluestein_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bluestein_table_kernel<<<(unsigned)need_r.size(), 256, smem>>>(d_rlist, t->d_chirp_off, t->d_bhat_off, t->d_chirp,
+                                                                   t->d_bhat, t->d_tw, t->logTW);
+    CLB_CUDA_CHECK(cudaGetLastError());
+    CLB_CUDA_CHECK(cudaDeviceSynchronize());
+    cudaFree(d_rlist);
+  }
+  size_t max_ana = 0, max_syn = 0;
+  for (size_t k = 0; k < keys.size(); ++k) {
+    FftClass c;
+    c.logM = keys[k].logM; c.bluestein = keys[k].blu; c.count = (int)members[k].size();
+    c.rmax = 0;
+    for (int rp : members[k]) c.rmax = std::max(c.rmax, p->h_nphi[rp] / 4);
+    const long M = 1L << c.logM;
+    c.threads = (int)std::min<long>(256, std::max<long>(32, M / 4));
+    if (M >= 4096) c.threads = 512;
+    c.smem_ana = sizeof(double2) * (M + c.rmax);
+    c.smem_syn = sizeof(double2) * (M + c.rmax + 1) + sizeof(float2) * (c.bluestein ? c.rmax : 2 * c.rmax + 1);
+    max_ana = std::max(max_ana, c.smem_ana); max_syn = std::max(max_syn, c.smem_syn);
+    CLB_CUDA_CHECK(cudaMalloc(&c.d_rp, sizeof(int) * c.count));
+    CLB_CUDA_CHECK(cudaMemcpy(c.d_rp, members[k].data(), sizeof(int) * c.count, cudaMemcpyHostToDevice));
+    t->classes.push_back(c);
+  }
+  if (max_ana > 227 * 1024 || max_syn > 227 * 1024) {
+    fprintf(stderr, "calclens_b200: ring FFT needs %zu bytes of shared memory (Nside=%ld); the single-CTA ring FFT "
+                    "supports Nside <= 4096\n", std::max(max_ana, max_syn), nside);
+    abort();
+  }
+  CLB_CUDA_CHECK(cudaFuncSetAttribute(ring_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_ana));
+  CLB_CUDA_CHECK(cudaFuncSetAttribute(ring_synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_syn));
+}
+
+// defined in sht_plan.cu
+int *plan_rp_to_local(const ShtPlan *p);
+
+int launch_ring_analysis(const ShtPlan *p, const float *d_map, double2 *d_g_send, cudaStream_t st)
+{
+  const FftTables *t = p->fft;
+  int launches = 0;
+  for (const auto &c : t->classes) {
+    ring_analysis_kernel<<<2 * c.count, c.threads, c.smem_ana, st>>>(
+        d_map, d_g_send, geom_of(p), c.d_rp, plan_rp_to_local(p), p->d_m_goff, (int)p->lmax, c.logM, c.bluestein,
+        t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat, t->d_tw, t->logTW);
+    ++launches;
+  }
+  CLB_CUDA_CHECK(cudaGetLastError());
+  return launches;
+}
+
+int launch_ring_synthesis(const ShtPlan *p, const double2 *d_b_recv, float *const d_maps[6], cudaStream_t st)
+{
+  const FftTables *t = p->fft;
+  MapPtrs mp;
+  for (int k = 0; k < 6; ++k) mp.p[k] = d_maps[k];
+  int launches = 0;
+  for (const auto &c : t->classes) {
+    dim3 grid(2 * c.count, 6);
+    ring_synthesis_kernel<<<grid, c.threads, c.smem_syn, st>>>(
+        d_b_recv, mp, geom_of(p), c.d_rp, plan_rp_to_local(p), p->d_m_boff, 2 * p->nrp_loc, (int)p->lmax, c.logM,
+        c.bluestein, c.rmax, t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat, t->d_tw, t->logTW);
+    ++launches;
+  }
+  ring_cot_terms_kernel<<<2 * p->nrp_loc, 256, 0, st>>>(mp, geom_of(p), p->d_rp_loc);
+  ++launches;
+  CLB_CUDA_CHECK(cudaGetLastError());
+  return launches;
+}
+
+}  // namespace clb

@@ -1,0 +1,105 @@
+/* include/calclens_b200.h -- C ABI of libcalclens_b200.so (sm_100a CUDA implementation of the CALCLENS SHTONLY
+ * lens-plane hot path).  Plain C types only; every entry point cites the reference interface it replaces
+ * (paths relative to the CALCLENS source tree).  There is no CPU fallback: every call needs a CUDA device and
+ * aborts with a message on any CUDA error, which is the reference's own failure mode on this path
+ * (MPI_Abort(MPI_COMM_WORLD,123), map2alm_transpose_mpi.c:129-138, shtpoissonsolve.c:683-689).
+ *
+ * Conventions
+ *   ring pair rp = 0 .. 2*Nside-1 : north ring rp+1 and its mirror 4*Nside-1-rp (the last pair is the equator).
+ *   maps      : float32, RING order, full-sky buffer of 12*Nside^2 pixels (a rank touches only its own rings).
+ *   alm       : double, m-major: for each owned m (ascending), l = m..lmax contiguous
+ *               (map2alm_transpose_mpi.c:418-425, healpix_shtrans.c:523-526 lm2index).
+ *   six fields: 0 phi, 1 d_theta, 2 d_phi/sin, 3 d_theta d_theta, 4 d_theta d_phi, 5 d_phi d_phi -- the argument
+ *               order of alm2allmaps_mpi (healpix_shtrans.h:70-72).
+ *   rays      : the reference's 176-byte HEALPixRay records (raytrace.h:284-293), unchanged.
+ *   "_dev" entry points take DEVICE pointers and a cudaStream_t (as void*); they return the number of kernels
+ *   they launched.  The other entry points take HOST pointers and do their own transfers.
+ */
+#ifndef CALCLENS_B200_H
+#define CALCLENS_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct clb_sht_plan clb_sht_plan;
+
+int clb_abi_version(void);
+/* number of CUDA devices; aborts if the CUDA runtime reports none (no CPU fallback exists) */
+int clb_device_count(void);
+void clb_set_device(int device);
+/* kernels launched by this library since load (bench.py reports it as gpu_launches) */
+long clb_launch_count(void);
+/* tuning knobs: what = 0 synthesis rings per thread (1, 2 or 4) */
+void clb_set_tuning(int what, int value);
+
+/* ---- plan: replaces healpixsht_plan / healpixsht_destroy_plan (healpix_shtrans.c:54-160, :496-516) and
+ * read_ring_weights' result (healpix_shtrans.c:361-423: ring_weights = the 2*Nside doubles of
+ * weight_ring_nNNNNN.fits, or NULL).  lmax travels in the reference plan (healpix_shtrans.h:39) and is honoured
+ * as given.  rp_owner[2*Nside] / m_owner[lmax+1] give the owning rank of every ring pair / every m (NULL = rank 0
+ * owns all); they generalise the reference's contiguous firstRingTasks/lastRingTasks and firstMTasks/lastMTasks. */
+clb_sht_plan *clb_sht_plan_create(long order, long lmax, const double *ring_weights, int nranks, int rank,
+                                  const int *rp_owner, const int *m_owner);
+void clb_sht_plan_destroy(clb_sht_plan *plan);
+/* what: 0 Npix, 1 lmax, 2 number of local alm (Nlm of healpix_shtrans.h:41), 3 local ring pairs, 4 local m,
+ * 5/6 g send/recv totals, 7/8 b send/recv totals (units of complex doubles), 9 nranks, 10 rank */
+long clb_sht_plan_query(const clb_sht_plan *plan, int what);
+/* per-peer element counts of the two transposes (complex doubles): which = 0 g_send, 1 g_recv, 2 b_send, 3 b_recv.
+ * They replace the sendcnts/recvcnts of map2alm_transpose_mpi.c:329-347 and alm2allmaps_transpose_mpi.c:656-672. */
+void clb_sht_plan_counts(const clb_sht_plan *plan, int which, long *counts);
+void clb_sht_plan_local_m(const clb_sht_plan *plan, int *m_list);
+void clb_sht_plan_local_ring_pairs(const clb_sht_plan *plan, int *rp_list);
+
+/* ---- stages of map2alm_mpi (map2alm_transpose_mpi.c:54-641) ---- */
+/* ring weights + r2c + alias/phase + pack: :151-315.  g_send: clb_sht_plan_query(5) complex doubles */
+int clb_ring_analysis_dev(const clb_sht_plan *plan, const float *map, double *g_send, void *stream);
+/* Legendre analysis :427-536, optionally fused with the Poisson filter of shtpoissonsolve.c:526-550 */
+int clb_legendre_analysis_dev(clb_sht_plan *plan, const double *g_recv, double *alm_re, double *alm_im,
+                              int apply_poisson_filter, void *stream);
+/* ---- stages of alm2allmaps_mpi (alm2allmaps_transpose_mpi.c:53-1240) ---- */
+/* Legendre synthesis of the six fields :272-595.  b_send: clb_sht_plan_query(7) complex doubles */
+int clb_legendre_synthesis_dev(clb_sht_plan *plan, const double *alm_re, const double *alm_im, double *b_send, void *stream);
+/* unpack/alias fold + phase + c2r + 1/sin scalings + cot terms :818-1147 */
+int clb_ring_synthesis_dev(const clb_sht_plan *plan, const double *b_recv, float *const maps[6], void *stream);
+
+/* ---- density scaling of shtpoissonsolve.c:426,454-502 (full-sky: no vacuum cells):
+ * map = (map * premul) * densmul - backdens, all in float like the reference ---- */
+int clb_scale_density_dev(float *map, long npix, float premul, float densmul, float backdens, void *stream);
+
+/* ---- ray step.  mode bits: 1 zero phi/alpha/U (raytrace.c:213-230); 2 interpolate + accumulate
+ * (shtpoissonsolve.c:666-702 with shearinterp_comp :1122-1204); 4 propagate = rayprop_sphere(wp, wpm1, wpm2, .)
+ * (rayprop.c:18-189; argument names as in raytrace.h:431).  maps are needed only with bit 2. ---- */
+int clb_ray_step_dev(void *rays, long nrays, const float *const maps[6], long map_order, double wp, double wpm1,
+                     double wpm2, int mode, void *stream);
+
+/* ---- host-pointer entry points (single rank; transfers inside) ---- */
+/* map2alm_mpi on a RING-ordered map (healpix_shtrans.h:67) */
+void clb_map2alm(clb_sht_plan *plan, const float *ringmap, double *alm_re, double *alm_im, int apply_poisson_filter);
+/* alm2allmaps_mpi; maps = 6 consecutive RING-ordered maps (healpix_shtrans.h:70-72) */
+void clb_alm2allmaps(clb_sht_plan *plan, const double *alm_re, const double *alm_im, float *maps);
+/* The same two transforms on the reference's padded ring-pair buffers ("mapvec", healpix_shtrans.c:90-118): ring
+ * pair i starts at north_start[i] / south_start[i] (units of 8 bytes, -1 for the equator's missing mirror).  These
+ * are what a link-time replacement of map2alm_mpi / alm2allmaps_mpi forwards to. */
+void clb_map2alm_mapvec(clb_sht_plan *plan, float *mapvec, const long *north_start, const long *south_start,
+                        double *alm_re, double *alm_im);
+void clb_alm2allmaps_mapvec(clb_sht_plan *plan, const double *alm_re, const double *alm_im, float *const mapvec[6],
+                            const long *north_start, const long *south_start);
+/* rayprop_sphere over a host array of HEALPixRay (rayprop.c:18); mode as clb_ray_step_dev; maps (host, 6
+ * consecutive RING maps) may be NULL unless bit 2 is set */
+void clb_ray_step(void *rays, long nrays, const float *maps, long map_order, double wp, double wpm1, double wpm2, int mode);
+/* One lens plane end to end, the work of do_healpix_sht_poisson_solve (shtpoissonsolve.c:38-708) from the scaled
+ * map on plus the plane's rayprop_sphere calls (raytrace.c:256-269): counts map (host, RING) -> scale -> map2alm ->
+ * filter -> alm2allmaps -> zero/interpolate/propagate the rays (host array, updated in place). */
+void clb_lens_plane(clb_sht_plan *plan, const float *ringmap, float premul, float densmul, float backdens, void *rays,
+                    long nrays, double wp, double wpm1, double wpm2);
+
+/* ---- HEALPix indexing on the device, exposed for the bit-exactness tests (device pointers) ----
+ * what: 0 ring2nest, 1 nest2ring, 2 ang2nest(theta,phi), 3 nest2peano      (healpix_utils.c:420,413,548,427) */
+void clb_healpix_index_dev(int what, long order, long n, const long *in, const double *theta, const double *phi,
+                           long *out, void *stream);
+/* vec2ang + get_interpol (healpix_utils.c:120,971): vec[3n] -> pix[4n], wgt[4n] */
+void clb_healpix_interpol_dev(long order, long n, const double *vec, long *pix, double *wgt, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

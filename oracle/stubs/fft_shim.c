@@ -4,7 +4,10 @@
  * Computes", 1d real data): r2c  Y_k = sum_j X_j exp(-2 pi i j k / n), k = 0..n/2;  c2r (unnormalised inverse)
  * X_j = sum_{k=0}^{n-1} Y_k exp(+2 pi i j k / n) with Y_{n-k} = conj(Y_k), imaginary parts of Y_0 and Y_{n/2}
  * ignored.  Arithmetic: complex FP64 FFT (radix-2 for powers of two, Bluestein otherwise), result rounded to
- * float exactly once.  In-place use (in == out) is supported because input is copied before any store. */
+ * float exactly once.  In-place use (in == out) is supported because input is copied before any store.
+ * Exactly-rounded means ties must not be left to FFT round-off: the outputs whose twiddle factors are rational
+ * (r2c bins 0, n/4, n/2 and the real parts of bins n/6, n/3; c2r samples 0, n/4, n/2, 3n/4) are exact sums of floats
+ * and land on float rounding ties with probability ~1/n, so they are evaluated by exact (long double) summation. */
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
@@ -155,6 +158,29 @@ void fftwf_execute(const fftwf_plan p)
     fftwf_complex *y = (fftwf_complex*)p->out;
     for (int j = 0; j < n; ++j) { a[j].re = (double)x[j]; a[j].im = 0.0; }
     dft_forward(a, n);
+    {
+      /* exact sums for the rational-twiddle bins; T[c] = sum of x_j over j = c (mod 12) */
+      long double T[12]; for (int c = 0; c < 12; ++c) T[c] = 0.0L;
+      for (int j = 0; j < n; ++j) T[j % 12] += (long double)x[j];
+      long double s = 0; for (int c = 0; c < 12; ++c) s += T[c];
+      a[0].re = (double)s; a[0].im = 0.0;
+      if (n % 2 == 0) {
+        s = 0; for (int c = 0; c < 12; ++c) s += (c & 1) ? -T[c] : T[c];
+        a[n / 2].re = (double)s; a[n / 2].im = 0.0;
+      }
+      if (n % 4 == 0 && n >= 4) {
+        a[n / 4].re = (double)((T[0] + T[4] + T[8]) - (T[2] + T[6] + T[10]));
+        a[n / 4].im = (double)((T[3] + T[7] + T[11]) - (T[1] + T[5] + T[9]));
+      }
+      if (n % 12 == 0) {
+        static const long double c6[6] = {1.0L, 0.5L, -0.5L, -1.0L, -0.5L, 0.5L};
+        static const long double c3[3] = {1.0L, -0.5L, -0.5L};
+        s = 0; for (int c = 0; c < 12; ++c) s += c6[c % 6] * T[c];
+        a[n / 6].re = (double)s;
+        s = 0; for (int c = 0; c < 12; ++c) s += c3[c % 3] * T[c];
+        a[n / 3].re = (double)s;
+      }
+    }
     for (int k = 0; k <= n / 2; ++k) { y[k][0] = (float)a[k].re; y[k][1] = (float)a[k].im; }
   } else {
     const fftwf_complex *y = (const fftwf_complex*)p->in;
@@ -166,8 +192,18 @@ void fftwf_execute(const fftwf_plan p)
       a[k].re = re; a[k].im = -im;
       if (k != 0 && 2 * k != n) { a[n - k].re = re; a[n - k].im = im; }
     }
+    long double R[4] = {0, 0, 0, 0}, I[4] = {0, 0, 0, 0}, y0 = (long double)y[0][0], yh = (n % 2 == 0) ? (long double)y[n / 2][0] : 0.0L;
+    for (int k = 1; 2 * k < n; ++k) { R[k & 3] += (long double)y[k][0]; I[k & 3] += (long double)y[k][1]; }
     dft_forward(a, n);
     for (int j = 0; j < n; ++j) x[j] = (float)a[j].re;
+    if (n % 4 == 0 && n >= 4) {
+      /* x_j = Y_0 + (-1)^j Y_{n/2} + 2 sum_{0<k<n/2} Re(Y_k e^{2 pi i jk/n}) at j = 0, n/4, n/2, 3n/4 */
+      long double sr = ((n / 4) & 1) ? -1.0L : 1.0L;
+      x[0] = (float)(double)(y0 + yh + 2.0L * (R[0] + R[1] + R[2] + R[3]));
+      x[n / 2] = (float)(double)(y0 + yh + 2.0L * ((R[0] + R[2]) - (R[1] + R[3])));
+      x[n / 4] = (float)(double)(y0 + sr * yh + 2.0L * ((R[0] - R[2]) - (I[1] - I[3])));
+      x[3 * (n / 4)] = (float)(double)(y0 + sr * yh + 2.0L * ((R[0] - R[2]) + (I[1] - I[3])));
+    }
   }
   free(a);
 }
