@@ -15,6 +15,8 @@ int launch_legendre_analysis(ShtPlan *p, const double2 *d_g_recv, double *d_alm_
 int launch_legendre_synthesis(ShtPlan *p, const double *d_alm_re, const double *d_alm_im, double2 *d_b_send, cudaStream_t st);
 int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long order, double wp, double wpm1, double wpm2,
                     int mode, cudaStream_t st);
+int launch_ray_init(Ray *d_rays, long nrays, long first_nest, long ray_order, double binL_2, cudaStream_t st);
+int launch_ray_summary(const Ray *d_rays, long nrays, double *d_out6, cudaStream_t st);
 void launch_healpix_index(int what, long order, long n, const long *in, const double *th, const double *ph, long *out, cudaStream_t st);
 void launch_healpix_interpol(long order, long n, const double *vec, long *pix, double *wgt, cudaStream_t st);
 extern int g_syn_rings_per_thread;
@@ -155,6 +157,16 @@ int clb_ray_step_dev(void *rays, long nrays, const float *const maps[6], long ma
 {
   if ((mode & 2) && !maps) { fprintf(stderr, "calclens_b200: clb_ray_step_dev mode 2 needs maps\n"); abort(); }
   int n = launch_ray_step(reinterpret_cast<Ray *>(rays), nrays, maps, map_order, wp, wpm1, wpm2, mode, (cudaStream_t)stream);
+  g_launches += n; return n;
+}
+int clb_ray_init_dev(void *rays, long nrays, long first_nest, long ray_order, double binL_2, void *stream)
+{
+  int n = launch_ray_init(reinterpret_cast<Ray *>(rays), nrays, first_nest, ray_order, binL_2, (cudaStream_t)stream);
+  g_launches += n; return n;
+}
+int clb_ray_summary_dev(const void *rays, long nrays, double *out6, void *stream)
+{
+  int n = launch_ray_summary(reinterpret_cast<const Ray *>(rays), nrays, out6, (cudaStream_t)stream);
   g_launches += n; return n;
 }
 void clb_healpix_index_dev(int what, long order, long n, const long *in, const double *theta, const double *phi,

@@ -90,8 +90,12 @@ CLB_HD void ray_interp_accumulate(Ray &ray, long order, const float *m_phi, cons
   get_interpol(theta, phi, pix, wgt, order);
   double pot = 0.0, gtheta = 0.0, gphi = 0.0;
   double ti[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  const long npix_map = 12L << (2 * order);
   for (int k = 0; k < 4; ++k) {
     long p = pix[k];
+    // a ray with a non-finite position would index outside the maps; the reference aborts on a missing cell
+    // (shtpoissonsolve.c:683-689) -- here the gather is kept in bounds and the NaNs stay visible in the ray
+    if (!(p >= 0 && p < npix_map)) p = 0;
     double vec[3], z, ph, c, s, tvec[2], rtvec[2], T[2][2], RT[2][2];
     pot += m_phi[p] * wgt[k];
     ringpix2zphi(p, order, z, ph);

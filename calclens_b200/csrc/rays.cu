@@ -56,6 +56,59 @@ int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long 
   return 1;
 }
 
+// Ray initialisation: ray i observes from the centre of NEST pixel first_nest+i at rayOrder, sits at radius binL/2,
+// A = Aprev = identity                                                  [raytrace_utils.c:302-347 init_rays]
+__global__ void ray_init_kernel(Ray *__restrict__ rays, long nrays, long first_nest, long ray_order, double binL_2)
+{
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrays) return;
+  Ray ray;
+  ray.nest = first_nest + i;
+  nest2vec(ray.nest, ray_order, ray.beta);
+  ray.n[0] = ray.beta[0] * binL_2; ray.n[1] = ray.beta[1] * binL_2; ray.n[2] = ray.beta[2] * binL_2;
+  ray.A[0] = 1.0; ray.A[1] = 0.0; ray.A[2] = 0.0; ray.A[3] = 1.0;
+  ray.Aprev[0] = 1.0; ray.Aprev[1] = 0.0; ray.Aprev[2] = 0.0; ray.Aprev[3] = 1.0;
+  ray.phi = 0.0; ray.alpha[0] = 0.0; ray.alpha[1] = 0.0;
+  ray.U[0] = 0.0; ray.U[1] = 0.0; ray.U[2] = 0.0; ray.U[3] = 0.0;
+  rays[i] = ray;
+}
+int launch_ray_init(Ray *d_rays, long nrays, long first_nest, long ray_order, double binL_2, cudaStream_t st)
+{
+  if (nrays <= 0) return 0;
+  ray_init_kernel<<<(unsigned)((nrays + 255) / 256), 256, 0, st>>>(d_rays, nrays, first_nest, ray_order, binL_2);
+  CLB_CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+// Per-step scalar summary read back by the host each plane: sums over rays of
+// kappa = 1 - (A00+A11)/2, gamma1 = (A11-A00)/2, gamma2 = -(A01+A10)/2, |alpha|^2, phi, omega = (A10-A01)/2
+__global__ void ray_summary_kernel(const Ray *__restrict__ rays, long nrays, double *__restrict__ out)
+{
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nrays; i += (long)gridDim.x * blockDim.x) {
+    const Ray &r = rays[i];
+    s[0] += 1.0 - 0.5 * (r.A[0] + r.A[3]);
+    s[1] += 0.5 * (r.A[3] - r.A[0]);
+    s[2] += -0.5 * (r.A[1] + r.A[2]);
+    s[3] += r.alpha[0] * r.alpha[0] + r.alpha[1] * r.alpha[1];
+    s[4] += r.phi;
+    s[5] += 0.5 * (r.A[2] - r.A[1]);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    for (int o = 16; o; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&out[k], s[k]);
+  }
+}
+int launch_ray_summary(const Ray *d_rays, long nrays, double *d_out6, cudaStream_t st)
+{
+  CLB_CUDA_CHECK(cudaMemsetAsync(d_out6, 0, 6 * sizeof(double), st));
+  if (nrays <= 0) return 0;
+  ray_summary_kernel<<<148 * 4, 256, 0, st>>>(d_rays, nrays, d_out6);
+  CLB_CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
 // ---- small utility kernels used by tests: device versions of the indexing functions ----
 __global__ void healpix_index_kernel(int what, long order, long n, const long *__restrict__ in, const double *__restrict__ th,
                                      const double *__restrict__ ph, long *__restrict__ out)

@@ -1,0 +1,66 @@
+"""Exchange layouts of the two SHT transposes, host-side and CUDA-free.
+
+The map side is sharded by ring pairs, the alm side by m.  Between the ring FFTs and the
+Legendre stage the ranks exchange, per direction, one block per peer -- the counterpart of the sendcnts/recvcnts of
+map2alm_transpose_mpi.c:329-347 (analysis: my rings x the peer's m) and alm2allmaps_transpose_mpi.c:656-672
+(synthesis: my m x 6 fields x the peer's rings).  The C library computes the same tables for its kernels
+(csrc/sht_plan.cu); tests check the two against each other, and the gloo tests run the exchange on CPU ranks.
+All counts and offsets are in units of one complex double.
+"""
+import numpy as np
+
+
+class ExchangeLayout:
+    def __init__(self, nside, lmax, nranks, rank, rp_owner, m_owner):
+        self.nside, self.lmax, self.nranks, self.rank = nside, lmax, nranks, rank
+        nrp = 2 * nside
+        self.rp_owner = np.asarray(rp_owner, dtype=np.int64)
+        self.m_owner = np.asarray(m_owner, dtype=np.int64)
+        assert self.rp_owner.size == nrp and self.m_owner.size == lmax + 1
+        self.nrp_of = np.bincount(self.rp_owner, minlength=nranks)
+        self.nm_of = np.bincount(self.m_owner, minlength=nranks)
+        # index of every ring pair / m inside its owner's ascending list
+        self.rp_local = np.zeros(nrp, dtype=np.int64)
+        self.m_local = np.zeros(lmax + 1, dtype=np.int64)
+        for q in range(nranks):
+            sel = np.nonzero(self.rp_owner == q)[0]; self.rp_local[sel] = np.arange(sel.size)
+            sel = np.nonzero(self.m_owner == q)[0]; self.m_local[sel] = np.arange(sel.size)
+        self.my_rp = np.nonzero(self.rp_owner == rank)[0]
+        self.my_m = np.nonzero(self.m_owner == rank)[0]
+        nslot_mine = 2 * self.my_rp.size
+        nm_mine = self.my_m.size
+        self.nslot_mine = nslot_mine
+        self.g_send_counts = [int(self.nm_of[q]) * nslot_mine for q in range(nranks)]
+        self.g_recv_counts = [nm_mine * 2 * int(self.nrp_of[q]) for q in range(nranks)]
+        self.b_send_counts = [nm_mine * 6 * 2 * int(self.nrp_of[q]) for q in range(nranks)]
+        self.b_recv_counts = [int(self.nm_of[q]) * 6 * nslot_mine for q in range(nranks)]
+        self.g_sbase = np.concatenate([[0], np.cumsum(self.g_send_counts)])
+        self.g_rbase = np.concatenate([[0], np.cumsum(self.g_recv_counts)])
+        self.b_sbase = np.concatenate([[0], np.cumsum(self.b_send_counts)])
+        self.b_rbase = np.concatenate([[0], np.cumsum(self.b_recv_counts)])
+
+    # analysis transpose --------------------------------------------------------------------------------------
+    def g_send_index(self, m, rp, hemi):
+        """where the FFT stage of the owner of ring pair rp (this rank) puts g_m of (rp, hemi)"""
+        q = self.m_owner[m]
+        return int(self.g_sbase[q] + self.m_local[m] * self.nslot_mine + 2 * self.rp_local[rp] + hemi)
+
+    def g_recv_index(self, m, rp, hemi):
+        """where the Legendre stage of the owner of m (this rank) finds g_m of (rp, hemi)"""
+        q = self.rp_owner[rp]
+        return int(self.g_rbase[q] + self.m_local[m] * 2 * self.nrp_of[q] + 2 * self.rp_local[rp] + hemi)
+
+    # synthesis transpose -------------------------------------------------------------------------------------
+    def b_send_index(self, m, field, rp, hemi):
+        q = self.rp_owner[rp]
+        return int(self.b_sbase[q] + (self.m_local[m] * 6 + field) * 2 * self.nrp_of[q] + 2 * self.rp_local[rp] + hemi)
+
+    def b_recv_index(self, m, field, rp, hemi):
+        q = self.m_owner[m]
+        return int(self.b_rbase[q] + (self.m_local[m] * 6 + field) * self.nslot_mine + 2 * self.rp_local[rp] + hemi)
+
+
+def ray_ranges(ray_order, nranks):
+    """Contiguous NEST ranges of rays per rank = compact sky domains (cf. loadbalance.c:151-181 equal-area split)."""
+    n = 12 << (2 * ray_order)
+    return [((n * r) // nranks, (n * (r + 1)) // nranks) for r in range(nranks)]

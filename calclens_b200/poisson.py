@@ -1,0 +1,177 @@
+"""Per-plane driver: the work of ``do_healpix_sht_poisson_solve`` (shtpoissonsolve.c:38-708, map-input path) followed by
+the plane's ``rayprop_sphere`` calls (raytrace.c:256-269), on one GPU or sharded over the ranks of a
+``torch.distributed`` process group (one process per GPU).
+
+Sharding follows the reference: the map side of the SHT is split by ring pairs, the alm side
+by m, joined by one transpose per direction (the MPI hypercube exchange of map2alm_transpose_mpi.c:339-381 and
+alm2allmaps_transpose_mpi.c:656-724 becomes one NCCL all-to-all-v over NVLink); rays are split into contiguous NEST
+ranges, i.e. compact sky domains (cf. loadbalance.c:151-181).  Instead of the reference's ring->domain shuffle with
+halo cells (map_shuffle.c) every rank receives the six full derivative maps (an all-reduce of disjoint ring sets), so
+rays never miss a map cell however far they have been deflected.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, sht
+from .rays import MODE_INTERP, MODE_PROP, MODE_ZERO
+
+CSOL = 299792.458          # raytrace.h:110
+RHO_CRIT = 2.77519737e11   # raytrace.h:109
+MASS_SCALE = 1e10          # the reference's internal mass unit (shtpoissonsolve.c:426,468)
+
+
+class Cosmology:
+    """a(w) for flat LCDM exactly as the reference tabulates it (cosmocalc.c:14-92): 20000-point table of
+    w(a) = 2997.92458 * int_a^1 da'/sqrt(a' Om + a'^4 (1-Om)), linear interpolation."""
+
+    N, AMIN, AMAX = 20000, 0.01, 1.0
+
+    def __init__(self, omega_m):
+        self.omega_m = float(omega_m)
+        i = np.arange(self.N - 1, dtype=np.float64)
+        a = (self.AMAX - self.AMIN) / (self.N - 1.0) * i + self.AMIN
+        x, w = np.polynomial.legendre.leggauss(96)
+        # Gauss-Legendre on [a, 1] (the integrand is smooth for a >= 0.01); the reference uses gsl_integration_qag
+        # with relerr 1e-8 (cosmocalc.c:42)
+        half = 0.5 * (1.0 - a)[:, None]
+        mid = 0.5 * (1.0 + a)[:, None]
+        t = mid + half * x[None, :]
+        f = 1.0 / np.sqrt(t * self.omega_m + t ** 4 * (1.0 - self.omega_m))
+        self.aexpn = np.concatenate([a, [1.0]])
+        self.comv = np.concatenate([(half[:, 0] * (f * w[None, :]).sum(axis=1)) * 2997.92458, [0.0]])
+
+    def acomvdist(self, dist):
+        """cosmocalc.c:57-92"""
+        c = self.comv
+        if dist < c[-1]:
+            return self.AMAX
+        if dist > c[0]:
+            return self.AMIN
+        # the reference's loop (cosmocalc.c:80-84) leaves i at the largest index with comv[i] > dist
+        idx = np.nonzero(c > dist)[0]
+        i = int(idx[-1]) if idx.size else 0
+        i = max(i, 1)
+        w = (dist - c[i - 1]) / (c[i] - c[i - 1])
+        return (1.0 - w) * self.aexpn[i - 1] + w * self.aexpn[i]
+
+
+def plane_params(plane, num_planes, max_comv_distance, omega_m, cosmo=None, pointmass=False, nobackdens=False):
+    """set_plane_params (raytrace.c:384-423): returns dict(wpm1, wp, wpp1, densfact, backdens, z).
+    Note the reference's naming at the call site raytrace.c:262: rayprop_sphere(planeRadPlus1, planeRad, planeRadMinus1)."""
+    cosmo = cosmo or Cosmology(omega_m)
+    binL = max_comv_distance / float(num_planes)
+    wm1 = 0.0 if plane - 1 < 0 else (plane - 1.0) * binL + binL / 2.0
+    w = plane * binL + binL / 2.0
+    wp1 = max_comv_distance if plane + 1 == num_planes else (plane + 1.0) * binL + binL / 2.0
+    if pointmass:
+        radialvolume = w * w * binL
+    else:
+        radialvolume = (math.pow(w + binL / 2.0, 3.0) - math.pow(w - binL / 2.0, 3.0)) / 3.0
+    zw = 1.0 / cosmo.acomvdist(w) - 1.0
+    densfact = 3.0 * 100.0 * 100.0 / CSOL / CSOL * omega_m * w * (1.0 + zw) * binL / (radialvolume * RHO_CRIT * omega_m)
+    backdens = 0.0 if nobackdens else 3.0 * 100.0 * 100.0 / CSOL / CSOL * omega_m * w * (1.0 + zw) * binL
+    return dict(wpm1=wm1, wp=w, wpp1=wp1, densfact=densfact, backdens=backdens, z=zw, binL=binL)
+
+
+def density_scalings(order, part_mass, densfact, backdens):
+    """The three float factors the reference applies to a raw count map (shtpoissonsolve.c:426,468,478)."""
+    area = 4.0 * math.pi / (12 << (2 * order))
+    return (np.float32(part_mass / MASS_SCALE), np.float32(densfact / area * MASS_SCALE), np.float32(backdens))
+
+
+class LensPlaneSolver:
+    """One rank's share of the per-plane hot path.  ``dist_group`` = None for a single GPU, otherwise an initialised
+    torch.distributed process group (NCCL) with one rank per GPU."""
+
+    def __init__(self, sht_order, lmax=None, ray_order=None, ring_weights=None, dist_group=None, device=None):
+        import torch.distributed as dist
+        self.dist = dist if dist_group is not None else None
+        self.group = dist_group
+        self.nranks = dist.get_world_size(dist_group) if dist_group is not None else 1
+        self.rank = dist.get_rank(dist_group) if dist_group is not None else 0
+        self.plan = sht.HEALPixSHTPlan(sht_order, lmax, ring_weights, self.nranks, self.rank, device=device)
+        self.device = self.plan.device
+        self.lib = self.plan.lib
+        self.order = int(sht_order)
+        self.npix = self.plan.npix
+        self.ray_order = self.order if ray_order is None else int(ray_order)
+        p = self.plan
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self.g_send = torch.empty(2 * max(p.g_send_total, 1), **f64)
+        self.b_send = torch.empty(2 * max(p.b_send_total, 1), **f64)
+        if self.nranks > 1:
+            self.g_recv = torch.empty(2 * max(p.g_recv_total, 1), **f64)
+            self.b_recv = torch.empty(2 * max(p.b_recv_total, 1), **f64)
+        else:
+            self.g_recv, self.b_recv = self.g_send, self.b_send
+        self.alm_re = torch.empty(max(p.Nlm, 1), **f64)
+        self.alm_im = torch.empty(max(p.Nlm, 1), **f64)
+        self.maps = torch.zeros((6, self.npix), dtype=torch.float32, device=self.device)
+        self.summary = torch.zeros(6, **f64)
+        self.rays = None
+        self.nrays = 0
+        self.first_nest = 0
+
+    # ---- rays ----
+    def init_rays(self, binL_2):
+        """alloc_rays + init_rays (raytrace_utils.c:265-347) for this rank's contiguous NEST range."""
+        nray_tot = 12 << (2 * self.ray_order)
+        lo = (nray_tot * self.rank) // self.nranks
+        hi = (nray_tot * (self.rank + 1)) // self.nranks
+        self.first_nest, self.nrays = lo, hi - lo
+        self.rays = torch.empty(max(self.nrays, 1) * 176, dtype=torch.uint8, device=self.device)
+        self.lib.clb_ray_init_dev(self.rays.data_ptr(), self.nrays, lo, self.ray_order, float(binL_2), self._stream())
+        return self.nrays
+
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def _all_to_all(self, send, recv, send_counts, recv_counts):
+        if self.nranks == 1:
+            return send
+        self.dist.all_to_all_single(recv[:2 * sum(recv_counts)], send[:2 * sum(send_counts)],
+                                    output_split_sizes=[2 * c for c in recv_counts],
+                                    input_split_sizes=[2 * c for c in send_counts], group=self.group)
+        return recv
+
+    # ---- the SHT Poisson solve: counts map in self.maps[0] -> six derivative maps in self.maps ----
+    def solve(self, premul, densmul, backdens):
+        p = self.plan
+        self.lib.clb_scale_density_dev(self.maps[0].data_ptr(), self.npix, float(premul), float(densmul), float(backdens),
+                                       self._stream())
+        p.ring_analysis(self.maps[0], self.g_send)
+        g = self._all_to_all(self.g_send, self.g_recv, p.counts[0], p.counts[1])
+        p.legendre_analysis(g, self.alm_re, self.alm_im, poisson_filter=True)
+        p.legendre_synthesis(self.alm_re, self.alm_im, self.b_send)
+        b = self._all_to_all(self.b_send, self.b_recv, p.counts[2], p.counts[3])
+        if self.nranks > 1:
+            self.maps.zero_()
+        p.ring_synthesis(b, self.maps)
+        if self.nranks > 1:
+            self.dist.all_reduce(self.maps, group=self.group)   # disjoint ring sets: x + 0 is exact
+        return self.maps
+
+    def ray_update(self, wpp1, wp, wpm1):
+        """zero + interpolate + propagate: rayprop_sphere(planeRadPlus1, planeRad, planeRadMinus1) as called at
+        raytrace.c:262, preceded by the reset of raytrace.c:213-230 and the interpolation of shtpoissonsolve.c:666-702."""
+        ptrs = (__import__("ctypes").c_void_p * 6)(*[self.maps[k].data_ptr() for k in range(6)])
+        self.lib.clb_ray_step_dev(self.rays.data_ptr(), self.nrays, ptrs, self.order, float(wpp1), float(wp), float(wpm1),
+                                  MODE_ZERO | MODE_INTERP | MODE_PROP, self._stream())
+
+    def step(self, counts_map, premul, densmul, backdens, wpp1, wp, wpm1, read_summary=True):
+        """One lens plane.  ``counts_map``: RING float32 full-sky map, a device tensor or a (pinned) host tensor."""
+        self.maps[0].copy_(counts_map, non_blocking=True)
+        self.solve(premul, densmul, backdens)
+        self.ray_update(wpp1, wp, wpm1)
+        if not read_summary:
+            return None
+        self.lib.clb_ray_summary_dev(self.rays.data_ptr(), self.nrays, self.summary.data_ptr(), self._stream())
+        if self.nranks > 1:
+            self.dist.all_reduce(self.summary, group=self.group)
+        return self.summary.cpu().numpy()
+
+    def rays_host(self):
+        from .rays import rays_from_device
+        return rays_from_device(self.rays[:self.nrays * 176])

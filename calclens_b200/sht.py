@@ -77,13 +77,12 @@ def read_ring_weights(path, order):
 
 
 def default_owners(order, lmax, nranks):
-    """Ring pairs are dealt to ranks in warp-sized groups, m round-robin: every rank sees all latitudes and all
-    m magnitudes, which balances both the FFT and the Legendre stage without the reference's cost polynomials
-    (healpix_shtrans.c:219-250, :597-626)."""
+    """Ring pairs are dealt to ranks round-robin in groups of four adjacent pairs (128-byte runs in the exchange
+    buffers), m round-robin: every rank sees all latitudes and all m magnitudes, which balances both the FFT and the
+    Legendre stage without the reference's cost polynomials (healpix_shtrans.c:219-250, :597-626)."""
     nrp = 2 * order2nside(order)
-    rp_owner = ((np.arange(nrp) // 32) % nranks).astype(np.int32)
-    if nrp // 32 < nranks:
-        rp_owner = (np.arange(nrp) % nranks).astype(np.int32)
+    group = 4 if nrp >= 32 * nranks else 1
+    rp_owner = ((np.arange(nrp) // group) % nranks).astype(np.int32)
     m_owner = (np.arange(lmax + 1) % nranks).astype(np.int32)
     return rp_owner, m_owner
 

@@ -71,6 +71,12 @@ int clb_scale_density_dev(float *map, long npix, float premul, float densmul, fl
 int clb_ray_step_dev(void *rays, long nrays, const float *const maps[6], long map_order, double wp, double wpm1,
                      double wpm2, int mode, void *stream);
 
+/* ray initialisation of init_rays (raytrace_utils.c:302-347): ray i observes from NEST pixel first_nest+i at
+ * ray_order, n = beta*binL/2, A = Aprev = identity */
+int clb_ray_init_dev(void *rays, long nrays, long first_nest, long ray_order, double binL_2, void *stream);
+/* six sums over the rays (convergence, shear 1/2, |alpha|^2, phi, rotation): the per-plane scalar a host reads back */
+int clb_ray_summary_dev(const void *rays, long nrays, double *out6, void *stream);
+
 /* ---- host-pointer entry points (single rank; transfers inside) ---- */
 /* map2alm_mpi on a RING-ordered map (healpix_shtrans.h:67) */
 void clb_map2alm(clb_sht_plan *plan, const float *ringmap, double *alm_re, double *alm_im, int apply_poisson_filter);

@@ -41,6 +41,7 @@ def lib():
         L.ref_read_ring_weights.restype = C.c_long; L.ref_read_ring_weights.argtypes = [C.c_char_p, C.c_long, C.c_void_p]
         L.ref_plmgen.restype = C.c_long; L.ref_plmgen.argtypes = [C.c_long, C.c_double, C.c_double, C.c_long, C.c_void_p]
         L.ref_sizeof_ray.restype = C.c_long
+        L.ref_init_rays.restype = None; L.ref_init_rays.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_double]
         assert L.ref_sizeof_ray() == 176
         # HEALPix helpers straight from healpix_utils.c
         L.ring2nest.restype = C.c_long; L.ring2nest.argtypes = [C.c_long, C.c_long]
@@ -113,18 +114,25 @@ def plmgen(lmax, cth, sth, m):
     return firstl, vec
 
 
-def init_rays(ray_order, binL_2, nest_ids=None):
+def init_rays(ray_order, binL_2, first=0, n=None):
     """Ray initialisation as raytrace_utils.c:302-347 (beta = pixel centre, n = beta*binL/2, A = Aprev = I)."""
-    L = lib()
     npix = 12 << (2 * ray_order)
-    ids = np.arange(npix, dtype=np.int64) if nest_ids is None else np.asarray(nest_ids, dtype=np.int64)
-    rays = np.zeros(ids.size, dtype=RAY_DTYPE)
-    v = (C.c_double * 3)()
-    for i, nest in enumerate(ids):
-        L.nest2vec(int(nest), v, ray_order)
-        rays["beta"][i] = (v[0], v[1], v[2])
-    rays["nest"] = ids
-    rays["n"] = rays["beta"] * binL_2
-    rays["A"][:, 0] = 1.0; rays["A"][:, 3] = 1.0
-    rays["Aprev"][:, 0] = 1.0; rays["Aprev"][:, 3] = 1.0
+    n = npix - first if n is None else n
+    rays = np.zeros(n, dtype=RAY_DTYPE)
+    lib().ref_init_rays(rays.ctypes.data, first, n, ray_order, binL_2)
     return rays
+
+
+NAME = "reference (oracle/_ref)"
+
+
+def ring2nest(p, order): return lib().ring2nest(int(p), order)
+def nest2ring(p, order): return lib().nest2ring(int(p), order)
+def nest2peano(p, order): return lib().nest2peano(int(p), order)
+def ang2nest(t, p, order): return lib().ang2nest(float(t), float(p), order)
+
+
+def get_interpol(theta, phi, order):
+    pix = (C.c_long * 4)(); wgt = (C.c_double * 4)()
+    lib().get_interpol(float(theta), float(phi), pix, wgt, order)
+    return list(pix), list(wgt)

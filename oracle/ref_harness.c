@@ -173,4 +173,17 @@ long ref_plmgen(long lmax, double cth, double sth, long m, double *vec)
   return firstl;
 }
 
+/* init_rays (raytrace_utils.c:302-347) for NEST pixels first..first+n-1, using the reference's nest2vec */
+void ref_init_rays(HEALPixRay *rays, long first, long n, long ray_order, double binL_2)
+{
+  long i;
+  memset(rays, 0, sizeof(HEALPixRay) * n);
+  for (i = 0; i < n; ++i) {
+    rays[i].nest = first + i;
+    nest2vec(rays[i].nest, rays[i].beta, ray_order);
+    rays[i].n[0] = rays[i].beta[0] * binL_2; rays[i].n[1] = rays[i].beta[1] * binL_2; rays[i].n[2] = rays[i].beta[2] * binL_2;
+    rays[i].A[0] = 1.0; rays[i].A[3] = 1.0; rays[i].Aprev[0] = 1.0; rays[i].Aprev[3] = 1.0;
+  }
+}
+
 long ref_sizeof_ray(void) { return (long)sizeof(HEALPixRay); }

@@ -1,0 +1,406 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the oracle on the
+same seeded inputs, against the committed golden vectors, and -- at the benchmark sizes, where the CPU oracle is too
+slow -- through size-independent properties.
+
+Tolerances (BASELINE.json north_star): pixel/ring indexing bit-exact; alm <= 1e-10 relative L2 (FP64); ray
+convergence, shear, deflection <= 1e-8 relative.  The six float32 derivative maps are compared bit for bit: the CUDA
+path rounds to float exactly where the reference does, so at most a handful of pixels may differ by one float ulp
+(FP64 round-off before a rounding boundary); the bound asserted is <= 1e-5 of the pixels and <= 2e-7 relative L2.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ALM_TOL = 1e-10
+RAY_TOL = 1e-8
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.sqrt(((a - b) ** 2).sum() / max((b ** 2).sum(), 1e-300)))
+
+
+def alm_err(gre, gim, are, aim):
+    return float(np.sqrt((((gre - are) ** 2 + (gim - aim) ** 2).sum()) / max((are ** 2 + aim ** 2).sum(), 1e-300)))
+
+
+def assert_maps_match(mg, mo, what):
+    """float maps: a pixel counts as different when it differs by more than one float ulp of its own value plus
+    1e-9 of the field's scale (pixels that vanish by symmetry hold pure FP64 round-off, ~1e-16 of the scale, on
+    both sides and cannot agree bit for bit)"""
+    for k in range(6):
+        a = mg[k].astype(np.float64); b = mo[k].astype(np.float64)
+        scale = np.abs(b).max()
+        bad = np.abs(a - b) > 1.2e-7 * np.maximum(np.abs(a), np.abs(b)) + 1e-9 * scale
+        ndiff = int(bad.sum())
+        assert ndiff <= max(2, 1e-5 * b.size), "%s field %d: %d of %d floats differ" % (what, k, ndiff, b.size)
+        assert rel_l2(a, b) <= 2e-7, "%s field %d rel L2 %g" % (what, k, rel_l2(a, b))
+
+
+def assert_rays_match(rg, ro, fields=("n", "beta", "A", "Aprev", "alpha", "U", "phi")):
+    for f in fields:
+        scale = max(np.abs(ro[f]).max(), 1e-300)
+        d = np.abs(rg[f] - ro[f]).max()
+        assert d <= RAY_TOL * scale, "ray field %s: max abs diff %g (scale %g)" % (f, d, scale)
+
+
+@pytest.fixture(scope="module")
+def clb():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import calclens_b200
+    from calclens_b200 import _lib
+    assert _lib.load().clb_device_count() >= 1
+    return calclens_b200
+
+
+@pytest.fixture(scope="module")
+def weights():
+    return np.load(os.path.join(GOLD, "ring_weights.npz"))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# indexing: bit-exact
+# ----------------------------------------------------------------------------------------------------------------
+def _index_dev(what, order, pix=None, theta=None, phi=None):
+    import torch
+    from calclens_b200 import _lib
+    L = _lib.load()
+    n = len(pix) if pix is not None else len(theta)
+    dev = torch.device("cuda")
+    tin = torch.from_numpy(np.asarray(pix if pix is not None else np.zeros(n), dtype=np.int64)).to(dev)
+    tth = torch.from_numpy(np.asarray(theta if theta is not None else np.zeros(n), dtype=np.float64)).to(dev)
+    tph = torch.from_numpy(np.asarray(phi if phi is not None else np.zeros(n), dtype=np.float64)).to(dev)
+    out = torch.empty(n, dtype=torch.int64, device=dev)
+    L.clb_healpix_index_dev(what, order, n, tin.data_ptr(), tth.data_ptr(), tph.data_ptr(), out.data_ptr(), None)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def test_indexing_golden_bit_exact(clb):
+    g = np.load(os.path.join(GOLD, "healpix_index.npz"))
+    for order in (0, 1, 2, 3, 4, 5):
+        p = np.arange(12 << (2 * order))
+        assert np.array_equal(_index_dev(0, order, p), g["ring2nest_o%d" % order])
+        assert np.array_equal(_index_dev(1, order, p), g["nest2ring_o%d" % order])
+        assert np.array_equal(_index_dev(3, order, p), g["nest2peano_o%d" % order])
+    for order in (0, 3, 8, 13):
+        assert np.array_equal(_index_dev(2, order, theta=g["theta"], phi=g["phi"]), g["ang2nest_o%d" % order])
+
+
+def test_indexing_vs_oracle_large(clb, oracle):
+    rng = np.random.default_rng(5)
+    for order in (7, 10, 12):
+        npix = 12 << (2 * order)
+        pix = rng.integers(0, npix, 4000)
+        # ring boundaries: first/last pixel of caps and of the equatorial belt
+        nside = 1 << order
+        ncap = 2 * nside * (nside - 1)
+        pix[:8] = [0, 3, 4, ncap - 1, ncap, npix - ncap - 1, npix - ncap, npix - 1]
+        assert np.array_equal(_index_dev(0, order, pix), np.array([oracle.ring2nest(p, order) for p in pix]))
+        assert np.array_equal(_index_dev(1, order, pix), np.array([oracle.nest2ring(p, order) for p in pix]))
+        # round trip on the device
+        assert np.array_equal(_index_dev(1, order, _index_dev(0, order, pix)), pix)
+        th = np.arccos(rng.uniform(-1, 1, 4000)); ph = rng.uniform(0, 2 * np.pi, 4000)
+        assert np.array_equal(_index_dev(2, order, theta=th, phi=ph), np.array([oracle.ang2nest(t, p, order) for t, p in zip(th, ph)]))
+
+
+def test_interpolation_stencil_vs_oracle(clb, oracle):
+    import torch
+    from calclens_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(6)
+    for order in (1, 4, 10):
+        n = 3000
+        v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1)[:, None]
+        v[:4] = [[1e-4, 0, 1], [0, 1e-4, -1], [1, 0, 0], [0.6, 0.0, 0.8]]     # near both poles, equator
+        v *= rng.uniform(10, 1000, n)[:, None]
+        tv = torch.from_numpy(v.copy()).cuda()
+        pix = torch.empty((n, 4), dtype=torch.int64, device="cuda"); wgt = torch.empty((n, 4), dtype=torch.float64, device="cuda")
+        L.clb_healpix_interpol_dev(order, n, tv.data_ptr(), pix.data_ptr(), wgt.data_ptr(), None)
+        torch.cuda.synchronize()
+        pix = pix.cpu().numpy(); wgt = wgt.cpu().numpy()
+        for i in range(n):
+            r = np.linalg.norm(v[i])
+            theta = np.arccos(v[i, 2] / r); phi = np.arctan2(v[i, 1], v[i, 0]) % (2 * np.pi)
+            p, w = oracle.get_interpol(theta, phi, order)
+            assert list(pix[i]) == p, (order, i)
+            assert np.abs(wgt[i] - np.array(w)).max() < 1e-9
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# SHT
+# ----------------------------------------------------------------------------------------------------------------
+def test_sht_golden(clb, weights):
+    g = np.load(os.path.join(GOLD, "sht.npz"))
+    for tag in "abcd":
+        order, lmax = int(g[tag + "_order"]), int(g[tag + "_lmax"])
+        w = weights["n%05d" % (1 << order)] if int(g[tag + "_weights"]) else None
+        plan = clb.HEALPixSHTPlan(order, lmax, ring_weights=w)
+        are, aim = clb.map2alm_mpi(g[tag + "_map"], plan)
+        assert alm_err(are, aim, g[tag + "_alm_re"], g[tag + "_alm_im"]) <= ALM_TOL
+        fre, fim = clb.map2alm_mpi(g[tag + "_map"], plan, poisson_filter=True)
+        assert alm_err(fre, fim, g[tag + "_falm_re"], g[tag + "_falm_im"]) <= ALM_TOL
+        maps = clb.alm2allmaps_mpi(g[tag + "_falm_re"], g[tag + "_falm_im"], plan)
+        assert_maps_match(maps, g[tag + "_maps"], "golden " + tag)
+        plan.destroy()
+
+
+@pytest.mark.parametrize("order,lmax,use_w", [(0, 2, False), (1, 5, False), (2, 8, False), (4, 32, True), (4, 47, True),
+                                              (5, 40, False), (6, 128, True), (6, 191, False), (7, 256, True), (8, 512, True)])
+def test_sht_vs_oracle(clb, oracle, weights, order, lmax, use_w):
+    """lmax = 3 Nside - 1 is the reference's own default (aliasing on every polar ring), lmax = 2 Nside the
+    BASELINE configs', the odd ones exercise ragged block/tile tails."""
+    rng = np.random.default_rng(100 + order)
+    nside = 1 << order; npix = 12 * nside * nside
+    w = weights["n%05d" % nside] if use_w else None
+    m = ((8.0 * rng.lognormal(sigma=0.5, size=npix)).astype(np.float32) * np.float32(3e-4) - np.float32(8 * np.exp(0.125) * 3e-4)).astype(np.float32)
+    are, aim = oracle.map2alm(order, lmax, m, w)
+    plan = clb.HEALPixSHTPlan(order, lmax, ring_weights=w)
+    gre, gim = clb.map2alm_mpi(m, plan)
+    assert alm_err(gre, gim, are, aim) <= ALM_TOL
+    fre, fim = oracle.poisson_filter(lmax, are, aim)
+    mo = oracle.alm2allmaps(order, lmax, fre, fim)
+    mg = clb.alm2allmaps_mpi(fre, fim, plan)
+    assert_maps_match(mg, mo, "order %d lmax %d" % (order, lmax))
+    plan.destroy()
+
+
+def test_sht_edge_inputs(clb, oracle):
+    order, lmax = 4, 32
+    npix = 12 << (2 * order)
+    plan = clb.HEALPixSHTPlan(order, lmax)
+    # empty map -> exactly zero alm and maps
+    are, aim = clb.map2alm_mpi(np.zeros(npix, dtype=np.float32), plan)
+    assert not are.any() and not aim.any()
+    assert not clb.alm2allmaps_mpi(are, aim, plan).any()
+    # point mass (single non-zero pixel) at a pole pixel, an equator pixel and a cap boundary pixel
+    for pix in (0, npix // 2, 2 * 16 * 15, npix - 1):
+        m = np.zeros(npix, dtype=np.float32); m[pix] = 1.0
+        a = oracle.map2alm(order, lmax, m); b = clb.map2alm_mpi(m, plan)
+        assert alm_err(b[0], b[1], a[0], a[1]) <= ALM_TOL
+        f = oracle.poisson_filter(lmax, *a)
+        assert_maps_match(clb.alm2allmaps_mpi(f[0], f[1], plan), oracle.alm2allmaps(order, lmax, *f), "point mass %d" % pix)
+    # constant map: only a_00 (removed by the filter)
+    a = clb.map2alm_mpi(np.full(npix, 2.5, dtype=np.float32), plan, poisson_filter=True)
+    assert a[0][0] == 0.0 and a[1][0] == 0.0
+    plan.destroy()
+
+
+def test_mapvec_entry_points(clb, oracle):
+    """the reference's padded ring-pair buffer layout (healpix_shtrans.c:90-118) through clb_*_mapvec"""
+    from calclens_b200 import _lib
+    L = _lib.load()
+    order, lmax = 3, 16
+    nside = 1 << order; npix = 12 * nside * nside
+    rng = np.random.default_rng(9)
+    m = rng.normal(size=npix).astype(np.float32)
+    # build the layout exactly as healpixsht_plan does for one rank
+    ns, ss, off = [], [], 0
+    for r in range(1, 2 * nside + 1):
+        n = 4 * min(r, nside)
+        ns.append(off); off += n // 2 + 1
+        if r != 2 * nside:
+            ss.append(off); off += n // 2 + 1
+        else:
+            ss.append(-1)
+    assert off == npix // 2 + 4 * nside - 1          # Nmapvec, SURVEY.md section 4
+    ns = np.array(ns, dtype=np.int64); ss = np.array(ss, dtype=np.int64)
+    mapvec = np.zeros(2 * off, dtype=np.float32)
+    for i, r in enumerate(range(1, 2 * nside + 1)):
+        n = 4 * min(r, nside)
+        start = 2 * r * (r - 1) if r < nside else 2 * nside * (nside - 1) + (r - nside) * 4 * nside
+        mapvec[2 * ns[i]:2 * ns[i] + n] = m[start:start + n]
+        if ss[i] >= 0:
+            mapvec[2 * ss[i]:2 * ss[i] + n] = m[npix - start - n:npix - start]
+    plan = clb.HEALPixSHTPlan(order, lmax)
+    are = np.empty(plan.Nlm); aim = np.empty(plan.Nlm)
+    L.clb_map2alm_mapvec(plan._h, mapvec.ctypes.data, ns.ctypes.data, ss.ctypes.data, are.ctypes.data, aim.ctypes.data)
+    ore, oim = oracle.map2alm(order, lmax, m)
+    assert alm_err(are, aim, ore, oim) <= ALM_TOL
+    bufs = [np.zeros(2 * off, dtype=np.float32) for _ in range(6)]
+    ptrs = (C.c_void_p * 6)(*[b.ctypes.data for b in bufs])
+    L.clb_alm2allmaps_mapvec(plan._h, ore.ctypes.data, oim.ctypes.data, ptrs, ns.ctypes.data, ss.ctypes.data)
+    mo = oracle.alm2allmaps(order, lmax, ore, oim)
+    for k in range(6):
+        for i, r in enumerate(range(1, 2 * nside + 1)):
+            n = 4 * min(r, nside)
+            start = 2 * r * (r - 1) if r < nside else 2 * nside * (nside - 1) + (r - nside) * 4 * nside
+            assert np.array_equal(bufs[k][2 * ns[i]:2 * ns[i] + n], mo[k][start:start + n])
+    plan.destroy()
+
+
+def test_sht_properties_at_benchmark_size(clb):
+    """Nside=1024, lmax=2048 (BASELINE configs[1]) without a CPU oracle: linearity, the Laplacian identity
+    grad_tt + grad_pp = -kappa-like source, and analysis(synthesis(alm)) = alm to quadrature accuracy."""
+    import torch
+    order, lmax = 10, 2048
+    plan = clb.HEALPixSHTPlan(order, lmax)
+    dev = plan.device
+    gen = torch.Generator(device=dev); gen.manual_seed(3)
+    ls = torch.cat([torch.arange(m, lmax + 1, device=dev, dtype=torch.float64) for m in range(lmax + 1)])
+    amp = (ls + 10.0) ** -1.1
+    are = torch.randn(plan.Nlm, generator=gen, device=dev, dtype=torch.float64) * amp
+    aim = torch.randn(plan.Nlm, generator=gen, device=dev, dtype=torch.float64) * amp
+    aim[:lmax + 1] = 0.0
+    are[0] = 0.0
+    maps = plan.ring_synthesis(plan.legendre_synthesis(are, aim)).clone()
+    # Laplacian identity: maps[3] + maps[5] is the synthesis of -l(l+1) a_lm
+    lap = plan.ring_synthesis(plan.legendre_synthesis(-ls * (ls + 1) * are, -ls * (ls + 1) * aim))[0]
+    num = (maps[3].double() + maps[5].double() - lap.double()).pow(2).sum().sqrt()
+    assert float(num / lap.double().pow(2).sum().sqrt()) < 2e-5
+    # linearity of synthesis (float32 output): S(2a) == 2 S(a) exactly, S(a+b) ~ S(a)+S(b)
+    maps2 = plan.ring_synthesis(plan.legendre_synthesis(2 * are, 2 * aim))
+    assert torch.equal(maps2[0], 2 * maps[0])
+    # round trip through analysis (no ring weights: HEALPix quadrature error ~1e-3 at lmax = 2 Nside)
+    bre, bim = plan.legendre_analysis(plan.ring_analysis(maps[0].contiguous()))
+    err = float(((bre - are).pow(2) + (bim - aim).pow(2)).sum().sqrt() / (are.pow(2) + aim.pow(2)).sum().sqrt())
+    assert err < 5e-3
+    plan.destroy()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# rays
+# ----------------------------------------------------------------------------------------------------------------
+def test_rays_golden(clb):
+    g = np.load(os.path.join(GOLD, "rays.npz"))
+    order = int(g["order"])
+    rays = g["rays0"].view(clb.RAY_DTYPE).copy()
+    clb.shearinterp_rays(g["maps"], order, rays)
+    assert_rays_match(rays, g["rays_interp"].view(clb.RAY_DTYPE), ("alpha", "U", "phi"))
+    rays = g["rays_interp"].view(clb.RAY_DTYPE).copy()
+    clb.rayprop_sphere(45.0, 15.0, 0.0, rays)
+    assert_rays_match(rays, g["rays_prop1"].view(clb.RAY_DTYPE))
+    rz = g["rz0"].view(clb.RAY_DTYPE).copy()          # alpha == 0 branch
+    clb.rayprop_sphere(45.0, 15.0, 0.0, rz)
+    assert_rays_match(rz, g["rz1"].view(clb.RAY_DTYPE))
+
+
+def test_rays_multi_plane_vs_oracle(clb, oracle):
+    rng = np.random.default_rng(21)
+    order = 6
+    npix = 12 << (2 * order)
+    ro = oracle.init_rays(7, 15.0)[::5].copy()
+    rg = ro.copy()
+    w = [15.0 + 30.0 * p for p in range(6)]
+    for p in range(4):
+        maps = (rng.normal(size=(6, npix)) * np.array([1, 2e-4, 2e-4, 3e-3, 3e-3, 3e-3])[:, None]).astype(np.float32)
+        for r in (ro, rg):
+            r["alpha"] = 0; r["U"] = 0; r["phi"] = 0
+        oracle.shearinterp(order, 3, maps, ro)
+        clb.shearinterp_rays(maps, order, rg)
+        wm1 = 0.0 if p == 0 else w[p - 1]
+        oracle.rayprop(ro, w[p + 1], w[p], wm1)
+        clb.rayprop_sphere(w[p + 1], w[p], wm1, rg)
+        assert_rays_match(rg, ro)
+    kap_o = 1 - 0.5 * (ro["A"][:, 0] + ro["A"][:, 3]); kap_g = 1 - 0.5 * (rg["A"][:, 0] + rg["A"][:, 3])
+    assert np.abs(kap_g - kap_o).max() <= RAY_TOL * np.abs(kap_o).max()
+
+
+def test_ray_init_matches_reference_init(clb, oracle):
+    import torch
+    from calclens_b200 import _lib
+    from calclens_b200.rays import rays_from_device
+    L = _lib.load()
+    order = 6
+    n = 12 << (2 * order)
+    t = torch.empty(n * 176, dtype=torch.uint8, device="cuda")
+    L.clb_ray_init_dev(t.data_ptr(), n, 0, order, 15.0, None)
+    torch.cuda.synchronize()
+    rg = rays_from_device(t)
+    ro = oracle.init_rays(order, 15.0)
+    assert np.array_equal(rg["nest"], ro["nest"])
+    for f in ("beta", "n"):
+        assert np.abs(rg[f] - ro[f]).max() <= 1e-15 * max(1.0, np.abs(ro[f]).max())
+    assert np.array_equal(rg["A"], ro["A"]) and np.array_equal(rg["Aprev"], ro["Aprev"])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# whole lens plane through the C ABI, and the sharded (N > 1) decomposition emulated on one GPU
+# ----------------------------------------------------------------------------------------------------------------
+def _oracle_plane(oracle, order, lmax, counts, premul, densmul, backdens, rays, wpp1, wp, wpm1, w=None):
+    m = ((counts * premul) * densmul - backdens).astype(np.float32)
+    are, aim = oracle.map2alm(order, lmax, m, w)
+    are, aim = oracle.poisson_filter(lmax, are, aim)
+    maps = oracle.alm2allmaps(order, lmax, are, aim)
+    rays["alpha"] = 0; rays["U"] = 0; rays["phi"] = 0
+    oracle.shearinterp(order, 2, maps, rays)
+    oracle.rayprop(rays, wpp1, wp, wpm1)
+    return maps
+
+
+def test_lens_plane_end_to_end(clb, oracle):
+    from calclens_b200 import _lib
+    L = _lib.load()
+    order, lmax = 6, 128
+    npix = 12 << (2 * order)
+    rng = np.random.default_rng(31)
+    counts = (8.0 * rng.lognormal(sigma=0.5, size=npix)).astype(np.float32)
+    premul, densmul, backdens = np.float32(1.0), np.float32(2e-4), np.float32(8.0 * np.exp(0.125) * 2e-4)
+    ro = oracle.init_rays(order, 15.0); rg = ro.copy()
+    plan = clb.HEALPixSHTPlan(order, lmax)
+    for (wpp1, wp, wpm1) in ((45.0, 15.0, 0.0), (75.0, 45.0, 15.0)):
+        _oracle_plane(oracle, order, lmax, counts, premul, densmul, backdens, ro, wpp1, wp, wpm1)
+        L.clb_lens_plane(plan._h, counts.ctypes.data, float(premul), float(densmul), float(backdens), rg.ctypes.data, rg.size, wpp1, wp, wpm1)
+        assert_rays_match(rg, ro)
+    plan.destroy()
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_sharded_decomposition_emulated_on_one_gpu(clb, oracle, nranks):
+    """N ranks' plans on one device; the two all-to-alls are done by slicing the send buffers with the plans'
+    per-peer counts.  The assembled result must equal the single-rank result bit for bit."""
+    import torch
+    order, lmax = 5, 64
+    npix = 12 << (2 * order)
+    rng = np.random.default_rng(41)
+    m = rng.normal(size=npix).astype(np.float32)
+    dm = torch.from_numpy(m).cuda()
+    single = clb.HEALPixSHTPlan(order, lmax)
+    s_re, s_im = single.legendre_analysis(single.ring_analysis(dm), poisson_filter=True)
+    s_maps = single.ring_synthesis(single.legendre_synthesis(s_re, s_im)).cpu().numpy()
+    s_re = s_re.cpu().numpy(); s_im = s_im.cpu().numpy()
+    plans = [clb.HEALPixSHTPlan(order, lmax, nranks=nranks, rank=r) for r in range(nranks)]
+    from calclens_b200 import layout
+    rp_owner, m_owner = clb.default_owners(order, lmax, nranks)
+    for r, p in enumerate(plans):    # the CUDA-free layout module and the C plan agree
+        lay = layout.ExchangeLayout(1 << order, lmax, nranks, r, rp_owner, m_owner)
+        assert p.counts == [lay.g_send_counts, lay.g_recv_counts, lay.b_send_counts, lay.b_recv_counts]
+        assert list(p.m_local) == list(lay.my_m) and list(p.rp_local) == list(lay.my_rp)
+
+    def all_to_all(sends, which_send, which_recv):
+        recvs = []
+        for d in range(nranks):
+            parts = []
+            for s in range(nranks):
+                cnt = plans[s].counts[which_send]
+                off = 2 * sum(cnt[:d])
+                parts.append(sends[s][off:off + 2 * cnt[d]])
+            recvs.append(torch.cat(parts) if parts else torch.zeros(0, dtype=torch.float64, device="cuda"))
+            assert recvs[-1].numel() == 2 * sum(plans[d].counts[which_recv])
+        return recvs
+    g_send = [p.ring_analysis(dm).clone() for p in plans]
+    g_recv = all_to_all(g_send, 0, 1)
+    alms = [p.legendre_analysis(g, poisson_filter=True) for p, g in zip(plans, g_recv)]
+    # reassemble alm in single-rank m-major order
+    full_re = np.zeros_like(s_re); full_im = np.zeros_like(s_im)
+    for p, (are, aim) in zip(plans, alms):
+        are = are.cpu().numpy(); aim = aim.cpu().numpy(); off = 0
+        for mm in p.m_local:
+            n = lmax - mm + 1
+            dst = clb.lm2index(mm, mm, lmax)
+            full_re[dst:dst + n] = are[off:off + n]; full_im[dst:dst + n] = aim[off:off + n]; off += n
+    assert np.array_equal(full_re, s_re) and np.array_equal(full_im, s_im)
+    b_send = [p.legendre_synthesis(a[0], a[1]).clone() for p, a in zip(plans, alms)]
+    b_recv = all_to_all(b_send, 2, 3)
+    total = torch.zeros((6, npix), dtype=torch.float32, device="cuda")
+    for p, b in zip(plans, b_recv):
+        total += p.ring_synthesis(b)           # disjoint ring sets
+    assert np.array_equal(total.cpu().numpy(), s_maps)
+    for p in plans + [single]:
+        p.destroy()
