@@ -628,7 +628,11 @@ void fft_tables_create(ShtPlan *p)
     CLB_CUDA_CHECK(cudaMalloc(&d_rlist, sizeof(int) * need_r.size()));
     CLB_CUDA_CHECK(cudaMemcpy(d_rlist, need_r.data(), sizeof(int) * need_r.size(), cudaMemcpyHostToDevice));
     size_t smem = sizeof(double2) << maxLogM;
-    CLB_CUDA_CHECK(cudaFuncSetAttribute(bluestein_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t attr_blu = 0;
+    if (smem > attr_blu) {
+      CLB_CUDA_CHECK(cudaFuncSetAttribute(bluestein_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_blu = smem;
+    }
     bluestein_table_kernel<<<(unsigned)need_r.size(), 256, smem>>>(d_rlist, t->d_chirp_off, t->d_bhat_off, t->d_chirp,
                                                                    t->d_bhat, t->d_tw, t->logTW);
     CLB_CUDA_CHECK(cudaGetLastError());
@@ -656,8 +660,17 @@ void fft_tables_create(ShtPlan *p)
                     "supports Nside <= 4096\n", std::max(max_ana, max_syn), nside);
     abort();
   }
-  CLB_CUDA_CHECK(cudaFuncSetAttribute(ring_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_ana));
-  CLB_CUDA_CHECK(cudaFuncSetAttribute(ring_synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_syn));
+  // the attribute is per function, not per plan: several plans may be alive (one per emulated rank, or one per
+  // resolution), so it is only ever raised
+  static size_t attr_ana = 0, attr_syn = 0;
+  if (max_ana > attr_ana) {
+    CLB_CUDA_CHECK(cudaFuncSetAttribute(ring_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_ana));
+    attr_ana = max_ana;
+  }
+  if (max_syn > attr_syn) {
+    CLB_CUDA_CHECK(cudaFuncSetAttribute(ring_synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_syn));
+    attr_syn = max_syn;
+  }
 }
 
 // defined in sht_plan.cu
