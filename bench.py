@@ -216,19 +216,20 @@ def make_count_maps(solver, nmaps, lmax, seed=1234, nbar=8.0, sigma=0.5):
         gen = torch.Generator(device=solver.device); gen.manual_seed(seed + k + 7919 * solver.rank)
         are = torch.randn(max(p.Nlm, 1), generator=gen, device=solver.device, dtype=torch.float64)
         aim = torch.randn(max(p.Nlm, 1), generator=gen, device=solver.device, dtype=torch.float64)
-        # scale by sqrt(C_l/2): build l for every local (m, l)
-        ls = torch.cat([torch.arange(int(m), lmax + 1, device=solver.device, dtype=torch.float64) for m in p.m_local]) if p.nm_loc else torch.zeros(1, device=solver.device, dtype=torch.float64)
+        # scale by sqrt(C_l/2): degree l of every local (m, l) without one launch per m
+        if p.nm_loc:
+            mloc = torch.as_tensor(np.asarray(p.m_local), device=solver.device, dtype=torch.int64)
+            cnt = lmax + 1 - mloc
+            start = torch.cumsum(cnt, 0) - cnt
+            ls = (torch.arange(int(cnt.sum()), device=solver.device, dtype=torch.int64)
+                  - torch.repeat_interleave(start, cnt) + torch.repeat_interleave(mloc, cnt)).double()
+            ms = torch.repeat_interleave(mloc, cnt)
+        else:
+            ls = torch.zeros(1, device=solver.device, dtype=torch.float64); ms = torch.zeros(1, device=solver.device, dtype=torch.int64)
         amp = torch.sqrt(0.5 * (ls + 10.0) ** -1.2)
         amp[ls < 1] = 0.0
         are[:ls.numel()] *= amp; aim[:ls.numel()] *= amp
-        # m = 0 coefficients are real
-        off = 0
-        for m in p.m_local:
-            n = lmax - int(m) + 1
-            if m == 0:
-                aim[off:off + n] = 0.0
-                are[off:off + n] *= math.sqrt(2.0)
-            off += n
+        aim[:ls.numel()][ms == 0] = 0.0          # m = 0 coefficients are real
         b = p.legendre_synthesis(are, aim, solver.b_send)
         b = solver._all_to_all(solver.b_send, solver.b_recv, p.counts[2], p.counts[3])
         if solver.nranks > 1:

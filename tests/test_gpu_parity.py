@@ -404,3 +404,17 @@ def test_sharded_decomposition_emulated_on_one_gpu(clb, oracle, nranks):
     assert np.array_equal(total.cpu().numpy(), s_maps)
     for p in plans + [single]:
         p.destroy()
+
+
+def test_multi_gpu_step_matches_single_gpu(clb):
+    """two ranks over NCCL (needs >= 2 visible GPUs; skipped on a one-GPU box)"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "tests", "dist_gpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "DIST CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
