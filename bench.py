@@ -265,6 +265,11 @@ def main():
     if a.impl == "reference":
         return run_reference_arm(a)
 
+    # stdout carries exactly one JSON line: libraries that print to fd 1 (NCCL's version banner, ...) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import calclens_b200 as clb
@@ -455,7 +460,8 @@ def main():
                 "hbm_peak_source": hbm_src,
                 "cpu_baseline": cpu_baseline,
                 "setup_s": t_setup}
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -1,0 +1,17 @@
+"""Run one SHT stage a few times (for ncu captures): python tools/prof_stage.py <order> <lmax> [reps]"""
+import sys
+import torch
+sys.path.insert(0, ".")
+import calclens_b200 as clb
+
+order, lmax = int(sys.argv[1]), int(sys.argv[2])
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+plan = clb.HEALPixSHTPlan(order, lmax)
+m = torch.randn(plan.npix, device="cuda", dtype=torch.float32)
+for _ in range(reps):
+    g = plan.ring_analysis(m)
+    are, aim = plan.legendre_analysis(g, poisson_filter=True)
+    b = plan.legendre_synthesis(are, aim)
+    maps = plan.ring_synthesis(b)
+torch.cuda.synchronize()
+print("done")
