@@ -22,123 +22,147 @@
 namespace clb {
 
 constexpr int kLB = 16;            // degrees per register block (== kSeedAlign)
-constexpr int kAnaThreads = 256;
-constexpr int kSynThreads = 256;
-constexpr int kSynTile = 32;       // degrees per shared-memory coefficient tile
+constexpr int kLegWarps = 4;       // warps per CTA of both Legendre kernels
+constexpr int kLegThreads = kLegWarps * 32;
 static_assert(kLB == kSeedAlign, "l-blocks must line up with the seed alignment");
 
-// ring pair handled by (chunk c, warp w, slot j, lane): warp-sized groups of adjacent rings are dealt round-robin
-// to chunks so that every CTA sees all latitudes (balanced start degrees)
-__device__ __forceinline__ int ring_of(int c, int nchunk, int w, int nwarp, int j, int lane)
-{
-  return (((j * nwarp + w) * nchunk + c) << 5) + lane;
-}
+// Ring pairs are dealt in contiguous runs: warp W of the grid row owns the 32*R adjacent ring pairs starting at
+// W*32*R, thread `lane` of it the pairs W*32*R + j*32 + lane (j < R).  Adjacent rings reach |lambda| > 1e-30 at almost
+// the same degree, so one start degree per warp (analysis: per CTA) wastes ~1 % of the work and the whole warp runs
+// branch-free: rings that start later carry mu = 0 until their seed is injected at their own (16-aligned) start.
 
 // ---------------------------------------------------------------------------------------------------------------
 // analysis
 // ---------------------------------------------------------------------------------------------------------------
-template <int RPT>
-__global__ void __launch_bounds__(kAnaThreads)
+// One CTA = kLegWarps*32*R adjacent ring pairs of one m; one warp = 32*R of them, running on its own from the first
+// degree where any of its rings is above 1e-30.  Per degree and ring pair: DMUL + DFMA (recurrence) and two DFMA
+// (re, im accumulate) -- the ring state lives in registers for the whole degree range.  After every block of KB
+// degrees the 2*KB per-thread partial sums are reduced over the warp with a transpose-reduce (one shuffle + add per
+// value) and parked in the warp's row of a shared-memory tile of kAnaTile degrees; once per tile the CTA adds its
+// warps' rows in a fixed order (deterministic) and writes them to this ring chunk's partial-sum row.
+// alm_finish_kernel adds the chunks.
+constexpr int kAnaTile = 128;
+
+template <int R, int KB>
+__global__ void __launch_bounds__(kLegThreads, 3)
 legendre_analysis_kernel(const double2 *__restrict__ g_recv, const long *__restrict__ g_off,
                          const int *__restrict__ g_stride, const double *__restrict__ Atab,
                          const long *__restrict__ row_off, const int *__restrict__ ls_tab,
                          const double2 *__restrict__ seed_tab, const double *__restrict__ cth_rp,
                          const int *__restrict__ m_loc, const long *__restrict__ alm_off, double2 *__restrict__ part,
-                         long alm_total, int nrp, int lmax, int nchunk)
+                         long alm_total, int nrp, int lmax)
 {
-  extern __shared__ unsigned char smem_raw[];
-  double2 *s_state = reinterpret_cast<double2 *>(smem_raw);                 // [RPT][T]
-  double2 *s_gp = s_state + RPT * kAnaThreads;                                // [RPT][T] G+ = gN + gS
-  double2 *s_gm = s_gp + RPT * kAnaThreads;                                   // [RPT][T] G- = gN - gS
-  double *s_x = reinterpret_cast<double *>(s_gm + RPT * kAnaThreads);         // [RPT][T]
-  int *s_ls = reinterpret_cast<int *>(s_x + RPT * kAnaThreads);               // [RPT][T]
-  __shared__ double s_red[kAnaThreads / 32][32];
+  static_assert(KB == 8 || KB == 16, "block of 8 or 16 degrees");
+  constexpr int V = 2 * KB;   // v[i] = re(l0+i), v[KB+i] = im(l0+i)
+  __shared__ double2 s_out[2][kLegWarps][kAnaTile];
+  __shared__ double s_A[kLegWarps][2][KB];
   __shared__ int s_lsmin;
 
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nwarp = kAnaThreads / 32;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int c = blockIdx.x, mi = blockIdx.y;
   const int m = m_loc[mi];
   if (tid == 0) s_lsmin = kNoStart;
   __syncthreads();
-  int lsmin = kNoStart;
+  int ls[R];
+  double mp[R], mc[R], x[R], gpx[R], gpy[R], gmx[R], gmy[R];
+  int lsw = kNoStart;
+  const int rp0 = (c * kLegWarps + w) * 32 * R + lane;
 #pragma unroll
-  for (int j = 0; j < RPT; ++j) {
-    const int rp = ring_of(c, nchunk, w, nwarp, j, lane);
-    int ls = kNoStart;
-    double2 st = make_double2(0.0, 0.0), gp = st, gm = st;
-    double x = 0.0;
+  for (int j = 0; j < R; ++j) {
+    const int rp = rp0 + j * 32;
+    ls[j] = kNoStart; mp[j] = 0.0; mc[j] = 0.0; x[j] = 0.0; gpx[j] = 0.0; gpy[j] = 0.0; gmx[j] = 0.0; gmy[j] = 0.0;
     if (rp < nrp) {
-      ls = ls_tab[(size_t)mi * nrp + rp];
-      if (ls != kNoStart) {
-        st = seed_tab[(size_t)mi * nrp + rp];
+      ls[j] = ls_tab[(size_t)mi * nrp + rp];
+      if (ls[j] != kNoStart) {
         const double2 *g = g_recv + g_off[rp] + (long)mi * g_stride[rp];
-        double2 gn = g[0], gs = g[1];
-        gp = make_double2(gn.x + gs.x, gn.y + gs.y);
-        gm = make_double2(gn.x - gs.x, gn.y - gs.y);
-        x = cth_rp[rp];
+        const double2 gn = g[0], gs = g[1];
+        gpx[j] = gn.x + gs.x; gpy[j] = gn.y + gs.y;     // G+ = gN + gS multiplies even l+m
+        gmx[j] = gn.x - gs.x; gmy[j] = gn.y - gs.y;     // G- = gN - gS multiplies odd l+m
+        x[j] = cth_rp[rp];
       }
     }
-    s_state[j * kAnaThreads + tid] = st; s_gp[j * kAnaThreads + tid] = gp; s_gm[j * kAnaThreads + tid] = gm;
-    s_x[j * kAnaThreads + tid] = x; s_ls[j * kAnaThreads + tid] = ls;
-    lsmin = min(lsmin, ls);
+    lsw = min(lsw, ls[j]);
   }
-  for (int o = 16; o; o >>= 1) lsmin = min(lsmin, __shfl_xor_sync(0xffffffffu, lsmin, o));
-  if (lane == 0) atomicMin(&s_lsmin, lsmin);
+  for (int o = 16; o; o >>= 1) lsw = min(lsw, __shfl_xor_sync(0xffffffffu, lsw, o));
+  if (lane == 0) atomicMin(&s_lsmin, lsw);
   __syncthreads();
-  lsmin = s_lsmin;
+  const int lsmin = s_lsmin;
   double2 *out = part + (size_t)c * alm_total + alm_off[mi];   // index l - m
   // degrees below the first active block get exact zeros
   {
     const int lz = (lsmin == kNoStart) ? lmax + 1 : lsmin;
-    for (int l = m + tid; l < lz; l += kAnaThreads) out[l - m] = make_double2(0.0, 0.0);
+    for (int l = m + tid; l < lz; l += kLegThreads) out[l - m] = make_double2(0.0, 0.0);
     if (lsmin == kNoStart) return;
   }
-  const double *Arow = Atab + row_off[mi];
-  for (int l0 = lsmin; l0 <= lmax; l0 += kLB) {
-    double A[kLB];
+  const double *Arow = Atab + row_off[mi];     // rows are zero padded beyond lmax+1 (kRowPad)
+  double *sA = &s_A[w][0][0];
+  if (lsw != kNoStart) {
+    if (lane < KB) sA[lane] = Arow[lsw - m + lane];
+    __syncwarp();
+  }
+  int cur = 0, tb = 0;
+  for (int lt = lsmin; lt <= lmax; lt += kAnaTile, tb ^= 1) {
+    double2 *srow = &s_out[tb][w][0];
+    const int lend = min(lt + kAnaTile, lmax + 1);
+    for (int l0 = lt; l0 < lend; l0 += KB) {
+      if (l0 < lsw) {   // this warp's rings are all still below 1e-30 (warp-uniform; also lsw == kNoStart)
+        if (lane < KB) srow[l0 - lt + lane] = make_double2(0.0, 0.0);
+        continue;
+      }
+      double a_next = 0.0;
+      if (lane < KB) a_next = __ldg(&Arow[l0 + KB - m + lane]);
+      if ((l0 - m) % kSeedAlign == 0) {
 #pragma unroll
-    for (int i = 0; i < kLB; ++i) A[i] = __ldg(&Arow[l0 - m + i]);
-    double v[2 * kLB];   // v[i] = re(l0+i), v[kLB+i] = im(l0+i)
+        for (int j = 0; j < R; ++j)
+          if (ls[j] == l0) {
+            const double2 sd = seed_tab[(size_t)mi * nrp + rp0 + j * 32];
+            mp[j] = sd.x; mc[j] = sd.y;
+          }
+      }
+      double v[V];
 #pragma unroll
-    for (int i = 0; i < 2 * kLB; ++i) v[i] = 0.0;
+      for (int i = 0; i < V; ++i) v[i] = 0.0;
+      const double *sa = sA + cur * KB;
 #pragma unroll
-    for (int j = 0; j < RPT; ++j) {
-      if (l0 >= s_ls[j * kAnaThreads + tid]) {
-        double2 st = s_state[j * kAnaThreads + tid];
-        const double2 gp = s_gp[j * kAnaThreads + tid], gm = s_gm[j * kAnaThreads + tid];
-        const double x = s_x[j * kAnaThreads + tid];
-        double mp = st.x, mc = st.y;
+      for (int i = 0; i < KB; ++i) {
+        const double a = sa[i];
 #pragma unroll
-        for (int i = 0; i < kLB; i += 2) {
-          v[i] = fma(mc, gp.x, v[i]); v[kLB + i] = fma(mc, gp.y, v[kLB + i]);
-          double mn = fma(x * A[i], mc, -mp); mp = mc; mc = mn;
-          v[i + 1] = fma(mc, gm.x, v[i + 1]); v[kLB + i + 1] = fma(mc, gm.y, v[kLB + i + 1]);
-          mn = fma(x * A[i + 1], mc, -mp); mp = mc; mc = mn;
+        for (int j = 0; j < R; ++j) {
+          const double mu = mc[j];
+          if (i & 1) { v[i] = fma(mu, gmx[j], v[i]); v[KB + i] = fma(mu, gmy[j], v[KB + i]); }
+          else       { v[i] = fma(mu, gpx[j], v[i]); v[KB + i] = fma(mu, gpy[j], v[KB + i]); }
+          const double mn = fma(x[j] * a, mu, -mp[j]);
+          mp[j] = mu; mc[j] = mn;
         }
-        s_state[j * kAnaThreads + tid] = make_double2(mp, mc);
       }
-    }
-    // warp transpose-reduce: afterwards lane L holds the warp total of v[L]
+      // warp transpose-reduce: afterwards lane L holds the warp total of v[L % V]
 #pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-      const bool upper = (lane & s) != 0;
+      for (int s = V / 2; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
 #pragma unroll
-      for (int k = 0; k < s; ++k) {
-        double send = upper ? v[k] : v[k + s];
-        double keep = upper ? v[k + s] : v[k];
-        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        for (int k = 0; k < s; ++k) {
+          const double send = upper ? v[k] : v[k + s];
+          const double keep = upper ? v[k + s] : v[k];
+          v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
       }
-    }
-    s_red[w][lane] = v[0];
-    __syncthreads();
-    if (w == 0) {
-      double t = 0.0;
-#pragma unroll
-      for (int k = 0; k < kAnaThreads / 32; ++k) t += s_red[k][lane];   // fixed order: deterministic
-      double ti = __shfl_down_sync(0xffffffffu, t, kLB);                 // imaginary part lives kLB lanes up
-      if (lane < kLB && l0 + lane <= lmax) out[l0 - m + lane] = make_double2(t, ti);
+      if (V == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+      const double ti = __shfl_down_sync(0xffffffffu, v[0], KB);   // imaginary part lives KB lanes up
+      if (lane < KB) {
+        srow[l0 - lt + lane] = make_double2(v[0], ti);
+        sA[(cur ^ 1) * KB + lane] = a_next;
+      }
+      cur ^= 1;
+      __syncwarp();
     }
     __syncthreads();
+    // add the warps' rows (fixed order: deterministic); the tile is double buffered, so one barrier per tile suffices
+    for (int i = tid; i < lend - lt; i += kLegThreads) {
+      double2 t = s_out[tb][0][i];
+#pragma unroll
+      for (int k = 1; k < kLegWarps; ++k) { const double2 u = s_out[tb][k][i]; t.x += u.x; t.y += u.y; }
+      out[lt - m + i] = t;
+    }
   }
 }
 
@@ -215,86 +239,100 @@ __global__ void synthesis_coef_kernel(const double *__restrict__ alm_re, const d
   }
 }
 
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// One warp = 32*R adjacent ring pairs of one m, independent of the other warps of its CTA (no block barrier): it
+// streams the per-degree coefficient records {A, P, D, K} of its own degree range through a private double-buffered
+// shared-memory tile (cp.async, 1 KB per 16 degrees) and reads them back as broadcast LDS.128 -- two per degree for
+// 8*R FP64 instructions, which keeps the shared-memory pipe at ~1/4 of the FP64 pipe's time for R = 4.
 template <int R>
-__global__ void __launch_bounds__(kSynThreads)
+__global__ void __launch_bounds__(kLegThreads, (R >= 4) ? 3 : 4)
 legendre_synthesis_kernel(const double *__restrict__ coef, const long *__restrict__ row_off,
                           const int *__restrict__ ls_tab, const double2 *__restrict__ seed_tab,
                           const double *__restrict__ cth_rp, const double *__restrict__ sth_rp,
                           const int *__restrict__ m_loc, const long *__restrict__ b_off,
-                          const int *__restrict__ b_stride, double2 *__restrict__ b_send, int nrp, int lmax, int nchunk)
+                          const int *__restrict__ b_stride, double2 *__restrict__ b_send, int nrp, int lmax)
 {
-  __shared__ __align__(16) double s_tile[kSynTile * 8];
-  __shared__ int s_lsmin;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nwarp = kSynThreads / 32;
+  __shared__ __align__(16) double s_tile[kLegWarps][2][kLB * 8];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int c = blockIdx.x, mi = blockIdx.y;
   const int m = m_loc[mi];
-  if (tid == 0) s_lsmin = kNoStart;
-  __syncthreads();
-  int ls[R], rpv[R];
+  int ls[R];
   double mp[R], mc[R], x[R];
   double acc[R][12];   // [parity(0 even,1 odd)*6 + {Pre,Pim,Dre,Dim,Kre,Kim}]
   int lsmin = kNoStart;
+  const int rp0 = (c * kLegWarps + w) * 32 * R + lane;
 #pragma unroll
   for (int j = 0; j < R; ++j) {
-    const int rp = ring_of(c, nchunk, w, nwarp, j, lane);
-    rpv[j] = rp; ls[j] = kNoStart; mp[j] = 0.0; mc[j] = 0.0; x[j] = 0.0;
+    const int rp = rp0 + j * 32;
+    ls[j] = kNoStart; mp[j] = 0.0; mc[j] = 0.0; x[j] = 0.0;
     if (rp < nrp) {
       ls[j] = ls_tab[(size_t)mi * nrp + rp];
-      if (ls[j] != kNoStart) {
-        double2 st = seed_tab[(size_t)mi * nrp + rp];
-        mp[j] = st.x; mc[j] = st.y; x[j] = cth_rp[rp];
-      }
+      if (ls[j] != kNoStart) x[j] = cth_rp[rp];
     }
 #pragma unroll
     for (int k = 0; k < 12; ++k) acc[j][k] = 0.0;
     lsmin = min(lsmin, ls[j]);
   }
   for (int o = 16; o; o >>= 1) lsmin = min(lsmin, __shfl_xor_sync(0xffffffffu, lsmin, o));
-  if (lane == 0) atomicMin(&s_lsmin, lsmin);
-  __syncthreads();
-  lsmin = s_lsmin;
   if (lsmin != kNoStart) {
-    const double *crow = coef + 8 * row_off[mi];
-    // tiles start at lsmin (a multiple of kLB above m) and run through degree lmax+1
-    const int per_thread = (kSynTile * 8) / kSynThreads;   // doubles of the tile each thread moves
-    static_assert((kSynTile * 8) % kSynThreads == 0 && per_thread == 1, "tile copy assumes one double per thread");
-    double nxt = __ldg(&crow[8 * (long)(lsmin - m) + tid]);
-    for (int l0 = lsmin; l0 <= lmax + 1; l0 += kSynTile) {
-      __syncthreads();
-      s_tile[tid] = nxt;
-      __syncthreads();
-      if (l0 + kSynTile <= lmax + 1) nxt = __ldg(&crow[8 * (long)(l0 + kSynTile - m) + tid]);
+    // tiles start at lsmin (a multiple of kLB above m) and run through degree lmax+1; rows are zero padded (kRowPad)
+    const double *crow = coef + 8 * (row_off[mi] + (long)(lsmin - m));
+    double *tile = &s_tile[w][0][0];
+    // lane moves bytes [32*lane, 32*lane+32) of the 1 KB tile
+    cp_async16(tile + 4 * lane, crow + 4 * lane);
+    cp_async16(tile + 4 * lane + 2, crow + 4 * lane + 2);
+    cp_async_commit();
+    int buf = 0;
+    for (int l0 = lsmin; l0 <= lmax + 1; l0 += kLB, buf ^= 1) {
+      crow += kLB * 8;
+      double *nxt = &s_tile[w][buf ^ 1][0];
+      cp_async16(nxt + 4 * lane, crow + 4 * lane);
+      cp_async16(nxt + 4 * lane + 2, crow + 4 * lane + 2);
+      cp_async_commit();
 #pragma unroll
-      for (int h = 0; h < kSynTile / kLB; ++h) {
-        const int lh = l0 + h * kLB;
+      for (int j = 0; j < R; ++j)
+        if (ls[j] == l0) {
+          const double2 sd = seed_tab[(size_t)mi * nrp + rp0 + j * 32];
+          mp[j] = sd.x; mc[j] = sd.y;
+        }
+      cp_async_wait<1>();
+      __syncwarp();
+      const double *t = &s_tile[w][buf][0];
+#pragma unroll
+      for (int i = 0; i < kLB; ++i) {
+        const double4 ra = *reinterpret_cast<const double4 *>(&t[i * 8]);
+        const double4 rb = *reinterpret_cast<const double4 *>(&t[i * 8 + 4]);
+        const int par = (i & 1) * 6;   // (l0 - m) is even, so the parity of l+m is the parity of i
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-          if (lh >= ls[j]) {
-#pragma unroll
-            for (int i = 0; i < kLB; ++i) {
-              const double4 ra = *reinterpret_cast<const double4 *>(&s_tile[(h * kLB + i) * 8]);
-              const double4 rb = *reinterpret_cast<const double4 *>(&s_tile[(h * kLB + i) * 8 + 4]);
-              const int par = (i & 1) * 6;   // (lh - m) is even, so parity of l+m is parity of i
-              const double mu = mc[j];
-              acc[j][par + 0] = fma(mu, ra.y, acc[j][par + 0]);
-              acc[j][par + 1] = fma(mu, ra.z, acc[j][par + 1]);
-              acc[j][par + 2] = fma(mu, ra.w, acc[j][par + 2]);
-              acc[j][par + 3] = fma(mu, rb.x, acc[j][par + 3]);
-              acc[j][par + 4] = fma(mu, rb.y, acc[j][par + 4]);
-              acc[j][par + 5] = fma(mu, rb.z, acc[j][par + 5]);
-              const double mn = fma(x[j] * ra.x, mu, -mp[j]);
-              mp[j] = mu; mc[j] = mn;
-            }
-          }
+          const double mu = mc[j];
+          acc[j][par + 0] = fma(mu, ra.y, acc[j][par + 0]);
+          acc[j][par + 1] = fma(mu, ra.z, acc[j][par + 1]);
+          acc[j][par + 2] = fma(mu, ra.w, acc[j][par + 2]);
+          acc[j][par + 3] = fma(mu, rb.x, acc[j][par + 3]);
+          acc[j][par + 4] = fma(mu, rb.y, acc[j][par + 4]);
+          acc[j][par + 5] = fma(mu, rb.z, acc[j][par + 5]);
+          const double mn = fma(x[j] * ra.x, mu, -mp[j]);
+          mp[j] = mu; mc[j] = mn;
         }
       }
+      __syncwarp();   // everyone is done with this tile before the next iteration's copy overwrites it
     }
+    cp_async_wait<0>();
   }
   // combine parities into north / south and form the six fields
   const double dm = (double)m, m2 = dm * dm;
 #pragma unroll
   for (int j = 0; j < R; ++j) {
-    const int rp = rpv[j];
+    const int rp = rp0 + j * 32;
     if (rp >= nrp) continue;
     const double sth = sth_rp[rp], cth = cth_rp[rp];
     const double isth = 1.0 / sth, cot = cth * isth, m2s2 = m2 * isth * isth;
@@ -321,46 +359,36 @@ legendre_synthesis_kernel(const double *__restrict__ coef, const long *__restric
 // ---------------------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------------------
-static int pick_rpt(int nrp)
-{
-  int per = (nrp + kAnaThreads - 1) / kAnaThreads;
-  if (per >= 8) return 8;
-  if (per >= 4) return 4;
-  if (per >= 2) return 2;
-  return 1;
-}
+int g_syn_rings_per_thread = 4;   // tunable through clb_set_tuning(0, .)
+int g_ana_rings_per_thread = 8;   // tunable through clb_set_tuning(1, .): 8 (blocks of 8 degrees) or 4, 2, 1 (16 degrees)
 
-template <int RPT>
+template <int R, int KB>
 static void launch_ana_t(const ShtPlan *p, const double2 *g_recv, int nchunk, cudaStream_t st)
 {
-  const size_t smem = (size_t)RPT * kAnaThreads * (3 * sizeof(double2) + sizeof(double) + sizeof(int));
-  static bool attr_set = false;
-  if (!attr_set) {
-    CLB_CUDA_CHECK(cudaFuncSetAttribute(legendre_analysis_kernel<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
   dim3 grid(nchunk, p->nm_loc);
-  legendre_analysis_kernel<RPT><<<grid, kAnaThreads, smem, st>>>(
+  legendre_analysis_kernel<R, KB><<<grid, kLegThreads, 0, st>>>(
       g_recv, p->d_g_off, p->d_g_stride, p->d_A, p->d_row_off, p->d_ls_ana, p->d_seed, p->d_cth, p->d_m_loc,
-      p->d_alm_off, reinterpret_cast<double2 *>(p->d_part), p->alm_total, p->nrp, (int)p->lmax, nchunk);
+      p->d_alm_off, reinterpret_cast<double2 *>(p->d_part), p->alm_total, p->nrp, (int)p->lmax);
 }
 
 int launch_legendre_analysis(ShtPlan *p, const double2 *d_g_recv, double *d_alm_re, double *d_alm_im, int apply_filter,
                              cudaStream_t st)
 {
   if (p->nm_loc == 0) return 0;
-  const int rpt = pick_rpt(p->nrp);
-  const int nchunk = (p->nrp + rpt * kAnaThreads - 1) / (rpt * kAnaThreads);
+  int R = g_ana_rings_per_thread;
+  while (R > 1 && p->nrp < kLegThreads * R) R >>= 1;   // small maps: do not leave most of a CTA without rings
+  const int nchunk = (p->nrp + R * kLegThreads - 1) / (R * kLegThreads);
   if (!p->d_part || p->ana_nchunk != nchunk) {
     if (p->d_part) cudaFree(p->d_part);
     CLB_CUDA_CHECK(cudaMalloc(&p->d_part, sizeof(double2) * (size_t)nchunk * p->alm_total));
     p->ana_nchunk = nchunk;
   }
-  switch (rpt) {
-    case 8: launch_ana_t<8>(p, d_g_recv, nchunk, st); break;
-    case 4: launch_ana_t<4>(p, d_g_recv, nchunk, st); break;
-    case 2: launch_ana_t<2>(p, d_g_recv, nchunk, st); break;
-    default: launch_ana_t<1>(p, d_g_recv, nchunk, st); break;
+  switch (R) {
+    case 8: launch_ana_t<8, 8>(p, d_g_recv, nchunk, st); break;
+    case 6: launch_ana_t<6, 16>(p, d_g_recv, nchunk, st); break;
+    case 4: launch_ana_t<4, 16>(p, d_g_recv, nchunk, st); break;
+    case 2: launch_ana_t<2, 16>(p, d_g_recv, nchunk, st); break;
+    default: launch_ana_t<1, 16>(p, d_g_recv, nchunk, st); break;
   }
   CLB_CUDA_CHECK(cudaGetLastError());
   dim3 grid((unsigned)((p->lmax + 256) / 256), p->nm_loc);
@@ -371,8 +399,6 @@ int launch_legendre_analysis(ShtPlan *p, const double2 *d_g_recv, double *d_alm_
   return 2;
 }
 
-int g_syn_rings_per_thread = 2;   // tunable through clb_set_tuning
-
 int launch_legendre_synthesis(ShtPlan *p, const double *d_alm_re, const double *d_alm_im, double2 *d_b_send,
                               cudaStream_t st)
 {
@@ -382,15 +408,16 @@ int launch_legendre_synthesis(ShtPlan *p, const double *d_alm_re, const double *
                                                (int)p->lmax, p->d_coef);
   CLB_CUDA_CHECK(cudaGetLastError());
   int R = g_syn_rings_per_thread;
-  if (p->nrp <= kSynThreads) R = 1;
-  const int nchunk = (p->nrp + R * kSynThreads - 1) / (R * kSynThreads);
+  while (R > 1 && p->nrp < kLegThreads * R) R >>= 1;
+  const int nchunk = (p->nrp + R * kLegThreads - 1) / (R * kLegThreads);
   dim3 grid(nchunk, p->nm_loc);
 #define CLB_SYN_LAUNCH(RR)                                                                                           \
-  legendre_synthesis_kernel<RR><<<grid, kSynThreads, 0, st>>>(p->d_coef, p->d_row_off, p->d_ls_syn, p->d_seed, p->d_cth, \
+  legendre_synthesis_kernel<RR><<<grid, kLegThreads, 0, st>>>(p->d_coef, p->d_row_off, p->d_ls_syn, p->d_seed, p->d_cth, \
                                                               p->d_sth, p->d_m_loc, p->d_b_off, p->d_b_stride, d_b_send, \
-                                                              p->nrp, (int)p->lmax, nchunk)
+                                                              p->nrp, (int)p->lmax)
   switch (R) {
     case 4: CLB_SYN_LAUNCH(4); break;
+    case 3: CLB_SYN_LAUNCH(3); break;
     case 2: CLB_SYN_LAUNCH(2); break;
     default: CLB_SYN_LAUNCH(1); break;
   }

@@ -6,6 +6,10 @@ import calclens_b200 as clb
 
 order, lmax = int(sys.argv[1]), int(sys.argv[2])
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+import os
+from calclens_b200 import _lib
+if os.environ.get("CLB_SYN_R"): _lib.load().clb_set_tuning(0, int(os.environ["CLB_SYN_R"]))
+if os.environ.get("CLB_ANA_R"): _lib.load().clb_set_tuning(1, int(os.environ["CLB_ANA_R"]))
 plan = clb.HEALPixSHTPlan(order, lmax)
 m = torch.randn(plan.npix, device="cuda", dtype=torch.float32)
 for _ in range(reps):

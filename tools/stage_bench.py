@@ -1,0 +1,52 @@
+"""Time the four SHT stages separately with CUDA events, for a list of tuning settings.
+   python tools/stage_bench.py <order> <lmax> [syn=R,R,...] [ana=R,R,...] [reps]"""
+import sys
+import torch
+sys.path.insert(0, ".")
+import calclens_b200 as clb
+from calclens_b200 import _lib
+
+order, lmax = int(sys.argv[1]), int(sys.argv[2])
+syn = [4]; ana = [8]; reps = 3
+for a in sys.argv[3:]:
+    if a.startswith("syn="): syn = [int(x) for x in a[4:].split(",")]
+    elif a.startswith("ana="): ana = [int(x) for x in a[4:].split(",")]
+    else: reps = int(a)
+L = _lib.load()
+plan = clb.HEALPixSHTPlan(order, lmax)
+m = torch.randn(plan.npix, device="cuda", dtype=torch.float32)
+
+
+def timeit(fn):
+    fn(); torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+
+
+g_buf = torch.empty(2 * max(plan.g_send_total, 1), dtype=torch.float64, device="cuda")
+are_b = torch.empty(max(plan.Nlm, 1), dtype=torch.float64, device="cuda"); aim_b = torch.empty_like(are_b)
+b_buf = torch.empty(2 * max(plan.b_send_total, 1), dtype=torch.float64, device="cuda")
+maps_b = torch.zeros((6, plan.npix), dtype=torch.float32, device="cuda")
+t, g = timeit(lambda: plan.ring_analysis(m, g_buf))
+print("ring_analysis        %8.3f ms" % t)
+ref = None
+for r in ana:
+    L.clb_set_tuning(1, r)
+    t, (are, aim) = timeit(lambda: plan.legendre_analysis(g, are_b, aim_b, poisson_filter=True))
+    if ref is None:
+        ref = (are.clone(), aim.clone())
+    err = float(((are - ref[0]).norm() ** 2 + (aim - ref[1]).norm() ** 2).sqrt() / (ref[0].norm() ** 2 + ref[1].norm() ** 2).sqrt())
+    print("legendre_analysis R=%d %8.3f ms   rel diff to first %.2e" % (r, t, err))
+bref = None
+for r in syn:
+    L.clb_set_tuning(0, r)
+    t, b = timeit(lambda: plan.legendre_synthesis(ref[0], ref[1], b_buf))
+    if bref is None:
+        bref = b.clone()
+    print("legendre_synthesis R=%d %8.3f ms  identical to first: %s" % (r, t, bool(torch.equal(b, bref))))
+t, maps = timeit(lambda: plan.ring_synthesis(bref, maps_b))
+print("ring_synthesis       %8.3f ms" % t)
