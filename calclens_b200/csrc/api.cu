@@ -67,7 +67,7 @@ long clb_launch_count(void) { return g_launches; }
 void clb_set_tuning(int what, int value)
 {
   if (what == 0 && value >= 1 && value <= 4) g_syn_rings_per_thread = value;
-  if (what == 1 && (value == 1 || value == 2 || value == 4 || value == 6 || value == 8)) g_ana_rings_per_thread = value;
+  if (what == 1 && (value == 1 || value == 2 || value == 4 || value == 6 || value == 8 || value == 10 || value == 12)) g_ana_rings_per_thread = value;
 }
 
 clb_sht_plan *clb_sht_plan_create(long order, long lmax, const double *ring_weights, int nranks, int rank,

@@ -34,17 +34,14 @@ static_assert(kLB == kSeedAlign, "l-blocks must line up with the seed alignment"
 // ---------------------------------------------------------------------------------------------------------------
 // analysis
 // ---------------------------------------------------------------------------------------------------------------
-// One CTA = kLegWarps*32*R adjacent ring pairs of one m; one warp = 32*R of them, running on its own from the first
-// degree where any of its rings is above 1e-30.  Per degree and ring pair: DMUL + DFMA (recurrence) and two DFMA
-// (re, im accumulate) -- the ring state lives in registers for the whole degree range.  After every block of KB
-// degrees the 2*KB per-thread partial sums are reduced over the warp with a transpose-reduce (one shuffle + add per
-// value) and parked in the warp's row of a shared-memory tile of kAnaTile degrees; once per tile the CTA adds its
-// warps' rows in a fixed order (deterministic) and writes them to this ring chunk's partial-sum row.
-// alm_finish_kernel adds the chunks.
-constexpr int kAnaTile = 128;
-
-template <int R, int KB>
-__global__ void __launch_bounds__(kLegThreads, 3)
+// One warp = 32*R adjacent ring pairs of one m, running on its own (no block barrier) from the first degree where any
+// of its rings is above 1e-30.  Per degree and ring pair: DMUL + DFMA (recurrence) and two DFMA (re, im accumulate);
+// the ring state (mu_{l-1}, mu_l, cos theta, G+, G-) lives in registers for the whole degree range.  After every
+// block of KB degrees the 2*KB per-thread partial sums are reduced over the warp with a transpose-reduce (one
+// shuffle + add per value) and written to the warp's own partial-sum row; alm_finish_kernel adds the rows of all
+// warps of an m in a fixed order (deterministic).
+template <int R, int KB, int NB>
+__global__ void __launch_bounds__(kLegThreads, NB)
 legendre_analysis_kernel(const double2 *__restrict__ g_recv, const long *__restrict__ g_off,
                          const int *__restrict__ g_stride, const double *__restrict__ Atab,
                          const long *__restrict__ row_off, const int *__restrict__ ls_tab,
@@ -53,116 +50,101 @@ legendre_analysis_kernel(const double2 *__restrict__ g_recv, const long *__restr
                          long alm_total, int nrp, int lmax)
 {
   static_assert(KB == 8 || KB == 16, "block of 8 or 16 degrees");
+  static_assert(R % 2 == 0 || R == 1, "start blocks are packed two per register");
   constexpr int V = 2 * KB;   // v[i] = re(l0+i), v[KB+i] = im(l0+i)
-  __shared__ double2 s_out[2][kLegWarps][kAnaTile];
+  constexpr int NP = (R + 1) / 2;
   __shared__ double s_A[kLegWarps][2][KB];
-  __shared__ int s_lsmin;
 
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int c = blockIdx.x, mi = blockIdx.y;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int chunk = blockIdx.x * kLegWarps + w, mi = blockIdx.y;
+  if (chunk * 32 * R >= nrp) return;     // whole warp beyond the last ring pair (no barriers in this kernel)
   const int m = m_loc[mi];
-  if (tid == 0) s_lsmin = kNoStart;
-  __syncthreads();
-  int ls[R];
+  unsigned sb[NP];            // start block (ls - m) / 16 of ring j in the (j & 1) half of sb[j / 2]; 0xffff = never
   double mp[R], mc[R], x[R], gpx[R], gpy[R], gmx[R], gmy[R];
-  int lsw = kNoStart;
-  const int rp0 = (c * kLegWarps + w) * 32 * R + lane;
+  int lsw = kNoStart, lsmax = -1;
+  const int rp0 = chunk * 32 * R + lane;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) sb[j] = 0xffffffffu;
 #pragma unroll
   for (int j = 0; j < R; ++j) {
     const int rp = rp0 + j * 32;
-    ls[j] = kNoStart; mp[j] = 0.0; mc[j] = 0.0; x[j] = 0.0; gpx[j] = 0.0; gpy[j] = 0.0; gmx[j] = 0.0; gmy[j] = 0.0;
-    if (rp < nrp) {
-      ls[j] = ls_tab[(size_t)mi * nrp + rp];
-      if (ls[j] != kNoStart) {
-        const double2 *g = g_recv + g_off[rp] + (long)mi * g_stride[rp];
-        const double2 gn = g[0], gs = g[1];
-        gpx[j] = gn.x + gs.x; gpy[j] = gn.y + gs.y;     // G+ = gN + gS multiplies even l+m
-        gmx[j] = gn.x - gs.x; gmy[j] = gn.y - gs.y;     // G- = gN - gS multiplies odd l+m
-        x[j] = cth_rp[rp];
-      }
+    mp[j] = 0.0; mc[j] = 0.0; x[j] = 0.0; gpx[j] = 0.0; gpy[j] = 0.0; gmx[j] = 0.0; gmy[j] = 0.0;
+    int ls = kNoStart;
+    if (rp < nrp) ls = ls_tab[(size_t)mi * nrp + rp];
+    if (ls != kNoStart) {
+      const double2 *g = g_recv + g_off[rp] + (long)mi * g_stride[rp];
+      const double2 gn = g[0], gs = g[1];
+      gpx[j] = gn.x + gs.x; gpy[j] = gn.y + gs.y;     // G+ = gN + gS multiplies even l+m
+      gmx[j] = gn.x - gs.x; gmy[j] = gn.y - gs.y;     // G- = gN - gS multiplies odd l+m
+      x[j] = cth_rp[rp];
+      const unsigned blk = (unsigned)(ls - m) / kSeedAlign;
+      sb[j / 2] = (j & 1) ? ((sb[j / 2] & 0x0000ffffu) | (blk << 16)) : ((sb[j / 2] & 0xffff0000u) | blk);
+      lsw = min(lsw, ls); lsmax = max(lsmax, ls);
     }
-    lsw = min(lsw, ls[j]);
   }
-  for (int o = 16; o; o >>= 1) lsw = min(lsw, __shfl_xor_sync(0xffffffffu, lsw, o));
-  if (lane == 0) atomicMin(&s_lsmin, lsw);
-  __syncthreads();
-  const int lsmin = s_lsmin;
-  double2 *out = part + (size_t)c * alm_total + alm_off[mi];   // index l - m
+  for (int o = 16; o; o >>= 1) {
+    lsw = min(lsw, __shfl_xor_sync(0xffffffffu, lsw, o));
+    lsmax = max(lsmax, __shfl_xor_sync(0xffffffffu, lsmax, o));
+  }
+  double2 *out = part + (size_t)chunk * alm_total + alm_off[mi];   // index l - m
   // degrees below the first active block get exact zeros
   {
-    const int lz = (lsmin == kNoStart) ? lmax + 1 : lsmin;
-    for (int l = m + tid; l < lz; l += kLegThreads) out[l - m] = make_double2(0.0, 0.0);
-    if (lsmin == kNoStart) return;
+    const int lz = (lsw == kNoStart) ? lmax + 1 : lsw;
+    for (int l = m + lane; l < lz; l += 32) out[l - m] = make_double2(0.0, 0.0);
+    if (lsw == kNoStart) return;
   }
   const double *Arow = Atab + row_off[mi];     // rows are zero padded beyond lmax+1 (kRowPad)
   double *sA = &s_A[w][0][0];
-  if (lsw != kNoStart) {
-    if (lane < KB) sA[lane] = Arow[lsw - m + lane];
+  if (lane < KB) sA[lane] = Arow[lsw - m + lane];
+  __syncwarp();
+  int cur = 0;
+  for (int l0 = lsw; l0 <= lmax; l0 += KB) {
+    double a_next = 0.0;
+    if (lane < KB) a_next = __ldg(&Arow[l0 + KB - m + lane]);
+    if (l0 <= lsmax && (l0 - m) % kSeedAlign == 0) {     // start-up phase of this warp: inject the seeds of rings starting here
+      const unsigned blk = (unsigned)(l0 - m) / kSeedAlign;
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+        if (((sb[j / 2] >> (16 * (j & 1))) & 0xffffu) == blk) {
+          const double2 sd = seed_tab[(size_t)mi * nrp + rp0 + j * 32];
+          mp[j] = sd.x; mc[j] = sd.y;
+        }
+    }
+    double v[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = 0.0;
+    const double *sa = sA + cur * KB;
+#pragma unroll
+    for (int i = 0; i < KB; ++i) {
+      const double a = sa[i];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const double mu = mc[j];
+        if (i & 1) { v[i] = fma(mu, gmx[j], v[i]); v[KB + i] = fma(mu, gmy[j], v[KB + i]); }
+        else       { v[i] = fma(mu, gpx[j], v[i]); v[KB + i] = fma(mu, gpy[j], v[KB + i]); }
+        const double mn = fma(x[j] * a, mu, -mp[j]);
+        mp[j] = mu; mc[j] = mn;
+      }
+    }
+    // warp transpose-reduce: afterwards lane L holds the warp total of v[L % V]
+#pragma unroll
+    for (int s = V / 2; s >= 1; s >>= 1) {
+      const bool upper = (lane & s) != 0;
+#pragma unroll
+      for (int k = 0; k < s; ++k) {
+        const double send = upper ? v[k] : v[k + s];
+        const double keep = upper ? v[k + s] : v[k];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+      }
+    }
+    if (V == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+    const double ti = __shfl_down_sync(0xffffffffu, v[0], KB);   // imaginary part lives KB lanes up
+    if (lane < KB) {
+      if (l0 + lane <= lmax) out[l0 - m + lane] = make_double2(v[0], ti);
+      sA[(cur ^ 1) * KB + lane] = a_next;
+    }
+    cur ^= 1;
     __syncwarp();
-  }
-  int cur = 0, tb = 0;
-  for (int lt = lsmin; lt <= lmax; lt += kAnaTile, tb ^= 1) {
-    double2 *srow = &s_out[tb][w][0];
-    const int lend = min(lt + kAnaTile, lmax + 1);
-    for (int l0 = lt; l0 < lend; l0 += KB) {
-      if (l0 < lsw) {   // this warp's rings are all still below 1e-30 (warp-uniform; also lsw == kNoStart)
-        if (lane < KB) srow[l0 - lt + lane] = make_double2(0.0, 0.0);
-        continue;
-      }
-      double a_next = 0.0;
-      if (lane < KB) a_next = __ldg(&Arow[l0 + KB - m + lane]);
-      if ((l0 - m) % kSeedAlign == 0) {
-#pragma unroll
-        for (int j = 0; j < R; ++j)
-          if (ls[j] == l0) {
-            const double2 sd = seed_tab[(size_t)mi * nrp + rp0 + j * 32];
-            mp[j] = sd.x; mc[j] = sd.y;
-          }
-      }
-      double v[V];
-#pragma unroll
-      for (int i = 0; i < V; ++i) v[i] = 0.0;
-      const double *sa = sA + cur * KB;
-#pragma unroll
-      for (int i = 0; i < KB; ++i) {
-        const double a = sa[i];
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const double mu = mc[j];
-          if (i & 1) { v[i] = fma(mu, gmx[j], v[i]); v[KB + i] = fma(mu, gmy[j], v[KB + i]); }
-          else       { v[i] = fma(mu, gpx[j], v[i]); v[KB + i] = fma(mu, gpy[j], v[KB + i]); }
-          const double mn = fma(x[j] * a, mu, -mp[j]);
-          mp[j] = mu; mc[j] = mn;
-        }
-      }
-      // warp transpose-reduce: afterwards lane L holds the warp total of v[L % V]
-#pragma unroll
-      for (int s = V / 2; s >= 1; s >>= 1) {
-        const bool upper = (lane & s) != 0;
-#pragma unroll
-        for (int k = 0; k < s; ++k) {
-          const double send = upper ? v[k] : v[k + s];
-          const double keep = upper ? v[k + s] : v[k];
-          v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-        }
-      }
-      if (V == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
-      const double ti = __shfl_down_sync(0xffffffffu, v[0], KB);   // imaginary part lives KB lanes up
-      if (lane < KB) {
-        srow[l0 - lt + lane] = make_double2(v[0], ti);
-        sA[(cur ^ 1) * KB + lane] = a_next;
-      }
-      cur ^= 1;
-      __syncwarp();
-    }
-    __syncthreads();
-    // add the warps' rows (fixed order: deterministic); the tile is double buffered, so one barrier per tile suffices
-    for (int i = tid; i < lend - lt; i += kLegThreads) {
-      double2 t = s_out[tb][0][i];
-#pragma unroll
-      for (int k = 1; k < kLegWarps; ++k) { const double2 u = s_out[tb][k][i]; t.x += u.x; t.y += u.y; }
-      out[lt - m + i] = t;
-    }
   }
 }
 
@@ -362,11 +344,11 @@ legendre_synthesis_kernel(const double *__restrict__ coef, const long *__restric
 int g_syn_rings_per_thread = 4;   // tunable through clb_set_tuning(0, .)
 int g_ana_rings_per_thread = 8;   // tunable through clb_set_tuning(1, .): 8 (blocks of 8 degrees) or 4, 2, 1 (16 degrees)
 
-template <int R, int KB>
+template <int R, int KB, int NB>
 static void launch_ana_t(const ShtPlan *p, const double2 *g_recv, int nchunk, cudaStream_t st)
 {
-  dim3 grid(nchunk, p->nm_loc);
-  legendre_analysis_kernel<R, KB><<<grid, kLegThreads, 0, st>>>(
+  dim3 grid((nchunk + kLegWarps - 1) / kLegWarps, p->nm_loc);
+  legendre_analysis_kernel<R, KB, NB><<<grid, kLegThreads, 0, st>>>(
       g_recv, p->d_g_off, p->d_g_stride, p->d_A, p->d_row_off, p->d_ls_ana, p->d_seed, p->d_cth, p->d_m_loc,
       p->d_alm_off, reinterpret_cast<double2 *>(p->d_part), p->alm_total, p->nrp, (int)p->lmax);
 }
@@ -376,19 +358,21 @@ int launch_legendre_analysis(ShtPlan *p, const double2 *d_g_recv, double *d_alm_
 {
   if (p->nm_loc == 0) return 0;
   int R = g_ana_rings_per_thread;
-  while (R > 1 && p->nrp < kLegThreads * R) R >>= 1;   // small maps: do not leave most of a CTA without rings
-  const int nchunk = (p->nrp + R * kLegThreads - 1) / (R * kLegThreads);
+  while (R > 1 && p->nrp < 32 * R) R = (R > 8) ? 8 : R >> 1;   // small maps: do not leave most of a warp without rings
+  const int nchunk = (p->nrp + 32 * R - 1) / (32 * R);        // one partial-sum row per warp
   if (!p->d_part || p->ana_nchunk != nchunk) {
     if (p->d_part) cudaFree(p->d_part);
     CLB_CUDA_CHECK(cudaMalloc(&p->d_part, sizeof(double2) * (size_t)nchunk * p->alm_total));
     p->ana_nchunk = nchunk;
   }
   switch (R) {
-    case 8: launch_ana_t<8, 8>(p, d_g_recv, nchunk, st); break;
-    case 6: launch_ana_t<6, 16>(p, d_g_recv, nchunk, st); break;
-    case 4: launch_ana_t<4, 16>(p, d_g_recv, nchunk, st); break;
-    case 2: launch_ana_t<2, 16>(p, d_g_recv, nchunk, st); break;
-    default: launch_ana_t<1, 16>(p, d_g_recv, nchunk, st); break;
+    case 12: launch_ana_t<12, 8, 2>(p, d_g_recv, nchunk, st); break;
+    case 10: launch_ana_t<10, 16, 2>(p, d_g_recv, nchunk, st); break;
+    case 8: launch_ana_t<8, 8, 3>(p, d_g_recv, nchunk, st); break;
+    case 6: launch_ana_t<6, 16, 3>(p, d_g_recv, nchunk, st); break;
+    case 4: launch_ana_t<4, 16, 3>(p, d_g_recv, nchunk, st); break;
+    case 2: launch_ana_t<2, 16, 4>(p, d_g_recv, nchunk, st); break;
+    default: launch_ana_t<1, 16, 4>(p, d_g_recv, nchunk, st); break;
   }
   CLB_CUDA_CHECK(cudaGetLastError());
   dim3 grid((unsigned)((p->lmax + 256) / 256), p->nm_loc);

@@ -64,6 +64,75 @@ __global__ void __launch_bounds__(128, (R >= 4) ? 3 : 4) syn_k(double *out, int 
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// analysis-like: R rings in registers, per degree one LDS.64 (broadcast) + R*(DMUL + 3 DFMA); every KB degrees an
+// optional warp transpose-reduce of the 2*KB partial sums (MODE 1: shuffles, MODE 2: through shared memory)
+template <int R, int KB, int MODE, int NB = 3>
+__global__ void __launch_bounds__(128, NB) ana_k(double *out, int iters, double a0)
+{
+  constexpr int V = 2 * KB;
+  __shared__ double sA[2][KB];
+  __shared__ double sT[4][V][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x < KB) { sA[0][threadIdx.x] = 1.0 + 1e-3 * threadIdx.x + a0; sA[1][threadIdx.x] = 1.0 - 1e-3 * threadIdx.x + a0; }
+  __syncthreads();
+  double mp[R], mc[R], x[R], gpx[R], gpy[R], gmx[R], gmy[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    mp[j] = 0.1 * j; mc[j] = 0.2 + threadIdx.x * 1e-4; x[j] = 0.3 + j * 0.01;
+    gpx[j] = 1 + j; gpy[j] = 2 + j; gmx[j] = 3 + j; gmy[j] = 4 + j + a0;
+  }
+  double tot = 0;
+  for (int it = 0; it < iters; ++it) {
+    const double *sa = sA[it & 1];
+    double v[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < KB; ++i) {
+      const double a = sa[i];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const double mu = mc[j];
+        if (i & 1) { v[i] = fma(mu, gmx[j], v[i]); v[KB + i] = fma(mu, gmy[j], v[KB + i]); }
+        else       { v[i] = fma(mu, gpx[j], v[i]); v[KB + i] = fma(mu, gpy[j], v[KB + i]); }
+        const double mn = fma(x[j] * a, mu, -mp[j]);
+        mp[j] = mu; mc[j] = mn;
+      }
+    }
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) tot += v[i];
+    } else if (MODE == 1) {
+#pragma unroll
+      for (int s = V / 2; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int k = 0; k < s; ++k) {
+          const double send = upper ? v[k] : v[k + s];
+          const double keep = upper ? v[k + s] : v[k];
+          v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+      }
+      if (V == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+      tot += v[0];
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) sT[w][i][lane] = v[i];
+      __syncwarp();
+      double t = 0;
+      const int row = lane % V, half = (V == 16) ? (lane >> 4) : 0;
+      constexpr int NC = (V == 16) ? 16 : 32;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) t += sT[w][row][half * 16 + ((k + lane) & (NC - 1))];
+      if (V == 16) t += __shfl_xor_sync(0xffffffffu, t, 16);
+      tot += t;
+      __syncwarp();
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = tot + mc[0] + mc[R - 1];
+}
+
 template <typename F>
 static float timeit(F f)
 {
@@ -113,6 +182,36 @@ int main()
       printf(" %6.2f", 16.0 * 4 * 16 * it2 * sms * warps * 32 / ms * 1e-9);
     }
     printf("\n");
+  }
+  printf("analysis-like loop at 12 warps/SM (8 flop per ring-degree): TFLOP/s, modes none / shuffle reduce / smem reduce\n");
+  {
+    float ms; const int it3 = 1 << 12; const int ctas = sms * 3;
+#define ANA(R, KB) \
+    printf("R=%d KB=%2d:", R, KB); \
+    ms = timeit([&] { ana_k<R, KB, 0><<<ctas, 128>>>(out, it3, 1e-9); }); printf(" %6.2f", 8.0 * R * KB * it3 * ctas * 128 / ms * 1e-9); \
+    ms = timeit([&] { ana_k<R, KB, 1><<<ctas, 128>>>(out, it3, 1e-9); }); printf(" %6.2f", 8.0 * R * KB * it3 * ctas * 128 / ms * 1e-9); \
+    ms = timeit([&] { ana_k<R, KB, 2><<<ctas, 128>>>(out, it3, 1e-9); }); printf(" %6.2f\n", 8.0 * R * KB * it3 * ctas * 128 / ms * 1e-9);
+    ANA(8, 8) ANA(6, 16)
+    {
+      const int ctas2 = sms * 2;
+      printf("2 CTAs/SM R=12 KB=8:");
+      ms = timeit([&] { ana_k<12, 8, 0, 2><<<ctas2, 128>>>(out, it3, 1e-9); }); printf(" %6.2f", 8.0 * 12 * 8 * it3 * ctas2 * 128 / ms * 1e-9);
+      ms = timeit([&] { ana_k<12, 8, 1, 2><<<ctas2, 128>>>(out, it3, 1e-9); }); printf(" %6.2f", 8.0 * 12 * 8 * it3 * ctas2 * 128 / ms * 1e-9);
+      ms = timeit([&] { ana_k<12, 8, 2, 2><<<ctas2, 128>>>(out, it3, 1e-9); }); printf(" %6.2f\n", 8.0 * 12 * 8 * it3 * ctas2 * 128 / ms * 1e-9);
+      printf("2 CTAs/SM R=10 KB=16:");
+      ms = timeit([&] { ana_k<10, 16, 0, 2><<<ctas2, 128>>>(out, it3, 1e-9); }); printf(" %6.2f", 8.0 * 10 * 16 * it3 * ctas2 * 128 / ms * 1e-9);
+      ms = timeit([&] { ana_k<10, 16, 1, 2><<<ctas2, 128>>>(out, it3, 1e-9); }); printf(" %6.2f", 8.0 * 10 * 16 * it3 * ctas2 * 128 / ms * 1e-9);
+      ms = timeit([&] { ana_k<10, 16, 2, 2><<<ctas2, 128>>>(out, it3, 1e-9); }); printf(" %6.2f\n", 8.0 * 10 * 16 * it3 * ctas2 * 128 / ms * 1e-9);
+      printf("2 CTAs/SM R=8 KB=8:");
+      ms = timeit([&] { ana_k<8, 8, 0, 2><<<ctas2, 128>>>(out, it3, 1e-9); }); printf(" %6.2f", 8.0 * 8 * 8 * it3 * ctas2 * 128 / ms * 1e-9);
+      ms = timeit([&] { ana_k<8, 8, 1, 2><<<ctas2, 128>>>(out, it3, 1e-9); }); printf(" %6.2f", 8.0 * 8 * 8 * it3 * ctas2 * 128 / ms * 1e-9);
+      ms = timeit([&] { ana_k<8, 8, 2, 2><<<ctas2, 128>>>(out, it3, 1e-9); }); printf(" %6.2f\n", 8.0 * 8 * 8 * it3 * ctas2 * 128 / ms * 1e-9);
+      const int ctas4 = sms * 4;
+      printf("4 CTAs/SM R=8 KB=8 (128 regs):");
+      ms = timeit([&] { ana_k<8, 8, 0, 4><<<ctas4, 128>>>(out, it3, 1e-9); }); printf(" %6.2f", 8.0 * 8 * 8 * it3 * ctas4 * 128 / ms * 1e-9);
+      ms = timeit([&] { ana_k<8, 8, 1, 4><<<ctas4, 128>>>(out, it3, 1e-9); }); printf(" %6.2f", 8.0 * 8 * 8 * it3 * ctas4 * 128 / ms * 1e-9);
+      ms = timeit([&] { ana_k<8, 8, 2, 4><<<ctas4, 128>>>(out, it3, 1e-9); }); printf(" %6.2f\n", 8.0 * 8 * 8 * it3 * ctas4 * 128 / ms * 1e-9);
+    }
   }
   cudaError_t e = cudaDeviceSynchronize();
   printf("status %s\n", cudaGetErrorString(e));
