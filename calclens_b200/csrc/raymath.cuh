@@ -116,6 +116,156 @@ CLB_HD void ray_interp_accumulate(Ray &ray, long order, const float *m_phi, cons
   ray.U[0] += ti[0][0]; ray.U[1] += ti[0][1]; ray.U[2] += ti[1][0]; ray.U[3] += ti[1][1];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fast device path.  Same mathematics as the functions above with the per-ring quantities tabulated once per map
+// resolution and the transport angle evaluated without normalising the rotation axis:
+//   R e = e cos(a) + (u x e) + u (u.e) / (1 + cos(a)),   u = v x v'  (|u| = sin(a)),
+// which is Rodrigues' formula with axis u/|u| (rot_paratrans.c:78-92) after cancelling |u|.  Pixel indices and
+// interpolation weights are formed by exactly the reference's expressions (they must be bit-exact); the transported
+// quantities agree with the line-by-line mirror above to ~1e-15.
+// ---------------------------------------------------------------------------------------------------------------
+struct RingTab {      // one entry per ring 1 .. 4*Nside-1 (entry 0 unused)
+  double theta;       // atan2(sin, cos) of the ring as get_interpol takes it           [healpix_utils.c:986,1001]
+  double cz, sz;      // cos/sin(theta) of the pixel centres as nest2ang+ang2vec give them [healpix_utils.c:133-141,700-748]
+  double inv_sz;
+  double cd, sd;      // cos/sin of the pixel spacing pi/2/nr
+};
+
+// transport angle from unit vector v (with phi-hat numerator p = (-vy, vx, 0)) to unit vector r;
+// inv_norm = 1 / (sin(theta_v) sin(theta_r))
+CLB_HD void paratrans_angle_unit(const double v[3], const double r[3], double inv_norm, double &cospsi, double &sinpsi)
+{
+  const double ux = v[1] * r[2] - v[2] * r[1], uy = v[2] * r[0] - v[0] * r[2], uz = v[0] * r[1] - v[1] * r[0];
+  const double c = v[0] * r[0] + v[1] * r[1] + v[2] * r[2];
+  const double up = (uy * v[0] - ux * v[1]) / (1.0 + c);
+  const double e0 = -c * v[1] - uz * v[0] + ux * up;
+  const double e1 = c * v[0] - uz * v[1] + uy * up;
+  const double e2 = (ux * v[0] + uy * v[1]) + uz * up;
+  const double rxy2 = r[0] * r[0] + r[1] * r[1];
+  sinpsi = (r[2] * (e0 * r[0] + e1 * r[1]) - e2 * rxy2) * inv_norm;
+  cospsi = (e1 * r[0] - e0 * r[1]) * inv_norm;
+}
+
+#if defined(__CUDACC__)
+// get_interpol (healpix_utils.c:971-1043) with the two ring colatitudes read from the table; additionally returns
+// the two rings the stencil lives on.  Every expression that feeds an index or a weight is the reference's.
+__device__ __forceinline__ void get_interpol_tab(double theta, double phi, long pix[4], double wgt[4], long order,
+                                                 const RingTab *__restrict__ tab, long &ringA, long &ringB)
+{
+  long nside = 1L << order;
+  long npix = 12L * (1L << (2 * order));
+  double z = cos(theta);
+  long ir1 = ring_above(z, order);
+  long ir2 = ir1 + 1;
+  double theta1 = 0.0, theta2 = 0.0, w1, tmp, dphi;
+  long i1, i2;
+  if (ir1 > 0) {
+    RingInfo ri = ring_info(ir1, order);
+    theta1 = tab[ir1].theta;
+    dphi = 2.0 * CLB_PI / ri.ringpix;
+    tmp = (phi / dphi - .5 * ri.shifted);
+    i1 = (tmp < 0) ? ((long)(tmp)) - 1 : (long)(tmp);
+    w1 = (phi - (i1 + .5 * ri.shifted) * dphi) / dphi;
+    i2 = i1 + 1;
+    if (i1 < 0) i1 += ri.ringpix;
+    if (i2 >= ri.ringpix) i2 -= ri.ringpix;
+    pix[0] = ri.startpix + i1; pix[1] = ri.startpix + i2;
+    wgt[0] = 1 - w1; wgt[1] = w1;
+  }
+  if (ir2 < (4 * nside)) {
+    RingInfo ri = ring_info(ir2, order);
+    theta2 = tab[ir2].theta;
+    dphi = 2.0 * CLB_PI / ri.ringpix;
+    tmp = (phi / dphi - .5 * ri.shifted);
+    i1 = (tmp < 0) ? ((long)(tmp)) - 1 : (long)(tmp);
+    w1 = (phi - (i1 + .5 * ri.shifted) * dphi) / dphi;
+    i2 = i1 + 1;
+    if (i1 < 0) i1 += ri.ringpix;
+    if (i2 >= ri.ringpix) i2 -= ri.ringpix;
+    pix[2] = ri.startpix + i1; pix[3] = ri.startpix + i2;
+    wgt[2] = 1 - w1; wgt[3] = w1;
+  }
+  ringA = ir1; ringB = ir2;
+  if (ir1 == 0) {
+    double wtheta = theta / theta2;
+    wgt[2] *= wtheta; wgt[3] *= wtheta;
+    double fac = (1 - wtheta) * 0.25;
+    wgt[0] = fac; wgt[1] = fac; wgt[2] += fac; wgt[3] += fac;
+    pix[0] = (pix[2] + 2) % 4;
+    pix[1] = (pix[3] + 2) % 4;
+    ringA = 1;
+  } else if (ir2 == 4 * nside) {
+    double wtheta = (theta - theta1) / (CLB_PI - theta1);
+    wgt[0] *= (1 - wtheta); wgt[1] *= (1 - wtheta);
+    double fac = wtheta * 0.25;
+    wgt[0] += fac; wgt[1] += fac; wgt[2] = fac; wgt[3] = fac;
+    pix[2] = ((pix[0] + 2) & 3) + npix - 4;
+    pix[3] = ((pix[1] + 2) & 3) + npix - 4;
+    ringB = 4 * nside - 1;
+  } else {
+    double wtheta = (theta - theta1) / (theta2 - theta1);
+    wgt[0] *= (1 - wtheta); wgt[1] *= (1 - wtheta);
+    wgt[2] *= wtheta; wgt[3] *= wtheta;
+  }
+}
+
+__device__ __forceinline__ void ray_interp_accumulate_fast(Ray &ray, long order, const RingTab *__restrict__ tab,
+                                                           const float *__restrict__ m_phi, const float *__restrict__ m_gt,
+                                                           const float *__restrict__ m_gp, const float *__restrict__ m_gtt,
+                                                           const float *__restrict__ m_gtp, const float *__restrict__ m_gpp)
+{
+  double theta, phi, wgt[4];
+  long pix[4], ring[2];
+  vec2ang(ray.n, theta, phi);
+  get_interpol_tab(theta, phi, pix, wgt, order, tab, ring[0], ring[1]);
+  const long npix_map = 12L << (2 * order);
+  // ray-side quantities shared by the four transports
+  const double inv_r = 1.0 / sqrt(ray.n[0] * ray.n[0] + ray.n[1] * ray.n[1] + ray.n[2] * ray.n[2]);
+  const double rv[3] = {ray.n[0] * inv_r, ray.n[1] * inv_r, ray.n[2] * inv_r};
+  const double inv_sr = 1.0 / sqrt((1.0 - rv[2]) * (1.0 + rv[2]));
+  double pot = 0.0, gtheta = 0.0, gphi = 0.0, t00 = 0.0, t01 = 0.0, t10 = 0.0, t11 = 0.0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const RingTab rt = tab[ring[h]];
+    const RingInfo ri = ring_info(ring[h], order);
+    long p0 = pix[2 * h], p1 = pix[2 * h + 1];
+    // a ray with a non-finite position would index outside the maps; the reference aborts on a missing cell
+    // (shtpoissonsolve.c:683-689) -- here the gather is kept in bounds and the NaNs stay visible in the ray
+    if (!(p0 >= 0 && p0 < npix_map)) p0 = 0;
+    if (!(p1 >= 0 && p1 < npix_map)) p1 = 0;
+    // azimuth of the first pixel: (j + shifted/2) * 2 pi / ringpix; the second one is one pixel spacing further
+    // (modulo the ring), i.e. a rotation by the tabulated (cd, sd)
+    const long j0 = p0 - ri.startpix;
+    double s0, c0;
+    sincospi((double)(2 * j0 + ri.shifted) / (double)ri.ringpix, &s0, &c0);
+    const double c1 = c0 * rt.cd - s0 * rt.sd, s1 = s0 * rt.cd + c0 * rt.sd;
+    const double inv_norm = rt.inv_sz * inv_sr;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const long p = k ? p1 : p0;
+      const double w = wgt[2 * h + k];
+      const double v[3] = {rt.sz * (k ? c1 : c0), rt.sz * (k ? s1 : s0), rt.cz};
+      double c, s;
+      paratrans_angle_unit(v, rv, inv_norm, c, s);
+      pot += m_phi[p] * w;
+      const double tv0 = m_gt[p], tv1 = m_gp[p];
+      gtheta += (tv0 * c + tv1 * s) * w;
+      gphi += (tv1 * c - tv0 * s) * w;
+      const double T00 = m_gtt[p], T01 = m_gtp[p], T11 = m_gpp[p];
+      // R^T T R with R = [[c, -s], [s, c]], T symmetric                       [rot_paratrans.c:251-270]
+      const double a0 = T00 * c + T01 * s, a1 = T01 * c - T00 * s;   // row 0 of T R
+      const double b0 = T01 * c + T11 * s, b1 = T11 * c - T01 * s;   // row 1 of T R
+      t00 += (c * a0 + s * b0) * w; t01 += (c * a1 + s * b1) * w;
+      t10 += (c * b0 - s * a0) * w; t11 += (c * b1 - s * a1) * w;
+    }
+  }
+  ray.phi = pot;
+  ray.alpha[0] += -1.0 * gtheta;
+  ray.alpha[1] += -1.0 * gphi;
+  ray.U[0] += t00; ray.U[1] += t01; ray.U[2] += t10; ray.U[3] += t11;
+}
+#endif
+
 // One lens-plane step of one ray: wp = w_{p+1}, wpm1 = w_p, wpm2 = w_{p-1} (the reference's argument names).
 //                                        [rayprop.c:18-189 rayprop_sphere (non-BORNAPPRX branch),
 //                                         rot_paratrans.c:17-45 generate_rotmat_axis_angle_countercw]
@@ -176,7 +326,17 @@ CLB_HD void ray_propagate(Ray &ray, double wp, double wpm1, double wpm2)
                       + (wpm1 * (wp - wpm2) / wp / (wpm1 - wpm2)) * ray.A[m + 2 * n]
                       - ((wp - wpm1) / wp) * (ray.U[0 + 2 * n] * ray.A[m + 2 * 0] + ray.U[1 + 2 * n] * ray.A[m + 2 * 1]);
   double c, s, T[2][2], RT[2][2];
+#if defined(__CUDA_ARCH__)
+  {
+    const double i0 = 1.0 / sqrt(ray.n[0] * ray.n[0] + ray.n[1] * ray.n[1] + ray.n[2] * ray.n[2]);
+    const double i1 = 1.0 / sqrt(np[0] * np[0] + np[1] * np[1] + np[2] * np[2]);
+    const double v0[3] = {ray.n[0] * i0, ray.n[1] * i0, ray.n[2] * i0}, v1[3] = {np[0] * i1, np[1] * i1, np[2] * i1};
+    const double inv_norm = 1.0 / sqrt((1.0 - v1[2]) * (1.0 + v1[2]) * (1.0 - v0[2]) * (1.0 + v0[2]));
+    paratrans_angle_unit(v0, v1, inv_norm, c, s);
+  }
+#else
   paratrans_angle(ray.n, np, c, s);
+#endif
   // Aprev <- transport(A), A <- transport(Ap)
   T[0][0] = ray.A[0]; T[0][1] = ray.A[1]; T[1][0] = ray.A[2]; T[1][1] = ray.A[3];
   transport_tensor(T, c, s, RT);

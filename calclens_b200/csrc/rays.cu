@@ -16,10 +16,46 @@ static_assert(sizeof(Ray) % 16 == 0, "ray struct must be a multiple of 16 bytes"
 
 struct RayMaps { const float *p[6]; };
 
+// per-ring table of the fast interpolation path (raymath.cuh), one per (device, map order), built on first use
+__global__ void ring_table_kernel(RingTab *__restrict__ tab, long order)
+{
+  const long ring = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long nside = 1L << order;
+  if (ring < 1 || ring > 4 * nside - 1) return;
+  const RingInfo ri = ring_info(ring, order);
+  RingTab t;
+  t.theta = atan2(ri.sintheta, ri.costheta);                  // get_interpol's theta1/theta2
+  const double th = acos(ri.costheta);                         // nest2ang returns acos(z), ang2vec takes cos of it again
+  t.cz = cos(th);
+  t.sz = sqrt((1.0 + t.cz) * (1.0 - t.cz));
+  t.inv_sz = 1.0 / t.sz;
+  const double dphi = CLB_PI_2 / (double)(ri.ringpix / 4);
+  t.cd = cos(dphi); t.sd = sin(dphi);
+  tab[ring] = t;
+}
+
+static const RingTab *ring_table(long order, cudaStream_t st)
+{
+  static RingTab *cache[16][32] = {};
+  int dev = 0;
+  CLB_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16 || order < 0 || order >= 32) { fprintf(stderr, "calclens_b200: ring_table(%d, %ld)\n", dev, order); abort(); }
+  if (!cache[dev][order]) {
+    const long n = 4L << order;
+    RingTab *t = nullptr;
+    CLB_CUDA_CHECK(cudaMalloc(&t, sizeof(RingTab) * n));
+    ring_table_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(t, order);
+    CLB_CUDA_CHECK(cudaGetLastError());
+    cache[dev][order] = t;
+  }
+  return cache[dev][order];
+}
+
 // mode bit 0: zero phi/alpha/U first (the driver's pre-solve reset, raytrace.c:213-230)
 // mode bit 1: interpolate + accumulate;  mode bit 2: propagate
 __global__ void __launch_bounds__(kRayThreads)
-ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, long order, double wp, double wpm1, double wpm2, int mode)
+ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab *__restrict__ tab, long order, double wp,
+                double wpm1, double wpm2, int mode)
 {
   __shared__ __align__(16) unsigned char s_raw[kRayThreads * sizeof(Ray)];
   Ray *s_rays = reinterpret_cast<Ray *>(s_raw);
@@ -35,7 +71,7 @@ ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, long order, do
       ray.phi = 0.0; ray.alpha[0] = 0.0; ray.alpha[1] = 0.0;
       ray.U[0] = 0.0; ray.U[1] = 0.0; ray.U[2] = 0.0; ray.U[3] = 0.0;
     }
-    if (mode & 2) ray_interp_accumulate(ray, order, maps.p[0], maps.p[1], maps.p[2], maps.p[3], maps.p[4], maps.p[5]);
+    if (mode & 2) ray_interp_accumulate_fast(ray, order, tab, maps.p[0], maps.p[1], maps.p[2], maps.p[3], maps.p[4], maps.p[5]);
     if (mode & 4) ray_propagate(ray, wp, wpm1, wpm2);
     s_rays[threadIdx.x] = ray;
   }
@@ -51,7 +87,8 @@ int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long 
   RayMaps m;
   for (int k = 0; k < 6; ++k) m.p[k] = d_maps ? d_maps[k] : nullptr;
   const long nblocks = (nrays + kRayThreads - 1) / kRayThreads;
-  ray_step_kernel<<<(unsigned)nblocks, kRayThreads, 0, st>>>(d_rays, nrays, m, order, wp, wpm1, wpm2, mode);
+  const RingTab *tab = (mode & 2) ? ring_table(order, st) : nullptr;
+  ray_step_kernel<<<(unsigned)nblocks, kRayThreads, 0, st>>>(d_rays, nrays, m, tab, order, wp, wpm1, wpm2, mode);
   CLB_CUDA_CHECK(cudaGetLastError());
   return 1;
 }

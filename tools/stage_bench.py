@@ -50,3 +50,17 @@ for r in syn:
     print("legendre_synthesis R=%d %8.3f ms  identical to first: %s" % (r, t, bool(torch.equal(b, bref))))
 t, maps = timeit(lambda: plan.ring_synthesis(bref, maps_b))
 print("ring_synthesis       %8.3f ms" % t)
+# ray stage on the maps just synthesised (scaled to lensing-like amplitudes)
+import ctypes as C
+maps = maps_b * (1e-3 / float(maps_b[3].abs().max()))
+nrays = plan.npix
+rays = torch.empty(nrays * 176, dtype=torch.uint8, device="cuda")
+L.clb_ray_init_dev(rays.data_ptr(), nrays, 0, order, 15.0, None)
+ptrs = (C.c_void_p * 6)(*[maps[k].data_ptr() for k in range(6)])
+torch.cuda.synchronize()
+def raystep():
+    L.clb_ray_init_dev(rays.data_ptr(), nrays, 0, order, 15.0, None)
+    L.clb_ray_step_dev(rays.data_ptr(), nrays, ptrs, order, 45.0, 15.0, 0.0, 7, None)
+t_both, _ = timeit(raystep)
+t_init, _ = timeit(lambda: L.clb_ray_init_dev(rays.data_ptr(), nrays, 0, order, 15.0, None))
+print("ray_step (interp+prop) %8.3f ms  (%d rays; init %.3f ms subtracted)" % (t_both - t_init, nrays, t_init))
