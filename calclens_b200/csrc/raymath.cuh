@@ -219,45 +219,52 @@ __device__ __forceinline__ void ray_interp_accumulate_fast(Ray &ray, long order,
   vec2ang(ray.n, theta, phi);
   get_interpol_tab(theta, phi, pix, wgt, order, tab, ring[0], ring[1]);
   const long npix_map = 12L << (2 * order);
+  // a ray with a non-finite position would index outside the maps; the reference aborts on a missing cell
+  // (shtpoissonsolve.c:683-689) -- here the gather is kept in bounds and the NaNs stay visible in the ray
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (!(pix[k] >= 0 && pix[k] < npix_map)) pix[k] = 0;
+  // issue the 24 gathers first: their latency hides behind the geometry below
+  float f_phi[4], f_gt[4], f_gp[4], f_gtt[4], f_gtp[4], f_gpp[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    f_phi[k] = __ldg(m_phi + pix[k]); f_gt[k] = __ldg(m_gt + pix[k]); f_gp[k] = __ldg(m_gp + pix[k]);
+    f_gtt[k] = __ldg(m_gtt + pix[k]); f_gtp[k] = __ldg(m_gtp + pix[k]); f_gpp[k] = __ldg(m_gpp + pix[k]);
+  }
   // ray-side quantities shared by the four transports
   const double inv_r = 1.0 / sqrt(ray.n[0] * ray.n[0] + ray.n[1] * ray.n[1] + ray.n[2] * ray.n[2]);
   const double rv[3] = {ray.n[0] * inv_r, ray.n[1] * inv_r, ray.n[2] * inv_r};
   const double inv_sr = 1.0 / sqrt((1.0 - rv[2]) * (1.0 + rv[2]));
-  double pot = 0.0, gtheta = 0.0, gphi = 0.0, t00 = 0.0, t01 = 0.0, t10 = 0.0, t11 = 0.0;
+  double pc[4], ps[4];   // transport angles of the four stencil pixels
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const RingTab rt = tab[ring[h]];
     const RingInfo ri = ring_info(ring[h], order);
-    long p0 = pix[2 * h], p1 = pix[2 * h + 1];
-    // a ray with a non-finite position would index outside the maps; the reference aborts on a missing cell
-    // (shtpoissonsolve.c:683-689) -- here the gather is kept in bounds and the NaNs stay visible in the ray
-    if (!(p0 >= 0 && p0 < npix_map)) p0 = 0;
-    if (!(p1 >= 0 && p1 < npix_map)) p1 = 0;
     // azimuth of the first pixel: (j + shifted/2) * 2 pi / ringpix; the second one is one pixel spacing further
     // (modulo the ring), i.e. a rotation by the tabulated (cd, sd)
-    const long j0 = p0 - ri.startpix;
+    const long j0 = pix[2 * h] - ri.startpix;
     double s0, c0;
     sincospi((double)(2 * j0 + ri.shifted) / (double)ri.ringpix, &s0, &c0);
     const double c1 = c0 * rt.cd - s0 * rt.sd, s1 = s0 * rt.cd + c0 * rt.sd;
     const double inv_norm = rt.inv_sz * inv_sr;
+    const double va[3] = {rt.sz * c0, rt.sz * s0, rt.cz}, vb[3] = {rt.sz * c1, rt.sz * s1, rt.cz};
+    paratrans_angle_unit(va, rv, inv_norm, pc[2 * h], ps[2 * h]);
+    paratrans_angle_unit(vb, rv, inv_norm, pc[2 * h + 1], ps[2 * h + 1]);
+  }
+  double pot = 0.0, gtheta = 0.0, gphi = 0.0, t00 = 0.0, t01 = 0.0, t10 = 0.0, t11 = 0.0;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const long p = k ? p1 : p0;
-      const double w = wgt[2 * h + k];
-      const double v[3] = {rt.sz * (k ? c1 : c0), rt.sz * (k ? s1 : s0), rt.cz};
-      double c, s;
-      paratrans_angle_unit(v, rv, inv_norm, c, s);
-      pot += m_phi[p] * w;
-      const double tv0 = m_gt[p], tv1 = m_gp[p];
-      gtheta += (tv0 * c + tv1 * s) * w;
-      gphi += (tv1 * c - tv0 * s) * w;
-      const double T00 = m_gtt[p], T01 = m_gtp[p], T11 = m_gpp[p];
-      // R^T T R with R = [[c, -s], [s, c]], T symmetric                       [rot_paratrans.c:251-270]
-      const double a0 = T00 * c + T01 * s, a1 = T01 * c - T00 * s;   // row 0 of T R
-      const double b0 = T01 * c + T11 * s, b1 = T11 * c - T01 * s;   // row 1 of T R
-      t00 += (c * a0 + s * b0) * w; t01 += (c * a1 + s * b1) * w;
-      t10 += (c * b0 - s * a0) * w; t11 += (c * b1 - s * a1) * w;
-    }
+  for (int k = 0; k < 4; ++k) {
+    const double w = wgt[k], c = pc[k], s = ps[k];
+    pot += f_phi[k] * w;
+    const double tv0 = f_gt[k], tv1 = f_gp[k];
+    gtheta += (tv0 * c + tv1 * s) * w;
+    gphi += (tv1 * c - tv0 * s) * w;
+    const double T00 = f_gtt[k], T01 = f_gtp[k], T11 = f_gpp[k];
+    // R^T T R with R = [[c, -s], [s, c]], T symmetric                       [rot_paratrans.c:251-270]
+    const double a0 = T00 * c + T01 * s, a1 = T01 * c - T00 * s;   // row 0 of T R
+    const double b0 = T01 * c + T11 * s, b1 = T11 * c - T01 * s;   // row 1 of T R
+    t00 += (c * a0 + s * b0) * w; t01 += (c * a1 + s * b1) * w;
+    t10 += (c * b0 - s * a0) * w; t11 += (c * b1 - s * a1) * w;
   }
   ray.phi = pot;
   ray.alpha[0] += -1.0 * gtheta;

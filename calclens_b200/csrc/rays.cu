@@ -7,6 +7,7 @@
 // shared memory so that HBM sees fully coalesced 16-byte accesses on the AoS array.
 #include "sht_internal.cuh"
 #include "raymath.cuh"
+#include <algorithm>
 
 namespace clb {
 
@@ -51,33 +52,63 @@ static const RingTab *ring_table(long order, cudaStream_t st)
   return cache[dev][order];
 }
 
+__device__ __forceinline__ void ray_cp_async16(void *smem, const void *gmem)
+{
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+
 // mode bit 0: zero phi/alpha/U first (the driver's pre-solve reset, raytrace.c:213-230)
 // mode bit 1: interpolate + accumulate;  mode bit 2: propagate
-__global__ void __launch_bounds__(kRayThreads)
+// Persistent CTAs walk the ray array in tiles of kRayThreads records; the next tile streams into the second
+// shared-memory buffer (cp.async) while the current one is being computed, and results leave through coalesced
+// 16-byte stores.
+__global__ void __launch_bounds__(kRayThreads, 4)
 ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab *__restrict__ tab, long order, double wp,
                 double wpm1, double wpm2, int mode)
 {
-  __shared__ __align__(16) unsigned char s_raw[kRayThreads * sizeof(Ray)];
-  Ray *s_rays = reinterpret_cast<Ray *>(s_raw);
-  const long first = (long)blockIdx.x * kRayThreads;
-  const int nblk = (int)min((long)kRayThreads, nrays - first);
-  const int4 *src = reinterpret_cast<const int4 *>(rays + first);
-  int4 *dst = reinterpret_cast<int4 *>(s_raw);
-  for (int i = threadIdx.x; i < nblk * kRayWords; i += kRayThreads) dst[i] = src[i];
-  __syncthreads();
-  if (threadIdx.x < nblk) {
-    Ray ray = s_rays[threadIdx.x];
-    if (mode & 1) {
-      ray.phi = 0.0; ray.alpha[0] = 0.0; ray.alpha[1] = 0.0;
-      ray.U[0] = 0.0; ray.U[1] = 0.0; ray.U[2] = 0.0; ray.U[3] = 0.0;
+  __shared__ __align__(16) unsigned char s_raw[2][kRayThreads * sizeof(Ray)];
+  const long ntiles = (nrays + kRayThreads - 1) / kRayThreads;
+  long tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  auto prefetch = [&](long t, int b) {
+    const long first = t * kRayThreads;
+    const int nblk = (int)min((long)kRayThreads, nrays - first);
+    const int4 *src = reinterpret_cast<const int4 *>(rays + first);
+    int4 *dst = reinterpret_cast<int4 *>(s_raw[b]);
+    for (int i = threadIdx.x; i < nblk * kRayWords; i += kRayThreads) ray_cp_async16(dst + i, src + i);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  prefetch(tile, 0);
+  int buf = 0;
+  for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    const long next = tile + gridDim.x;
+    if (next < ntiles) {
+      prefetch(next, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     }
-    if (mode & 2) ray_interp_accumulate_fast(ray, order, tab, maps.p[0], maps.p[1], maps.p[2], maps.p[3], maps.p[4], maps.p[5]);
-    if (mode & 4) ray_propagate(ray, wp, wpm1, wpm2);
-    s_rays[threadIdx.x] = ray;
+    __syncthreads();
+    const long first = tile * kRayThreads;
+    const int nblk = (int)min((long)kRayThreads, nrays - first);
+    Ray *s_rays = reinterpret_cast<Ray *>(s_raw[buf]);
+    if (threadIdx.x < nblk) {
+      Ray ray = s_rays[threadIdx.x];
+      if (mode & 1) {
+        ray.phi = 0.0; ray.alpha[0] = 0.0; ray.alpha[1] = 0.0;
+        ray.U[0] = 0.0; ray.U[1] = 0.0; ray.U[2] = 0.0; ray.U[3] = 0.0;
+      }
+      if (mode & 2) ray_interp_accumulate_fast(ray, order, tab, maps.p[0], maps.p[1], maps.p[2], maps.p[3], maps.p[4], maps.p[5]);
+      if (mode & 4) ray_propagate(ray, wp, wpm1, wpm2);
+      s_rays[threadIdx.x] = ray;
+    }
+    __syncthreads();
+    const int4 *ssrc = reinterpret_cast<const int4 *>(s_raw[buf]);
+    int4 *gdst = reinterpret_cast<int4 *>(rays + first);
+    for (int i = threadIdx.x; i < nblk * kRayWords; i += kRayThreads) gdst[i] = ssrc[i];
+    __syncthreads();   // the next iteration streams the tile after next into this buffer
   }
-  __syncthreads();
-  int4 *gdst = reinterpret_cast<int4 *>(rays + first);
-  for (int i = threadIdx.x; i < nblk * kRayWords; i += kRayThreads) gdst[i] = dst[i];
 }
 
 int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long order, double wp, double wpm1,
@@ -86,7 +117,14 @@ int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long 
   if (nrays <= 0) return 0;
   RayMaps m;
   for (int k = 0; k < 6; ++k) m.p[k] = d_maps ? d_maps[k] : nullptr;
-  const long nblocks = (nrays + kRayThreads - 1) / kRayThreads;
+  const long ntiles = (nrays + kRayThreads - 1) / kRayThreads;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    CLB_CUDA_CHECK(cudaGetDevice(&dev));
+    CLB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long nblocks = std::min<long>(ntiles, (long)sms * 4);
   const RingTab *tab = (mode & 2) ? ring_table(order, st) : nullptr;
   ray_step_kernel<<<(unsigned)nblocks, kRayThreads, 0, st>>>(d_rays, nrays, m, tab, order, wp, wpm1, wpm2, mode);
   CLB_CUDA_CHECK(cudaGetLastError());
