@@ -19,7 +19,7 @@ int launch_ray_init(Ray *d_rays, long nrays, long first_nest, long ray_order, do
 int launch_ray_summary(const Ray *d_rays, long nrays, double *d_out6, cudaStream_t st);
 void launch_healpix_index(int what, long order, long n, const long *in, const double *th, const double *ph, long *out, cudaStream_t st);
 void launch_healpix_interpol(long order, long n, const double *vec, long *pix, double *wgt, cudaStream_t st);
-extern int g_syn_rings_per_thread, g_ana_rings_per_thread;
+extern int g_syn_rings_per_thread, g_ana_rings_per_thread, g_fft_threads_big;
 
 static long g_launches = 0;
 
@@ -67,6 +67,7 @@ long clb_launch_count(void) { return g_launches; }
 void clb_set_tuning(int what, int value)
 {
   if (what == 0 && value >= 1 && value <= 4) g_syn_rings_per_thread = value;
+  if (what == 2 && (value == 256 || value == 512 || value == 1024)) g_fft_threads_big = value;   // read at plan creation
   if (what == 1 && (value == 1 || value == 2 || value == 4 || value == 6 || value == 8 || value == 10 || value == 12)) g_ana_rings_per_thread = value;
 }
 

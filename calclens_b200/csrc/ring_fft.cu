@@ -25,10 +25,11 @@
 
 namespace clb {
 
-struct FftClass {
-  int logM;          // work length M = 1 << logM
-  int bluestein;     // 0: r == M direct power-of-two path
-  int rmax;          // largest r in the class (sizes shared memory)
+struct FftClass {   // one launch group: ring pairs that share a shared-memory footprint
+  int logM;          // largest work length in the group, Mmax = 1 << logM
+  int bluestein;     // group key only (groups with logM <= kSmallLogM mix both paths)
+  int rmax;          // largest r in the group (sizes shared memory)
+  int tail;          // float2 entries behind bufB
   int count;         // ring pairs in the class (local ones only)
   int *d_rp = nullptr;   // [count] global ring-pair indices
   int threads;
@@ -43,6 +44,12 @@ struct FftTables {
   long *d_bhat_off = nullptr;    // [nside+1] offset of bhat_r (M(r) entries, bit-reversed order, includes 1/M)
   double2 *d_chirp = nullptr;
   double2 *d_bhat = nullptr;
+  // half-pixel phase factors exp(+i pi k / n), k = 0 .. n/2, one run per polar ring pair and one shared by all
+  // equatorial ones; formed with exactly the expression the reference uses per call (healpix_shtrans.c:186-197)
+  double2 *d_phase = nullptr;
+  long *d_phase_off = nullptr;   // [nrp]
+  signed char *d_rp_logM = nullptr;   // [nrp] work length per ring pair
+  signed char *d_rp_blu = nullptr;    // [nrp] 1: Bluestein
   std::vector<FftClass> classes;
 };
 
@@ -226,6 +233,31 @@ __global__ void bluestein_table_kernel(const int *__restrict__ rlist, const long
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// plan-time: phase tables
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void phase_table_kernel(const int *__restrict__ nphi, const long *__restrict__ phase_off, int nrp, int nside,
+                                   double2 *__restrict__ phase)
+{
+  const int rp = blockIdx.x;
+  const int n = nphi[rp];
+  if (n == 4 * nside && rp != nside - 1) return;   // equatorial rings share the run of the first one
+  double2 *t = phase + phase_off[rp];
+  for (int k = threadIdx.x; k <= n / 2; k += blockDim.x) {
+    const double ang = __ddiv_rn(__dmul_rn((double)k, CLB_PI), (double)n);
+    t[k] = make_double2(cos(ang), sin(ang));
+  }
+}
+// exp(-i pi x / n) for any integer x >= 0 from the table T[k] = exp(+i pi k / n), k <= n/2 (exact symmetries)
+__device__ __forceinline__ double2 phase_neg(const double2 *__restrict__ T, long x, int n)
+{
+  x %= 2L * n;
+  if (2 * x <= n) return cconj(__ldg(&T[x]));
+  if (x <= n) { const double2 t = __ldg(&T[n - x]); return make_double2(-t.x, -t.y); }
+  if (2 * x <= 3L * n) { const double2 t = __ldg(&T[x - n]); return make_double2(-t.x, t.y); }
+  return __ldg(&T[2L * n - x]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // analysis kernel: one CTA per (ring pair in class, hemisphere)
 // ---------------------------------------------------------------------------------------------------------------
 struct RingGeomDev {
@@ -236,17 +268,21 @@ struct RingGeomDev {
 
 __global__ void ring_analysis_kernel(const float *__restrict__ map, double2 *__restrict__ g_send, RingGeomDev geo,
                                      const int *__restrict__ class_rp, const int *__restrict__ rp_to_local,
-                                     const long *__restrict__ m_goff, int lmax, int logM, int bluestein,
+                                     const long *__restrict__ m_goff, int lmax, const signed char *__restrict__ rp_logM,
+                                     const signed char *__restrict__ rp_blu, int Mmax,
                                      const long *__restrict__ chirp_off, const long *__restrict__ bhat_off,
                                      const double2 *__restrict__ chirp_all, const double2 *__restrict__ bhat_all,
-                                     const double2 *__restrict__ tw, int logTW)
+                                     const double2 *__restrict__ tw, int logTW, const double2 *__restrict__ phase_all,
+                                     const long *__restrict__ phase_off)
 {
   extern __shared__ double2 smem[];
   const int rp = class_rp[blockIdx.x >> 1];
   const int hemi = blockIdx.x & 1;
   const int n = geo.nphi[rp];
   const int r = n >> 2;
+  const int logM = rp_logM[rp], bluestein = rp_blu[rp];
   const int M = 1 << logM;
+  const double2 *PT = phase_all + phase_off[rp];
   const long start = hemi ? geo.startS[rp] : geo.startN[rp];
   const int slot = 2 * rp_to_local[rp] + hemi;
   if (start < 0) {   // equator has no southern partner: its slot carries zeros
@@ -254,7 +290,7 @@ __global__ void ring_analysis_kernel(const float *__restrict__ map, double2 *__r
     return;
   }
   double2 *bufA = smem;          // [M]
-  double2 *bufB = smem + M;      // [r]  first spectrum, natural order
+  double2 *bufB = smem + Mmax;   // [r]  first spectrum, natural order
   const double w = geo.weight[rp];
   const double2 *chirp = bluestein ? chirp_all + chirp_off[r] : nullptr;
   const double2 *bhat = bluestein ? bhat_all + bhat_off[r] : nullptr;
@@ -326,7 +362,7 @@ __global__ void ring_analysis_kernel(const float *__restrict__ map, double2 *__r
     double2 X2 = make_double2(0.5 * (z2.x + z2c.x), 0.5 * (z2.y + z2c.y));
     double2 d2 = csub(z2, z2c);
     double2 X3 = make_double2(0.5 * d2.y, -0.5 * d2.x);
-    double2 W1 = unit_pi(-2L * mind, n);
+    double2 W1 = phase_neg(PT, 2L * mind, n);
     double2 W2 = cmul(W1, W1);
     double2 W3 = cmul(W1, W2);
     double2 F = cadd(cadd(X0, cmul(W1, X1)), cadd(cmul(W2, X2), cmul(W3, X3)));
@@ -349,8 +385,8 @@ __global__ void ring_analysis_kernel(const float *__restrict__ map, double2 *__r
     double gi = (double)__double2float_rn(F.y);
     if (conj_it) gi = -gi;
     if (shifted) {                                                  // [map2alm_transpose_mpi.c:255-271]
-      double ang = __ddiv_rn(__dmul_rn((double)m, CLB_PI), (double)n);
-      double p0 = cos(ang), p1 = -sin(ang);
+      const double2 ph = phase_neg(PT, m, n);                       // exp(-i m pi / n)
+      double p0 = ph.x, p1 = ph.y;
       double t0 = __dsub_rn(__dmul_rn(gr, p0), __dmul_rn(gi, p1));
       double t1 = __dadd_rn(__dmul_rn(gr, p1), __dmul_rn(gi, p0));
       gr = t0; gi = t1;
@@ -367,29 +403,59 @@ __global__ void ring_analysis_kernel(const float *__restrict__ map, double2 *__r
 __device__ __forceinline__ float2 fold_bin(const double2 *__restrict__ b_recv, const long *__restrict__ m_boff,
                                            long fslot, int k, int n, int lmax, int shifted)
 {
+  // The contributions to bin k come from m = k, n-k, n+k, 2n-k, 2n+k, ... (k > 0) or m = 0, n, n, 2n, 2n, ...
+  // (k = 0): term t >= 0 has m_t = (t+1)/2 * n + (t odd ? -k : +k) for k > 0; positive-m terms (t even) add b,
+  // negative-m terms (t odd) add conj(b).  Sign: skfact = -1 when the ring is shifted and the wrap count is odd
+  // (wrap count = j for the positive term of round j, j+1 for the negative one).
   float re = 0.f, im = 0.f;
-  auto add_pos = [&](long m, long j) {                              // [alm2allmaps_transpose_mpi.c:836-854]
-    double2 b = __ldg(&b_recv[m_boff[m] + fslot]);
-    double sk = (shifted && (j & 1)) ? -1.0 : 1.0;                  // l = (m - mp)/n = j
-    re = __double2float_rn(__dadd_rn((double)re, __dmul_rn(b.x, sk)));
-    im = __double2float_rn(__dadd_rn((double)im, __dmul_rn(b.y, sk)));
+  auto term_m = [&](int t) -> long {
+    if (k == 0) return (long)((t + 1) >> 1) * n;
+    return (long)((t + 1) >> 1) * n + ((t & 1) ? -k : k);
   };
-  auto add_neg = [&](long m, long j) {                              // [alm2allmaps_transpose_mpi.c:857-881]
-    double2 b = __ldg(&b_recv[m_boff[m] + fslot]);
-    double sk = (shifted && ((j + 1) & 1)) ? -1.0 : 1.0;            // l = (-m - mp)/n = -(j+1)
+  auto apply = [&](int t, double2 b) {
+    const int wraps = (t + 1) >> 1;                                 // [alm2allmaps_transpose_mpi.c:836-881]
+    const double sk = (shifted && (wraps & 1)) ? -1.0 : 1.0;
     re = __double2float_rn(__dadd_rn((double)re, __dmul_rn(b.x, sk)));
-    im = __double2float_rn(__dsub_rn((double)im, __dmul_rn(b.y, sk)));
+    if (t & 1) im = __double2float_rn(__dsub_rn((double)im, __dmul_rn(b.y, sk)));
+    else im = __double2float_rn(__dadd_rn((double)im, __dmul_rn(b.y, sk)));
   };
+  // k = 0 visits m = 0 once (positive term only), every later multiple of n twice (positive, then negative)
+  int t = 0;
   if (k == 0) {
-    add_pos(0, 0);
-    for (long j = 1; j * n <= lmax; ++j) { add_pos(j * n, j); add_neg(j * n, j - 1); }
-  } else {
-    for (long j = 0;; ++j) {
-      long mp = k + j * n, mn = (j + 1) * n - k;
-      if (mp > lmax) break;
-      add_pos(mp, j);
-      if (mn > lmax) break;
-      add_neg(mn, j);
+    apply(0, __ldg(&b_recv[m_boff[0] + fslot]));
+    for (long j = 1; j * n <= lmax; j += 4) {
+      double2 b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long m = (j + u) * n;
+        b[u] = (m <= lmax) ? __ldg(&b_recv[m_boff[m] + fslot]) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if ((j + u) * n > lmax) break;
+        // positive term of round j (wraps = j), then the negative term -j*n (wraps = j as well: l = (-m - 0)/n = -j)
+        const double sk = (shifted && ((j + u) & 1)) ? -1.0 : 1.0;
+        re = __double2float_rn(__dadd_rn((double)re, __dmul_rn(b[u].x, sk)));
+        im = __double2float_rn(__dadd_rn((double)im, __dmul_rn(b[u].y, sk)));
+        const double sk2 = (shifted && ((j + u - 1 + 1) & 1)) ? -1.0 : 1.0;
+        re = __double2float_rn(__dadd_rn((double)re, __dmul_rn(b[u].x, sk2)));
+        im = __double2float_rn(__dsub_rn((double)im, __dmul_rn(b[u].y, sk2)));
+      }
+    }
+    return make_float2(re, im);
+  }
+  for (;; t += 8) {
+    if (term_m(t) > lmax) break;
+    double2 b[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const long m = term_m(t + u);
+      b[u] = (m <= lmax) ? __ldg(&b_recv[m_boff[m] + fslot]) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (term_m(t + u) > lmax) return make_float2(re, im);   // terms are visited in ascending m: the first miss ends the bin
+      apply(t + u, b[u]);
     }
   }
   return make_float2(re, im);
@@ -401,10 +467,12 @@ struct MapPtrs { float *p[6]; };
 // reused as park).  On the Bluestein path the bins Y overlay bufA[M/2..M), which is unused until the zero fill.
 __global__ void ring_synthesis_kernel(const double2 *__restrict__ b_recv, MapPtrs maps, RingGeomDev geo,
                                       const int *__restrict__ class_rp, const int *__restrict__ rp_to_local,
-                                      const long *__restrict__ m_boff, int nslot_loc, int lmax, int logM, int bluestein,
-                                      int rmax, const long *__restrict__ chirp_off, const long *__restrict__ bhat_off,
-                                      const double2 *__restrict__ chirp_all, const double2 *__restrict__ bhat_all,
-                                      const double2 *__restrict__ tw, int logTW)
+                                      const long *__restrict__ m_boff, int nslot_loc, int lmax,
+                                      const signed char *__restrict__ rp_logM, const signed char *__restrict__ rp_blu,
+                                      int Mmax, int rmax, const long *__restrict__ chirp_off,
+                                      const long *__restrict__ bhat_off, const double2 *__restrict__ chirp_all,
+                                      const double2 *__restrict__ bhat_all, const double2 *__restrict__ tw, int logTW,
+                                      const double2 *__restrict__ phase_all, const long *__restrict__ phase_off)
 {
   extern __shared__ double2 smem[];
   const int field = blockIdx.y;
@@ -414,12 +482,14 @@ __global__ void ring_synthesis_kernel(const double2 *__restrict__ b_recv, MapPtr
   if (start < 0) return;
   const int n = geo.nphi[rp];
   const int r = n >> 2;
+  const int logM = rp_logM[rp], bluestein = rp_blu[rp];
   const int M = 1 << logM;
+  const double2 *PT = phase_all + phase_off[rp];
   const int shifted = geo.shifted[rp];
   const long fslot = (long)field * nslot_loc + 2 * rp_to_local[rp] + hemi;
   double2 *bufA = smem;
-  double2 *bufB = smem + M;
-  float2 *tailbuf = reinterpret_cast<float2 *>(smem + M + rmax + 1);
+  double2 *bufB = smem + Mmax;
+  float2 *tailbuf = reinterpret_cast<float2 *>(smem + Mmax + rmax + 1);
   float2 *Y = bluestein ? reinterpret_cast<float2 *>(smem + (M >> 1)) : tailbuf;
   float2 *park = tailbuf;
   const double2 *chirp = bluestein ? chirp_all + chirp_off[r] : nullptr;
@@ -429,8 +499,8 @@ __global__ void ring_synthesis_kernel(const double2 *__restrict__ b_recv, MapPtr
   for (int k = threadIdx.x; k <= 2 * r; k += blockDim.x) {
     float2 y = fold_bin(b_recv, m_boff, fslot, k, n, lmax, shifted);
     if (shifted) {                                                  // [healpix_shtrans.c:186-197]
-      double ang = __ddiv_rn(__dmul_rn((double)k, CLB_PI), (double)n);
-      double c = cos(ang), s = sin(ang);
+      const double2 ph = __ldg(&PT[k]);                             // (cos, sin)(k pi / n), tabulated at plan time
+      double c = ph.x, s = ph.y;
       double t0 = (double)y.x, t1 = (double)y.y;
       y.x = __double2float_rn(__dsub_rn(__dmul_rn(t0, c), __dmul_rn(t1, s)));
       y.y = __double2float_rn(__dadd_rn(__dmul_rn(t1, c), __dmul_rn(t0, s)));
@@ -476,7 +546,7 @@ __global__ void ring_synthesis_kernel(const double2 *__restrict__ b_recv, MapPtr
     double2 s02 = cadd(y[0], y[2]), d02 = csub(y[0], y[2]), s13 = cadd(y[1], y[3]), d13 = csub(y[1], y[3]);
     double2 T0 = cadd(s02, s13), T2 = csub(s02, s13);
     double2 T1 = cadd(d02, mul_pi(d13)), T3 = csub(d02, mul_pi(d13));
-    double2 E1 = unit_pi(2L * k0, n), E2 = cmul(E1, E1), E3 = cmul(E1, E2);
+    double2 E1 = __ldg(&PT[2 * k0]), E2 = cmul(E1, E1), E3 = cmul(E1, E2);   // exp(2 pi i k0 / n)
     double2 U1 = cmul(T1, E1), U2 = cmul(T2, E2), U3 = cmul(T3, E3);
     double2 v1 = cconj(cadd(T0, mul_pi(U1)));
     double2 v2 = cconj(cadd(U2, mul_pi(U3)));
@@ -553,6 +623,17 @@ __global__ void ring_cot_terms_kernel(MapPtrs maps, RingGeomDev geo, const int *
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
+int g_fft_threads_big = 512;   // threads per CTA for work lengths >= 4096 (clb_set_tuning(2, .))
+
+template <typename T>
+static T *to_dev(const std::vector<T> &v)
+{
+  T *d = nullptr;
+  CLB_CUDA_CHECK(cudaMalloc(&d, sizeof(T) * std::max<size_t>(v.size(), 1)));
+  if (!v.empty()) CLB_CUDA_CHECK(cudaMemcpy(d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  return d;
+}
+
 static int ilog2_ceil(long v) { int l = 0; while ((1L << l) < v) ++l; return l; }
 
 static RingGeomDev geom_of(const ShtPlan *p)
@@ -569,6 +650,7 @@ void fft_tables_destroy(ShtPlan *p)
   if (!t) return;
   for (auto &c : t->classes) cudaFree(c.d_rp);
   cudaFree(t->d_tw); cudaFree(t->d_chirp_off); cudaFree(t->d_bhat_off); cudaFree(t->d_chirp); cudaFree(t->d_bhat);
+  cudaFree(t->d_phase); cudaFree(t->d_phase_off); cudaFree(t->d_rp_logM); cudaFree(t->d_rp_blu);
   delete t;
   p->fft = nullptr;
 }
@@ -580,22 +662,43 @@ void fft_tables_create(ShtPlan *p)
   const long nside = p->nside;
   // classes over the local ring pairs
   struct Key { int logM, blu; };
+  constexpr int kSmallLogM = 11;   // every ring with M <= 2048 goes into one launch (they are latency bound one by one)
   std::vector<std::vector<int>> members;
   std::vector<Key> keys;
   int maxLogM = 1;
   std::vector<int> need_r;   // distinct non-power-of-two r among local rings
   std::vector<char> seen(nside + 1, 0);
+  std::vector<signed char> rp_logM(p->nrp, 0), rp_blu(p->nrp, 0);
+  for (int rp = 0; rp < p->nrp; ++rp) {
+    int r = p->h_nphi[rp] / 4;
+    int pow2 = (r & (r - 1)) == 0;
+    rp_logM[rp] = (signed char)(pow2 ? ilog2_ceil(r) : ilog2_ceil(2L * r - 1));
+    rp_blu[rp] = (signed char)!pow2;
+  }
   for (int i = 0; i < p->nrp_loc; ++i) {
     int rp = p->rp_loc[i];
     int r = p->h_nphi[rp] / 4;
-    int pow2 = (r & (r - 1)) == 0;
-    int logM = pow2 ? ilog2_ceil(r) : ilog2_ceil(2L * r - 1);
+    int pow2 = !rp_blu[rp];
+    int logM = rp_logM[rp];
     maxLogM = std::max(maxLogM, logM);
+    Key key = (logM <= kSmallLogM) ? Key{kSmallLogM, 2} : Key{logM, !pow2};
     size_t k = 0;
-    for (; k < keys.size(); ++k) if (keys[k].logM == logM && keys[k].blu == !pow2) break;
-    if (k == keys.size()) { keys.push_back({logM, !pow2}); members.emplace_back(); }
+    for (; k < keys.size(); ++k) if (keys[k].logM == key.logM && keys[k].blu == key.blu) break;
+    if (k == keys.size()) { keys.push_back(key); members.emplace_back(); }
     members[k].push_back(rp);
     if (!pow2 && !seen[r]) { seen[r] = 1; need_r.push_back(r); }
+  }
+  t->d_rp_logM = to_dev(rp_logM); t->d_rp_blu = to_dev(rp_blu);
+  // phase tables: polar ring pair rp (r = rp+1 < nside) owns entries [r*r-1, r*r+2r], the equatorial ones share a run
+  {
+    std::vector<long> poff(p->nrp);
+    const long eq_off = nside * nside - 1;
+    for (int rp = 0; rp < p->nrp; ++rp) { long r = p->h_nphi[rp] / 4; poff[rp] = (rp + 1 < nside) ? r * r - 1 : eq_off; }
+    const long total = eq_off + 2 * nside + 1;
+    t->d_phase_off = to_dev(poff);
+    CLB_CUDA_CHECK(cudaMalloc(&t->d_phase, sizeof(double2) * total));
+    phase_table_kernel<<<p->nrp, 256>>>(p->d_nphi, t->d_phase_off, p->nrp, (int)nside, t->d_phase);
+    CLB_CUDA_CHECK(cudaGetLastError());
   }
   // twiddles exp(-2 pi i k / TW), k < TW/2
   t->logTW = std::max(maxLogM, 2);
@@ -642,14 +745,19 @@ void fft_tables_create(ShtPlan *p)
   size_t max_ana = 0, max_syn = 0;
   for (size_t k = 0; k < keys.size(); ++k) {
     FftClass c;
-    c.logM = keys[k].logM; c.bluestein = keys[k].blu; c.count = (int)members[k].size();
-    c.rmax = 0;
-    for (int rp : members[k]) c.rmax = std::max(c.rmax, p->h_nphi[rp] / 4);
+    c.bluestein = keys[k].blu; c.count = (int)members[k].size();
+    c.rmax = 0; c.logM = 0; c.tail = 0;
+    for (int rp : members[k]) {
+      const int r = p->h_nphi[rp] / 4;
+      c.rmax = std::max(c.rmax, r);
+      c.logM = std::max<int>(c.logM, rp_logM[rp]);
+      c.tail = std::max(c.tail, rp_blu[rp] ? r : 2 * r + 1);
+    }
     const long M = 1L << c.logM;
     c.threads = (int)std::min<long>(256, std::max<long>(32, M / 4));
-    if (M >= 4096) c.threads = 512;
+    if (M >= 4096) c.threads = g_fft_threads_big;
     c.smem_ana = sizeof(double2) * (M + c.rmax);
-    c.smem_syn = sizeof(double2) * (M + c.rmax + 1) + sizeof(float2) * (c.bluestein ? c.rmax : 2 * c.rmax + 1);
+    c.smem_syn = sizeof(double2) * (M + c.rmax + 1) + sizeof(float2) * c.tail;
     max_ana = std::max(max_ana, c.smem_ana); max_syn = std::max(max_syn, c.smem_syn);
     CLB_CUDA_CHECK(cudaMalloc(&c.d_rp, sizeof(int) * c.count));
     CLB_CUDA_CHECK(cudaMemcpy(c.d_rp, members[k].data(), sizeof(int) * c.count, cudaMemcpyHostToDevice));
@@ -682,8 +790,8 @@ int launch_ring_analysis(const ShtPlan *p, const float *d_map, double2 *d_g_send
   int launches = 0;
   for (const auto &c : t->classes) {
     ring_analysis_kernel<<<2 * c.count, c.threads, c.smem_ana, st>>>(
-        d_map, d_g_send, geom_of(p), c.d_rp, plan_rp_to_local(p), p->d_m_goff, (int)p->lmax, c.logM, c.bluestein,
-        t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat, t->d_tw, t->logTW);
+        d_map, d_g_send, geom_of(p), c.d_rp, plan_rp_to_local(p), p->d_m_goff, (int)p->lmax, t->d_rp_logM, t->d_rp_blu,
+        1 << c.logM, t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat, t->d_tw, t->logTW, t->d_phase, t->d_phase_off);
     ++launches;
   }
   CLB_CUDA_CHECK(cudaGetLastError());
@@ -699,8 +807,9 @@ int launch_ring_synthesis(const ShtPlan *p, const double2 *d_b_recv, float *cons
   for (const auto &c : t->classes) {
     dim3 grid(2 * c.count, 6);
     ring_synthesis_kernel<<<grid, c.threads, c.smem_syn, st>>>(
-        d_b_recv, mp, geom_of(p), c.d_rp, plan_rp_to_local(p), p->d_m_boff, 2 * p->nrp_loc, (int)p->lmax, c.logM,
-        c.bluestein, c.rmax, t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat, t->d_tw, t->logTW);
+        d_b_recv, mp, geom_of(p), c.d_rp, plan_rp_to_local(p), p->d_m_boff, 2 * p->nrp_loc, (int)p->lmax, t->d_rp_logM,
+        t->d_rp_blu, 1 << c.logM, c.rmax, t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat, t->d_tw, t->logTW,
+        t->d_phase, t->d_phase_off);
     ++launches;
   }
   ring_cot_terms_kernel<<<2 * p->nrp_loc, 256, 0, st>>>(mp, geom_of(p), p->d_rp_loc);
