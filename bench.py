@@ -230,13 +230,7 @@ def make_count_maps(solver, nmaps, lmax, seed=1234, nbar=8.0, sigma=0.5):
         amp[ls < 1] = 0.0
         are[:ls.numel()] *= amp; aim[:ls.numel()] *= amp
         aim[:ls.numel()][ms == 0] = 0.0          # m = 0 coefficients are real
-        b = p.legendre_synthesis(are, aim, solver.b_send)
-        b = solver._all_to_all(solver.b_send, solver.b_recv, p.counts[2], p.counts[3])
-        if solver.nranks > 1:
-            solver.maps.zero_()
-        p.ring_synthesis(b, solver.maps)
-        if solver.nranks > 1:
-            solver.dist.all_reduce(solver.maps, group=solver.group)
+        solver.alm2allmaps(are, aim)
         g = solver.maps[0].double()
         g = g / g.std()
         counts = (nbar * torch.exp(sigma * g - 0.5 * sigma * sigma)).float()
@@ -257,6 +251,8 @@ def main():
     ap.add_argument("--ref-sample-order", type=int, default=8, help="log2 Nside of the bounded CPU sample of the reference arm")
     ap.add_argument("--cpu-baseline-order", type=int, default=9, help="log2 Nside of the cpu_baseline sample inside the GPU arm (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="multi-GPU exchange: stores into peer memory from the producing kernels, or NCCL all-to-all + all-reduce")
     a = ap.parse_args()
     if a.lmax is None:
         a.lmax = 2 * a.nside
@@ -295,7 +291,7 @@ def main():
     nrays_total = cfg["nrays"]
 
     t_setup = time.time()
-    solver = poisson.LensPlaneSolver(order, a.lmax, ray_order, dist_group=group, device=local_rank)
+    solver = poisson.LensPlaneSolver(order, a.lmax, ray_order, dist_group=group, device=local_rank, fused=(a.exchange == "fused"))
     cosmo = poisson.Cosmology(0.27)
     max_dist = 30.0 * a.planes
     pp = [poisson.plane_params(p, a.planes, max_dist, 0.27, cosmo) for p in range(a.planes)]
@@ -340,23 +336,12 @@ def main():
         p = solver.plan
         ev = []
 
-        def mark():
+        def mark(*_):
             if record:
                 e = torch.cuda.Event(enable_timing=True); e.record(); ev.append(e)
         solver.maps[0].copy_(src_maps[step % nmaps], non_blocking=True)
         mark()
-        L.clb_scale_density_dev(solver.maps[0].data_ptr(), solver.npix, float(premul), float(densmul), float(backdens), solver._stream()); mark()
-        p.ring_analysis(solver.maps[0], solver.g_send); mark()
-        g = solver._all_to_all(solver.g_send, solver.g_recv, p.counts[0], p.counts[1]); mark()
-        p.legendre_analysis(g, solver.alm_re, solver.alm_im, poisson_filter=True); mark()
-        p.legendre_synthesis(solver.alm_re, solver.alm_im, solver.b_send); mark()
-        b = solver._all_to_all(solver.b_send, solver.b_recv, p.counts[2], p.counts[3]); mark()
-        if world > 1:
-            solver.maps.zero_()
-        p.ring_synthesis(b, solver.maps); mark()
-        if world > 1:
-            dist.all_reduce(solver.maps)
-        mark()
+        solver.solve(premul, densmul, backdens, mark=lambda name: mark())
         solver.ray_update(wpp1, wp, wpm1); mark()
         return ev
 
@@ -460,6 +445,8 @@ def main():
                 "clocks": clocks,
                 "roofline": roofline, "roofline_stages": stages, "stage_ms": stage_ms,
                 "hbm_peak_source": hbm_src,
+                "exchange": ("fused peer stores (CUDA IPC over NVLink) + stream barriers" if solver.fused else
+                             "NCCL all-to-all-v + all-reduce" if world > 1 else "none (single GPU)"),
                 "cpu_baseline": cpu_baseline,
                 "setup_s": t_setup}
         real_stdout.write(json.dumps(line) + "\n")

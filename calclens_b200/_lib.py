@@ -34,6 +34,13 @@ def load():
         "clb_sht_plan_counts": (None, [vp, C.c_int, vp]),
         "clb_sht_plan_local_m": (None, [vp, vp]),
         "clb_sht_plan_local_ring_pairs": (None, [vp, vp]),
+        "clb_peer_alloc": (vp, [C.c_long]),
+        "clb_peer_free": (None, [vp]),
+        "clb_peer_export": (None, [vp, vp]),
+        "clb_peer_import": (vp, [vp]),
+        "clb_peer_release": (None, [vp]),
+        "clb_sht_plan_set_peers": (None, [vp, vp, vp]),
+        "clb_maps_broadcast_dev": (C.c_int, [vp, vp, vp, vp]),
         "clb_ring_analysis_dev": (C.c_int, [vp, vp, vp, vp]),
         "clb_legendre_analysis_dev": (C.c_int, [vp, vp, vp, vp, C.c_int, vp]),
         "clb_legendre_synthesis_dev": (C.c_int, [vp, vp, vp, vp, vp]),

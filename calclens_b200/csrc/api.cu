@@ -19,6 +19,8 @@ int launch_ray_init(Ray *d_rays, long nrays, long first_nest, long ray_order, do
 int launch_ray_summary(const Ray *d_rays, long nrays, double *d_out6, cudaStream_t st);
 void launch_healpix_index(int what, long order, long n, const long *in, const double *th, const double *ph, long *out, cudaStream_t st);
 void launch_healpix_interpol(long order, long n, const double *vec, long *pix, double *wgt, cudaStream_t st);
+void sht_plan_set_peers(ShtPlan *p, void *const *g_recv_ptrs, void *const *b_recv_ptrs);
+int launch_maps_broadcast(const ShtPlan *p, float *const local_maps[6], float *const *peer_maps, cudaStream_t st);
 extern int g_syn_rings_per_thread, g_ana_rings_per_thread, g_fft_threads_big;
 
 static long g_launches = 0;
@@ -123,6 +125,46 @@ void clb_sht_plan_local_ring_pairs(const clb_sht_plan *plan, int *rp_list)
 {
   const ShtPlan *p = P(plan);
   for (int i = 0; i < p->nrp_loc; ++i) rp_list[i] = p->rp_loc[i];
+}
+
+// ---- fused exchange over peer memory (one process per GPU on one NVLink/NVSwitch node) ----
+void *clb_peer_alloc(long bytes)
+{
+  void *p = nullptr;
+  CLB_CUDA_CHECK(cudaMalloc(&p, bytes > 0 ? (size_t)bytes : 16));
+  return p;
+}
+void clb_peer_free(void *p) { if (p) CLB_CUDA_CHECK(cudaFree(p)); }
+void clb_peer_export(void *p, void *handle64)
+{
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CLB_CUDA_CHECK(cudaIpcGetMemHandle(&h, p));
+  memcpy(handle64, &h, 64);
+}
+void *clb_peer_import(const void *handle64)
+{
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void *p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "calclens_b200: cudaIpcOpenMemHandle failed (%s): no peer access between the GPUs of this job\n",
+            cudaGetErrorString(e));
+    cudaGetLastError();
+    return nullptr;   // the caller falls back to the NCCL all-to-all exchange
+  }
+  return p;
+}
+void clb_peer_release(void *p) { if (p) CLB_CUDA_CHECK(cudaIpcCloseMemHandle(p)); }
+void clb_sht_plan_set_peers(clb_sht_plan *plan, void *const *g_recv_ptrs, void *const *b_recv_ptrs)
+{
+  sht_plan_set_peers(P(plan), g_recv_ptrs, b_recv_ptrs);
+}
+int clb_maps_broadcast_dev(const clb_sht_plan *plan, float *const local_maps[6], float *const *peer_maps, void *stream)
+{
+  int n = launch_maps_broadcast(P(plan), local_maps, peer_maps, (cudaStream_t)stream);
+  g_launches += n; return n;
 }
 
 int clb_ring_analysis_dev(const clb_sht_plan *plan, const float *map, double *g_send, void *stream)

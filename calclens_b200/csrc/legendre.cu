@@ -240,7 +240,8 @@ legendre_synthesis_kernel(const double *__restrict__ coef, const long *__restric
                           const int *__restrict__ ls_tab, const double2 *__restrict__ seed_tab,
                           const double *__restrict__ cth_rp, const double *__restrict__ sth_rp,
                           const int *__restrict__ m_loc, const long *__restrict__ b_off,
-                          const int *__restrict__ b_stride, double2 *__restrict__ b_send, int nrp, int lmax)
+                          const int *__restrict__ b_stride, double2 *__restrict__ b_send,
+                          double2 *const *__restrict__ rp_bptr, int nrp, int lmax)
 {
   __shared__ __align__(16) double s_tile[kLegWarps][2][kLB * 8];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -318,7 +319,8 @@ legendre_synthesis_kernel(const double *__restrict__ coef, const long *__restric
     if (rp >= nrp) continue;
     const double sth = sth_rp[rp], cth = cth_rp[rp];
     const double isth = 1.0 / sth, cot = cth * isth, m2s2 = m2 * isth * isth;
-    double2 *o = b_send + b_off[rp] + (long)mi * 6 * b_stride[rp];
+    // destination: this rank's send buffer, or (fused exchange) the ring owner's receive buffer over NVLink
+    double2 *o = (rp_bptr ? rp_bptr[rp] : b_send + b_off[rp]) + (long)mi * 6 * b_stride[rp];
     const long fs = b_stride[rp];
 #pragma unroll
     for (int hemi = 0; hemi < 2; ++hemi) {
@@ -398,7 +400,7 @@ int launch_legendre_synthesis(ShtPlan *p, const double *d_alm_re, const double *
 #define CLB_SYN_LAUNCH(RR)                                                                                           \
   legendre_synthesis_kernel<RR><<<grid, kLegThreads, 0, st>>>(p->d_coef, p->d_row_off, p->d_ls_syn, p->d_seed, p->d_cth, \
                                                               p->d_sth, p->d_m_loc, p->d_b_off, p->d_b_stride, d_b_send, \
-                                                              p->nrp, (int)p->lmax)
+                                                              p->d_rp_bptr, p->nrp, (int)p->lmax)
   switch (R) {
     case 4: CLB_SYN_LAUNCH(4); break;
     case 3: CLB_SYN_LAUNCH(3); break;

@@ -273,7 +273,7 @@ __global__ void ring_analysis_kernel(const float *__restrict__ map, double2 *__r
                                      const long *__restrict__ chirp_off, const long *__restrict__ bhat_off,
                                      const double2 *__restrict__ chirp_all, const double2 *__restrict__ bhat_all,
                                      const double2 *__restrict__ tw, int logTW, const double2 *__restrict__ phase_all,
-                                     const long *__restrict__ phase_off)
+                                     const long *__restrict__ phase_off, double2 *const *__restrict__ m_gptr)
 {
   extern __shared__ double2 smem[];
   const int rp = class_rp[blockIdx.x >> 1];
@@ -286,7 +286,8 @@ __global__ void ring_analysis_kernel(const float *__restrict__ map, double2 *__r
   const long start = hemi ? geo.startS[rp] : geo.startN[rp];
   const int slot = 2 * rp_to_local[rp] + hemi;
   if (start < 0) {   // equator has no southern partner: its slot carries zeros
-    for (int m = threadIdx.x; m <= lmax; m += blockDim.x) g_send[m_goff[m] + slot] = make_double2(0.0, 0.0);
+    for (int m = threadIdx.x; m <= lmax; m += blockDim.x)
+      (m_gptr ? m_gptr[m] : g_send + m_goff[m])[slot] = make_double2(0.0, 0.0);
     return;
   }
   double2 *bufA = smem;          // [M]
@@ -391,7 +392,8 @@ __global__ void ring_analysis_kernel(const float *__restrict__ map, double2 *__r
       double t1 = __dadd_rn(__dmul_rn(gr, p1), __dmul_rn(gi, p0));
       gr = t0; gi = t1;
     }
-    g_send[m_goff[m] + slot] = make_double2(gr, gi);
+    // destination: this rank's send buffer, or (fused exchange) the m owner's receive buffer over NVLink
+    (m_gptr ? m_gptr[m] : g_send + m_goff[m])[slot] = make_double2(gr, gi);
   }
 }
 
@@ -791,7 +793,8 @@ int launch_ring_analysis(const ShtPlan *p, const float *d_map, double2 *d_g_send
   for (const auto &c : t->classes) {
     ring_analysis_kernel<<<2 * c.count, c.threads, c.smem_ana, st>>>(
         d_map, d_g_send, geom_of(p), c.d_rp, plan_rp_to_local(p), p->d_m_goff, (int)p->lmax, t->d_rp_logM, t->d_rp_blu,
-        1 << c.logM, t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat, t->d_tw, t->logTW, t->d_phase, t->d_phase_off);
+        1 << c.logM, t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat, t->d_tw, t->logTW, t->d_phase, t->d_phase_off,
+        p->d_m_gptr);
     ++launches;
   }
   CLB_CUDA_CHECK(cudaGetLastError());
@@ -816,6 +819,40 @@ int launch_ring_synthesis(const ShtPlan *p, const double2 *d_b_recv, float *cons
   ++launches;
   CLB_CUDA_CHECK(cudaGetLastError());
   return launches;
+}
+
+// Fused exchange of the derivative maps: every rank stores the rings it synthesised into every peer's map buffers
+// (NVLink peer stores), replacing the ring -> domain shuffle of map_shuffle.c:22-631 by a broadcast of ring sets.
+struct PeerMaps { float *p[8][6]; };
+__global__ void ring_broadcast_kernel(MapPtrs local, PeerMaps peers, int nranks, int rank, RingGeomDev geo,
+                                      const int *__restrict__ rp_loc)
+{
+  const int rp = rp_loc[blockIdx.x >> 1];
+  const int hemi = blockIdx.x & 1;
+  const int field = blockIdx.y;
+  const long start = hemi ? geo.startS[rp] : geo.startN[rp];
+  if (start < 0) return;
+  const int n4 = geo.nphi[rp] >> 2;
+  const float4 *src = reinterpret_cast<const float4 *>(local.p[field] + start);
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const float4 v = src[i];
+    for (int q = 0; q < nranks; ++q)
+      if (q != rank) reinterpret_cast<float4 *>(peers.p[q][field] + start)[i] = v;
+  }
+}
+
+int launch_maps_broadcast(const ShtPlan *p, float *const local_maps[6], float *const *peer_maps, cudaStream_t st)
+{
+  if (p->nranks <= 1 || p->nrp_loc == 0) return 0;
+  if (p->nranks > 8) { fprintf(stderr, "calclens_b200: map broadcast supports up to 8 ranks per node\n"); abort(); }
+  MapPtrs loc; PeerMaps peers;
+  for (int k = 0; k < 6; ++k) loc.p[k] = local_maps[k];
+  for (int q = 0; q < 8; ++q)
+    for (int k = 0; k < 6; ++k) peers.p[q][k] = (q < p->nranks) ? peer_maps[q * 6 + k] : nullptr;
+  dim3 grid(2 * p->nrp_loc, 6);
+  ring_broadcast_kernel<<<grid, 256, 0, st>>>(loc, peers, p->nranks, p->rank, geom_of(p), p->d_rp_loc);
+  CLB_CUDA_CHECK(cudaGetLastError());
+  return 1;
 }
 
 }  // namespace clb

@@ -70,6 +70,10 @@ struct ShtPlan {
   long alm_total = 0;          // sum over local m of (lmax-m+1)
   std::vector<long> h_alm_off;
   long *d_alm_off = nullptr;
+  // fused exchange over peer memory (clb_sht_plan_set_peers): destination of every m's g block / every ring pair's b
+  // block inside the owning rank's receive buffer (NVLink peer pointers, or local ones for this rank's own share)
+  double2 **d_m_gptr = nullptr;    // [lmax+1]
+  double2 **d_rp_bptr = nullptr;   // [nrp]
   // FFT tables
   struct FftTables *fft = nullptr;
 };

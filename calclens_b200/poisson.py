@@ -3,12 +3,19 @@ the plane's ``rayprop_sphere`` calls (raytrace.c:256-269), on one GPU or sharded
 ``torch.distributed`` process group (one process per GPU).
 
 Sharding follows the reference: the map side of the SHT is split by ring pairs, the alm side
-by m, joined by one transpose per direction (the MPI hypercube exchange of map2alm_transpose_mpi.c:339-381 and
-alm2allmaps_transpose_mpi.c:656-724 becomes one NCCL all-to-all-v over NVLink); rays are split into contiguous NEST
-ranges, i.e. compact sky domains (cf. loadbalance.c:151-181).  Instead of the reference's ring->domain shuffle with
-halo cells (map_shuffle.c) every rank receives the six full derivative maps (an all-reduce of disjoint ring sets), so
+by m, joined by one transpose per direction (map2alm_transpose_mpi.c:339-381, alm2allmaps_transpose_mpi.c:656-724);
+rays are split into contiguous NEST ranges, i.e. compact sky domains (cf. loadbalance.c:151-181).  Instead of the
+reference's ring->domain shuffle with halo cells (map_shuffle.c) every rank receives the six full derivative maps, so
 rays never miss a map cell however far they have been deflected.
+
+Two exchange back ends:
+* fused (default on one NVLink/NVSwitch node): the receive buffers of all ranks are mapped into every process (CUDA
+  IPC) and the producing kernels -- ring-FFT epilogue, Legendre-synthesis epilogue, map broadcast -- store straight
+  into the consumer's buffers; the only collectives left are stream-ordered barriers between producer and consumer.
+* NCCL: one all-to-all-v per transpose and an all-reduce of the maps (disjoint ring sets); used when peer mapping is
+  unavailable, and by the CPU (gloo) tests of the exchange layout.
 """
+import ctypes as C
 import math
 
 import numpy as np
@@ -85,7 +92,7 @@ class LensPlaneSolver:
     """One rank's share of the per-plane hot path.  ``dist_group`` = None for a single GPU, otherwise an initialised
     torch.distributed process group (NCCL) with one rank per GPU."""
 
-    def __init__(self, sht_order, lmax=None, ray_order=None, ring_weights=None, dist_group=None, device=None):
+    def __init__(self, sht_order, lmax=None, ray_order=None, ring_weights=None, dist_group=None, device=None, fused=True):
         import torch.distributed as dist
         self.dist = dist if dist_group is not None else None
         self.group = dist_group
@@ -110,9 +117,70 @@ class LensPlaneSolver:
         self.alm_im = torch.empty(max(p.Nlm, 1), **f64)
         self.maps = torch.zeros((6, self.npix), dtype=torch.float32, device=self.device)
         self.summary = torch.zeros(6, **f64)
+        self.fused = False
+        self._peer_bufs = []
+        if self.nranks > 1 and fused:
+            self._setup_peer_exchange()
         self.rays = None
         self.nrays = 0
         self.first_nest = 0
+
+    # ---- fused exchange over peer memory ----
+    def _dev_view(self, ptr, shape, dtype):
+        """torch tensor over device memory owned by the library (CUDA array interface, zero copy)."""
+        class _Holder:
+            pass
+        h = _Holder()
+        h.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": {torch.float64: "<f8", torch.float32: "<f4"}[dtype],
+                                      "data": (int(ptr), False), "version": 2, "strides": None}
+        return torch.as_tensor(h, device=self.device)
+
+    def _setup_peer_exchange(self):
+        """Allocate the receive buffers as peer-mappable memory, exchange the IPC handles through the process group
+        and hand the peer pointers to the plan (clb_sht_plan_set_peers).  Falls back to the NCCL exchange, on all
+        ranks together, if any mapping fails."""
+        p, L = self.plan, self.lib
+        sizes = [16 * max(p.g_recv_total, 1), 16 * max(p.b_recv_total, 1), 4 * 6 * self.npix]
+        own = [L.clb_peer_alloc(n) for n in sizes]
+        handles = []
+        for ptr in own:
+            buf = C.create_string_buffer(64)
+            L.clb_peer_export(ptr, buf)
+            handles.append(buf.raw)
+        gathered = [None] * self.nranks
+        self.dist.all_gather_object(gathered, handles, group=self.group)
+        peers = [[None] * 3 for _ in range(self.nranks)]
+        ok = 1
+        for q in range(self.nranks):
+            for k in range(3):
+                if q == self.rank:
+                    peers[q][k] = own[k]
+                else:
+                    ptr = L.clb_peer_import(C.create_string_buffer(gathered[q][k], 64))
+                    if not ptr:
+                        ok = 0
+                    peers[q][k] = ptr
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)
+        self._peer_bufs = (own, peers)
+        if int(flag.item()) == 0:
+            return   # stay on the NCCL path (buffers are simply not used)
+        g_arr = (C.c_void_p * self.nranks)(*[peers[q][0] for q in range(self.nranks)])
+        b_arr = (C.c_void_p * self.nranks)(*[peers[q][1] for q in range(self.nranks)])
+        L.clb_sht_plan_set_peers(p._h, g_arr, b_arr)
+        self._peer_maps = (C.c_void_p * (6 * self.nranks))(*[peers[q][2] + 4 * self.npix * k for q in range(self.nranks) for k in range(6)])
+        self.g_recv = self._dev_view(own[0], (2 * max(p.g_recv_total, 1),), torch.float64)
+        self.b_recv = self._dev_view(own[1], (2 * max(p.b_recv_total, 1),), torch.float64)
+        self.maps = self._dev_view(own[2], (6, self.npix), torch.float32)
+        self.maps.zero_()
+        self.g_send = self.b_send = None   # producers store into the owners' receive buffers
+        self._tiny = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.fused = True
+        self.dist.barrier(group=self.group)
+
+    def _stream_barrier(self):
+        """All ranks' work enqueued so far has completed before anything enqueued afterwards starts (stream ordered)."""
+        self.dist.all_reduce(self._tiny, group=self.group)
 
     # ---- rays ----
     def init_rays(self, binL_2):
@@ -137,26 +205,65 @@ class LensPlaneSolver:
         return recv
 
     # ---- the SHT Poisson solve: counts map in self.maps[0] -> six derivative maps in self.maps ----
-    def solve(self, premul, densmul, backdens):
+    def solve(self, premul, densmul, backdens, mark=None):
+        """``mark(name)`` (optional) is called after each stage has been enqueued (bench.py records CUDA events there)."""
+        mark = mark or (lambda name: None)
         p = self.plan
         self.lib.clb_scale_density_dev(self.maps[0].data_ptr(), self.npix, float(premul), float(densmul), float(backdens),
                                        self._stream())
-        p.ring_analysis(self.maps[0], self.g_send)
-        g = self._all_to_all(self.g_send, self.g_recv, p.counts[0], p.counts[1])
-        p.legendre_analysis(g, self.alm_re, self.alm_im, poisson_filter=True)
-        p.legendre_synthesis(self.alm_re, self.alm_im, self.b_send)
+        mark("scale")
+        if self.fused:
+            # producers store into the consumers' buffers over NVLink; barriers order producer and consumer stages
+            self._stream_barrier()   # every rank is done with the previous plane's g, b and maps
+            self.lib.clb_ring_analysis_dev(p._h, self.maps[0].data_ptr(), None, self._stream()); mark("fft_analysis")
+            self._stream_barrier(); mark("a2a_g")
+            p.legendre_analysis(self.g_recv, self.alm_re, self.alm_im, poisson_filter=True); mark("legendre_analysis")
+            self.lib.clb_legendre_synthesis_dev(p._h, self.alm_re.data_ptr(), self.alm_im.data_ptr(), None, self._stream())
+            mark("legendre_synthesis")
+            self._stream_barrier(); mark("a2a_b")
+            p.ring_synthesis(self.b_recv, self.maps); mark("fft_synthesis")
+            ptrs = (C.c_void_p * 6)(*[self.maps[k].data_ptr() for k in range(6)])
+            self.lib.clb_maps_broadcast_dev(p._h, ptrs, self._peer_maps, self._stream())
+            self._stream_barrier(); mark("map_allreduce")
+            return self.maps
+        p.ring_analysis(self.maps[0], self.g_send); mark("fft_analysis")
+        g = self._all_to_all(self.g_send, self.g_recv, p.counts[0], p.counts[1]); mark("a2a_g")
+        p.legendre_analysis(g, self.alm_re, self.alm_im, poisson_filter=True); mark("legendre_analysis")
+        p.legendre_synthesis(self.alm_re, self.alm_im, self.b_send); mark("legendre_synthesis")
+        b = self._all_to_all(self.b_send, self.b_recv, p.counts[2], p.counts[3]); mark("a2a_b")
+        if self.nranks > 1:
+            self.maps.zero_()
+        p.ring_synthesis(b, self.maps); mark("fft_synthesis")
+        if self.nranks > 1:
+            self.dist.all_reduce(self.maps, group=self.group)   # disjoint ring sets: x + 0 is exact
+        mark("map_allreduce")
+        return self.maps
+
+    def alm2allmaps(self, alm_re, alm_im):
+        """alm2allmaps_mpi over the ranks of the group: local alm (this rank's m) -> the six full maps on every rank."""
+        p = self.plan
+        if self.fused:
+            self._stream_barrier()
+            self.lib.clb_legendre_synthesis_dev(p._h, alm_re.data_ptr(), alm_im.data_ptr(), None, self._stream())
+            self._stream_barrier()
+            p.ring_synthesis(self.b_recv, self.maps)
+            ptrs = (C.c_void_p * 6)(*[self.maps[k].data_ptr() for k in range(6)])
+            self.lib.clb_maps_broadcast_dev(p._h, ptrs, self._peer_maps, self._stream())
+            self._stream_barrier()
+            return self.maps
+        p.legendre_synthesis(alm_re, alm_im, self.b_send)
         b = self._all_to_all(self.b_send, self.b_recv, p.counts[2], p.counts[3])
         if self.nranks > 1:
             self.maps.zero_()
         p.ring_synthesis(b, self.maps)
         if self.nranks > 1:
-            self.dist.all_reduce(self.maps, group=self.group)   # disjoint ring sets: x + 0 is exact
+            self.dist.all_reduce(self.maps, group=self.group)
         return self.maps
 
     def ray_update(self, wpp1, wp, wpm1):
         """zero + interpolate + propagate: rayprop_sphere(planeRadPlus1, planeRad, planeRadMinus1) as called at
         raytrace.c:262, preceded by the reset of raytrace.c:213-230 and the interpolation of shtpoissonsolve.c:666-702."""
-        ptrs = (__import__("ctypes").c_void_p * 6)(*[self.maps[k].data_ptr() for k in range(6)])
+        ptrs = (C.c_void_p * 6)(*[self.maps[k].data_ptr() for k in range(6)])
         self.lib.clb_ray_step_dev(self.rays.data_ptr(), self.nrays, ptrs, self.order, float(wpp1), float(wp), float(wpm1),
                                   MODE_ZERO | MODE_INTERP | MODE_PROP, self._stream())
 

@@ -29,7 +29,8 @@ int clb_device_count(void);
 void clb_set_device(int device);
 /* kernels launched by this library since load (bench.py reports it as gpu_launches) */
 long clb_launch_count(void);
-/* tuning knobs: what = 0 synthesis rings per thread (1, 2 or 4) */
+/* tuning knobs: what = 0 synthesis rings per thread (1..4), 1 analysis rings per thread (1,2,4,6,8,10,12),
+ * 2 threads per CTA of the large ring FFTs (256, 512; read at plan creation) */
 void clb_set_tuning(int what, int value);
 
 /* ---- plan: replaces healpixsht_plan / healpixsht_destroy_plan (healpix_shtrans.c:54-160, :496-516) and
@@ -60,6 +61,27 @@ int clb_legendre_analysis_dev(clb_sht_plan *plan, const double *g_recv, double *
 int clb_legendre_synthesis_dev(clb_sht_plan *plan, const double *alm_re, const double *alm_im, double *b_send, void *stream);
 /* unpack/alias fold + phase + c2r + 1/sin scalings + cot terms :818-1147 */
 int clb_ring_synthesis_dev(const clb_sht_plan *plan, const double *b_recv, float *const maps[6], void *stream);
+
+/* ---- fused exchange over peer memory (one process per GPU, one NVLink/NVSwitch node).  It replaces the MPI
+ * hypercube transposes (map2alm_transpose_mpi.c:339-381, alm2allmaps_transpose_mpi.c:656-724) and the ring -> domain
+ * map shuffle (map_shuffle.c:22-631) by stores from the producing kernels straight into the consumer rank's buffers:
+ *   clb_peer_alloc/export/import : device buffers other ranks may map (CUDA IPC; the 64-byte handle travels through
+ *                                  whatever the host uses for bootstrap -- MPI_Allgather in CALCLENS, the
+ *                                  torch.distributed store here); import returns NULL when peer access is unavailable
+ *   clb_sht_plan_set_peers       : g_recv_ptrs[q] / b_recv_ptrs[q] = rank q's receive buffers (sizes
+ *                                  clb_sht_plan_query(6) / (8) complex doubles on rank q) as mapped into this process.
+ *                                  Afterwards clb_ring_analysis_dev ignores g_send and clb_legendre_synthesis_dev
+ *                                  ignores b_send: results land in the owners' receive buffers.  The host orders
+ *                                  producer and consumer stages with a stream barrier across ranks.
+ *   clb_maps_broadcast_dev       : store this rank's rings of the six maps into every peer's maps
+ *                                  (peer_maps[q*6+k] = map k of rank q, up to 8 ranks) ---- */
+void *clb_peer_alloc(long bytes);
+void clb_peer_free(void *p);
+void clb_peer_export(void *p, void *handle64);
+void *clb_peer_import(const void *handle64);
+void clb_peer_release(void *p);
+void clb_sht_plan_set_peers(clb_sht_plan *plan, void *const *g_recv_ptrs, void *const *b_recv_ptrs);
+int clb_maps_broadcast_dev(const clb_sht_plan *plan, float *const local_maps[6], float *const *peer_maps, void *stream);
 
 /* ---- density scaling of shtpoissonsolve.c:426,454-502 (full-sky: no vacuum cells):
  * map = (map * premul) * densmul - backdens, all in float like the reference ---- */

@@ -24,7 +24,12 @@ def main():
     rng = np.random.default_rng(77)
     counts = torch.from_numpy((8.0 * rng.lognormal(sigma=0.5, size=npix)).astype(np.float32))
     premul, densmul, backdens = np.float32(1.0), np.float32(2e-4), np.float32(8.0 * np.exp(0.125) * 2e-4)
-    solver = poisson.LensPlaneSolver(order, lmax, ray_order, dist_group=dist.group.WORLD, device=local_rank)
+    fused = os.environ.get("CLB_FUSED", "1") != "0"
+    solver = poisson.LensPlaneSolver(order, lmax, ray_order, dist_group=dist.group.WORLD, device=local_rank, fused=fused)
+    if rank == 0:
+        print("exchange:", "fused peer stores" if solver.fused else "NCCL all-to-all")
+    if fused and not solver.fused:
+        print("WARNING: fused exchange requested but peer mapping failed")
     solver.init_rays(15.0)
     planes = [(45.0, 15.0, 0.0), (75.0, 45.0, 15.0), (105.0, 75.0, 45.0)]
     sums = [solver.step(counts, premul, densmul, backdens, *pl) for pl in planes]
