@@ -46,6 +46,7 @@ def load():
         "clb_legendre_synthesis_dev": (C.c_int, [vp, vp, vp, vp, vp]),
         "clb_ring_synthesis_dev": (C.c_int, [vp, vp, vp, vp]),
         "clb_scale_density_dev": (C.c_int, [vp, C.c_long, C.c_float, C.c_float, C.c_float, vp]),
+        "clb_load_density_dev": (C.c_int, [vp, vp, vp, C.c_float, C.c_float, C.c_float, vp]),
         "clb_ray_step_dev": (C.c_int, [vp, C.c_long, vp, C.c_long, C.c_double, C.c_double, C.c_double, C.c_int, vp]),
         "clb_ray_init_dev": (C.c_int, [vp, C.c_long, C.c_long, C.c_long, C.c_double, vp]),
         "clb_ray_summary_dev": (C.c_int, [vp, C.c_long, vp, vp]),

@@ -21,6 +21,8 @@ void launch_healpix_index(int what, long order, long n, const long *in, const do
 void launch_healpix_interpol(long order, long n, const double *vec, long *pix, double *wgt, cudaStream_t st);
 void sht_plan_set_peers(ShtPlan *p, void *const *g_recv_ptrs, void *const *b_recv_ptrs);
 int launch_maps_broadcast(const ShtPlan *p, float *const local_maps[6], float *const *peer_maps, cudaStream_t st);
+int launch_load_density(const ShtPlan *p, const float *src, float *dst, float premul, float densmul, float backdens,
+                        cudaStream_t st);
 extern int g_syn_rings_per_thread, g_ana_rings_per_thread, g_fft_threads_big;
 
 static long g_launches = 0;
@@ -195,6 +197,12 @@ int clb_scale_density_dev(float *map, long npix, float premul, float densmul, fl
   scale_density_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(map, npix, premul, densmul, backdens);
   CLB_CUDA_CHECK(cudaGetLastError());
   g_launches += 1; return 1;
+}
+int clb_load_density_dev(const clb_sht_plan *plan, const float *src, float *dst, float premul, float densmul,
+                         float backdens, void *stream)
+{
+  int n = launch_load_density(P(plan), src, dst, premul, densmul, backdens, (cudaStream_t)stream);
+  g_launches += n; return n;
 }
 int clb_ray_step_dev(void *rays, long nrays, const float *const maps[6], long map_order, double wp, double wpm1,
                      double wpm2, int mode, void *stream)

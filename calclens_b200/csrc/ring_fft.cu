@@ -821,6 +821,46 @@ int launch_ring_synthesis(const ShtPlan *p, const double2 *d_b_recv, float *cons
   return launches;
 }
 
+// Density load: this rank's rings of a full-sky count map -> scaled density in a device map.  src may be device
+// memory or PINNED HOST memory (read through the unified address space, so only the rings this rank owns cross PCIe).
+//   v = (v * premul) * densmul - backdens, each step rounded to float        [shtpoissonsolve.c:426,468,478]
+__global__ void load_density_kernel(const float *__restrict__ src, float *__restrict__ dst, RingGeomDev geo,
+                                    const int *__restrict__ rp_loc, int nslots, float premul, float densmul, float backdens)
+{
+  // a few persistent CTAs walk the rings: enough loads in flight to fill a PCIe link, few enough SM slots that the
+  // kernel can run behind the previous plane's compute kernels on a high-priority stream
+  for (int slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+    const int rp = rp_loc[slot >> 1];
+    const int hemi = slot & 1;
+    const long start = hemi ? geo.startS[rp] : geo.startN[rp];
+    if (start < 0) continue;
+    const int n4 = geo.nphi[rp] >> 2;
+    const float4 *s4 = reinterpret_cast<const float4 *>(src + start);
+    float4 *d4 = reinterpret_cast<float4 *>(dst + start);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      float4 v = s4[i];
+      v.x = __fsub_rn(__fmul_rn(__fmul_rn(v.x, premul), densmul), backdens);
+      v.y = __fsub_rn(__fmul_rn(__fmul_rn(v.y, premul), densmul), backdens);
+      v.z = __fsub_rn(__fmul_rn(__fmul_rn(v.z, premul), densmul), backdens);
+      v.w = __fsub_rn(__fmul_rn(__fmul_rn(v.w, premul), densmul), backdens);
+      d4[i] = v;
+    }
+  }
+}
+int launch_load_density(const ShtPlan *p, const float *src, float *dst, float premul, float densmul, float backdens,
+                        cudaStream_t st)
+{
+  if (p->nrp_loc == 0) return 0;
+  cudaPointerAttributes attr;
+  const bool on_device = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+  cudaGetLastError();
+  const int nslots = 2 * p->nrp_loc;
+  const int grid = on_device ? std::min(nslots, 148 * 8) : std::min(nslots, 96);   // PCIe needs few CTAs, HBM many
+  load_density_kernel<<<grid, 512, 0, st>>>(src, dst, geom_of(p), p->d_rp_loc, nslots, premul, densmul, backdens);
+  CLB_CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
 // Fused exchange of the derivative maps: every rank stores the rings it synthesised into every peer's map buffers
 // (NVLink peer stores), replacing the ring -> domain shuffle of map_shuffle.c:22-631 by a broadcast of ring sets.
 struct PeerMaps { float *p[8][6]; };

@@ -117,6 +117,10 @@ class LensPlaneSolver:
         self.alm_im = torch.empty(max(p.Nlm, 1), **f64)
         self.maps = torch.zeros((6, self.npix), dtype=torch.float32, device=self.device)
         self.summary = torch.zeros(6, **f64)
+        self._dens = [torch.zeros(self.npix, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self._copy_stream = torch.cuda.Stream(device=self.device, priority=-1)   # runs behind the compute kernels, gets SM slots first
+        self._staged = None        # (host map, scalings, buffer index, ready event) of a prefetched plane
+        self._dens_free = [None, None]   # event after the last kernel that read each density buffer
         self.fused = False
         self._peer_bufs = []
         if self.nranks > 1 and fused:
@@ -205,17 +209,26 @@ class LensPlaneSolver:
         return recv
 
     # ---- the SHT Poisson solve: counts map in self.maps[0] -> six derivative maps in self.maps ----
-    def solve(self, premul, densmul, backdens, mark=None):
-        """``mark(name)`` (optional) is called after each stage has been enqueued (bench.py records CUDA events there)."""
+    def load_density(self, counts_map, premul, densmul, backdens, dst=None):
+        """Scale this rank's rings of a full-sky count map (device tensor or pinned host tensor, RING float32) into the
+        density buffer: shtpoissonsolve.c:342-502 for the raw-map input path."""
+        assert counts_map.dtype == torch.float32 and counts_map.numel() == self.npix and counts_map.is_contiguous()
+        assert counts_map.is_cuda or counts_map.is_pinned(), "host maps must be pinned (they are read by the GPU directly)"
+        dst = self._dens[0] if dst is None else dst
+        self.lib.clb_load_density_dev(self.plan._h, counts_map.data_ptr(), dst.data_ptr(), float(premul), float(densmul),
+                                      float(backdens), self._stream())
+        return dst
+
+    def solve(self, density=None, mark=None):
+        """density map (this rank's rings valid; default: the buffer load_density filled) -> six derivative maps.
+        ``mark(name)`` (optional) is called after each stage has been enqueued (bench.py records CUDA events there)."""
         mark = mark or (lambda name: None)
         p = self.plan
-        self.lib.clb_scale_density_dev(self.maps[0].data_ptr(), self.npix, float(premul), float(densmul), float(backdens),
-                                       self._stream())
-        mark("scale")
+        dens = self._dens[0] if density is None else density
         if self.fused:
             # producers store into the consumers' buffers over NVLink; barriers order producer and consumer stages
             self._stream_barrier()   # every rank is done with the previous plane's g, b and maps
-            self.lib.clb_ring_analysis_dev(p._h, self.maps[0].data_ptr(), None, self._stream()); mark("fft_analysis")
+            self.lib.clb_ring_analysis_dev(p._h, dens.data_ptr(), None, self._stream()); mark("fft_analysis")
             self._stream_barrier(); mark("a2a_g")
             p.legendre_analysis(self.g_recv, self.alm_re, self.alm_im, poisson_filter=True); mark("legendre_analysis")
             self.lib.clb_legendre_synthesis_dev(p._h, self.alm_re.data_ptr(), self.alm_im.data_ptr(), None, self._stream())
@@ -226,7 +239,7 @@ class LensPlaneSolver:
             self.lib.clb_maps_broadcast_dev(p._h, ptrs, self._peer_maps, self._stream())
             self._stream_barrier(); mark("map_allreduce")
             return self.maps
-        p.ring_analysis(self.maps[0], self.g_send); mark("fft_analysis")
+        p.ring_analysis(dens, self.g_send); mark("fft_analysis")
         g = self._all_to_all(self.g_send, self.g_recv, p.counts[0], p.counts[1]); mark("a2a_g")
         p.legendre_analysis(g, self.alm_re, self.alm_im, poisson_filter=True); mark("legendre_analysis")
         p.legendre_synthesis(self.alm_re, self.alm_im, self.b_send); mark("legendre_synthesis")
@@ -267,11 +280,39 @@ class LensPlaneSolver:
         self.lib.clb_ray_step_dev(self.rays.data_ptr(), self.nrays, ptrs, self.order, float(wpp1), float(wp), float(wpm1),
                                   MODE_ZERO | MODE_INTERP | MODE_PROP, self._stream())
 
-    def step(self, counts_map, premul, densmul, backdens, wpp1, wp, wpm1, read_summary=True):
-        """One lens plane.  ``counts_map``: RING float32 full-sky map, a device tensor or a (pinned) host tensor."""
-        self.maps[0].copy_(counts_map, non_blocking=True)
-        self.solve(premul, densmul, backdens)
+    def prefetch(self, counts_map, premul, densmul, backdens):
+        """Start loading the NEXT plane's density on the copy stream while the current plane computes: the host map is
+        read by the GPU directly (only this rank's rings), scaled, and parked in the spare density buffer."""
+        k = 1 if (self._staged is None or self._staged[2] == 0) else 0
+        cs = self._copy_stream
+        if self._dens_free[k] is not None:
+            cs.wait_event(self._dens_free[k])
+        with torch.cuda.stream(cs):
+            self.load_density(counts_map, premul, densmul, backdens, dst=self._dens[k])
+            ev = torch.cuda.Event(); ev.record(cs)
+        self._next_staged = (counts_map, (float(premul), float(densmul), float(backdens)), k, ev)
+
+    def step(self, counts_map, premul, densmul, backdens, wpp1, wp, wpm1, read_summary=True, prefetch=None):
+        """One lens plane.  ``counts_map``: RING float32 full-sky map, a device tensor or a pinned host tensor.
+        ``prefetch`` = (next_counts_map, premul, densmul, backdens) starts the next plane's load behind this plane's
+        kernels; a later step() given that same map picks the staged density up instead of loading again."""
+        st = self._staged
+        key = (float(premul), float(densmul), float(backdens))
+        if st is not None and st[0] is counts_map and st[1] == key:
+            torch.cuda.current_stream().wait_event(st[3])
+            k = st[2]
+        else:
+            k = 0 if st is None else 1 - st[2]
+            self.load_density(counts_map, premul, densmul, backdens, dst=self._dens[k])
+            self._staged = (None, None, k, None)
+        self.solve(self._dens[k])
+        ev = torch.cuda.Event(); ev.record()
+        self._dens_free[k] = ev
+        self._staged = (None, None, k, None)
         self.ray_update(wpp1, wp, wpm1)
+        if prefetch is not None:
+            self.prefetch(*prefetch)
+            self._staged = self._next_staged
         if not read_summary:
             return None
         self.lib.clb_ray_summary_dev(self.rays.data_ptr(), self.nrays, self.summary.data_ptr(), self._stream())

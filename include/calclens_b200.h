@@ -86,6 +86,11 @@ int clb_maps_broadcast_dev(const clb_sht_plan *plan, float *const local_maps[6],
 /* ---- density scaling of shtpoissonsolve.c:426,454-502 (full-sky: no vacuum cells):
  * map = (map * premul) * densmul - backdens, all in float like the reference ---- */
 int clb_scale_density_dev(float *map, long npix, float premul, float densmul, float backdens, void *stream);
+/* the same scaling while loading this rank's rings of a full-sky count map: src may be device memory or PINNED
+ * host memory (the raw map of shtpoissonsolve.c:342-436), dst is a device map; only the owned rings are read, so on
+ * N ranks each one moves 1/N of the map across PCIe */
+int clb_load_density_dev(const clb_sht_plan *plan, const float *src, float *dst, float premul, float densmul,
+                         float backdens, void *stream);
 
 /* ---- ray step.  mode bits: 1 zero phi/alpha/U (raytrace.c:213-230); 2 interpolate + accumulate
  * (shtpoissonsolve.c:666-702 with shearinterp_comp :1122-1204); 4 propagate = rayprop_sphere(wp, wpm1, wpm2, .)

@@ -22,7 +22,7 @@ def main():
     order, lmax, ray_order = 7, 256, 7
     npix = 12 << (2 * order)
     rng = np.random.default_rng(77)
-    counts = torch.from_numpy((8.0 * rng.lognormal(sigma=0.5, size=npix)).astype(np.float32))
+    counts = torch.from_numpy((8.0 * rng.lognormal(sigma=0.5, size=npix)).astype(np.float32)).pin_memory()
     premul, densmul, backdens = np.float32(1.0), np.float32(2e-4), np.float32(8.0 * np.exp(0.125) * 2e-4)
     fused = os.environ.get("CLB_FUSED", "1") != "0"
     solver = poisson.LensPlaneSolver(order, lmax, ray_order, dist_group=dist.group.WORLD, device=local_rank, fused=fused)
