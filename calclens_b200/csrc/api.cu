@@ -14,13 +14,15 @@ int launch_legendre_analysis(ShtPlan *p, const double2 *d_g_recv, double *d_alm_
                              cudaStream_t st);
 int launch_legendre_synthesis(ShtPlan *p, const double *d_alm_re, const double *d_alm_im, double2 *d_b_send, cudaStream_t st);
 int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long order, double wp, double wpm1, double wpm2,
-                    int mode, cudaStream_t st);
+                    int mode, cudaStream_t st, const unsigned char *d_need = nullptr, long coarse_order = 0, int rank = 0,
+                    int *d_err = nullptr);
 int launch_ray_init(Ray *d_rays, long nrays, long first_nest, long ray_order, double binL_2, cudaStream_t st);
 int launch_ray_summary(const Ray *d_rays, long nrays, double *d_out6, cudaStream_t st);
 void launch_healpix_index(int what, long order, long n, const long *in, const double *th, const double *ph, long *out, cudaStream_t st);
 void launch_healpix_interpol(long order, long n, const double *vec, long *pix, double *wgt, cudaStream_t st);
 void sht_plan_set_peers(ShtPlan *p, void *const *g_recv_ptrs, void *const *b_recv_ptrs);
-int launch_maps_broadcast(const ShtPlan *p, float *const local_maps[6], float *const *peer_maps, cudaStream_t st);
+int launch_maps_broadcast(const ShtPlan *p, float *const local_maps[6], float *const *peer_maps,
+                          const unsigned char *d_need, long coarse_order, cudaStream_t st);
 int launch_load_density(const ShtPlan *p, const float *src, float *dst, float premul, float densmul, float backdens,
                         cudaStream_t st);
 extern int g_syn_rings_per_thread, g_ana_rings_per_thread, g_fft_threads_big;
@@ -163,10 +165,44 @@ void clb_sht_plan_set_peers(clb_sht_plan *plan, void *const *g_recv_ptrs, void *
 {
   sht_plan_set_peers(P(plan), g_recv_ptrs, b_recv_ptrs);
 }
-int clb_maps_broadcast_dev(const clb_sht_plan *plan, float *const local_maps[6], float *const *peer_maps, void *stream)
+int clb_maps_broadcast_dev(const clb_sht_plan *plan, float *const local_maps[6], float *const *peer_maps,
+                           const unsigned char *need, long coarse_order, void *stream)
 {
-  int n = launch_maps_broadcast(P(plan), local_maps, peer_maps, (cudaStream_t)stream);
+  int n = launch_maps_broadcast(P(plan), local_maps, peer_maps, need, coarse_order, (cudaStream_t)stream);
   g_launches += n; return n;
+}
+// Host helper: which ranks need the map pixels of every coarse NEST cell.  Rank q traces the rays whose NEST index at
+// ray_order lies in [Nray q / nranks, Nray (q+1) / nranks) (cf. loadbalance.c:151-181); its rays stay within the halo
+// of that domain (the reference's MAPBUFF cells, raytrace_utils.c:116-161), so it needs every cell whose centre is
+// within margin_rad of the centre of a cell of its domain (margin_rad must include two coarse cell radii).
+void clb_domain_masks(long ray_order, int nranks, long coarse_order, double margin_rad, unsigned char *mask)
+{
+  if (nranks > 8 || coarse_order < 0 || coarse_order > 8) { fprintf(stderr, "calclens_b200: clb_domain_masks arguments\n"); abort(); }
+  const long nc = 12L << (2 * coarse_order);
+  const long nray = 12L << (2 * ray_order);
+  std::vector<double> cen(3 * nc);
+  std::vector<unsigned char> own(nc, 0);
+  for (long c = 0; c < nc; ++c) {
+    nest2vec(c, coarse_order, &cen[3 * c]);
+    long lo, hi;   // ray NEST range covered by (or covering) the cell
+    if (ray_order >= coarse_order) { lo = c << (2 * (ray_order - coarse_order)); hi = (c + 1) << (2 * (ray_order - coarse_order)); }
+    else { lo = c >> (2 * (coarse_order - ray_order)); hi = lo + 1; }
+    for (int q = 0; q < nranks; ++q) {
+      const long qlo = (nray * q) / nranks, qhi = (nray * (q + 1)) / nranks;
+      if (lo < qhi && qlo < hi) own[c] |= (unsigned char)(1u << q);
+    }
+  }
+  const double cosm = cos(margin_rad);
+  for (long c = 0; c < nc; ++c) {
+    unsigned m = own[c];
+    const double *a = &cen[3 * c];
+    for (long d = 0; d < nc && m != ((1u << nranks) - 1u); ++d) {
+      if ((own[d] | m) == m) continue;
+      const double *b = &cen[3 * d];
+      if (a[0] * b[0] + a[1] * b[1] + a[2] * b[2] >= cosm) m |= own[d];
+    }
+    mask[c] = (unsigned char)m;
+  }
 }
 
 int clb_ring_analysis_dev(const clb_sht_plan *plan, const float *map, double *g_send, void *stream)
@@ -209,6 +245,14 @@ int clb_ray_step_dev(void *rays, long nrays, const float *const maps[6], long ma
 {
   if ((mode & 2) && !maps) { fprintf(stderr, "calclens_b200: clb_ray_step_dev mode 2 needs maps\n"); abort(); }
   int n = launch_ray_step(reinterpret_cast<Ray *>(rays), nrays, maps, map_order, wp, wpm1, wpm2, mode, (cudaStream_t)stream);
+  g_launches += n; return n;
+}
+int clb_ray_step_checked_dev(void *rays, long nrays, const float *const maps[6], long map_order, double wp, double wpm1,
+                             double wpm2, int mode, const unsigned char *need, long coarse_order, int rank, int *err,
+                             void *stream)
+{
+  int n = launch_ray_step(reinterpret_cast<Ray *>(rays), nrays, maps, map_order, wp, wpm1, wpm2, mode, (cudaStream_t)stream,
+                          need, coarse_order, rank, err);
   g_launches += n; return n;
 }
 int clb_ray_init_dev(void *rays, long nrays, long first_nest, long ray_order, double binL_2, void *stream)

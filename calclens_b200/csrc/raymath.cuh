@@ -209,7 +209,7 @@ __device__ __forceinline__ void get_interpol_tab(double theta, double phi, long 
   }
 }
 
-__device__ __forceinline__ void ray_interp_accumulate_fast(Ray &ray, long order, const RingTab *__restrict__ tab,
+__device__ __forceinline__ long ray_interp_accumulate_fast(Ray &ray, long order, const RingTab *__restrict__ tab,
                                                            const float *__restrict__ m_phi, const float *__restrict__ m_gt,
                                                            const float *__restrict__ m_gp, const float *__restrict__ m_gtt,
                                                            const float *__restrict__ m_gtp, const float *__restrict__ m_gpp)
@@ -270,6 +270,7 @@ __device__ __forceinline__ void ray_interp_accumulate_fast(Ray &ray, long order,
   ray.alpha[0] += -1.0 * gtheta;
   ray.alpha[1] += -1.0 * gphi;
   ray.U[0] += t00; ray.U[1] += t01; ray.U[2] += t10; ray.U[3] += t11;
+  return pix[0];
 }
 #endif
 

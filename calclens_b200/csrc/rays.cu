@@ -65,7 +65,8 @@ __device__ __forceinline__ void ray_cp_async16(void *smem, const void *gmem)
 // 16-byte stores.
 __global__ void __launch_bounds__(kRayThreads, 4)
 ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab *__restrict__ tab, long order, double wp,
-                double wpm1, double wpm2, int mode)
+                double wpm1, double wpm2, int mode, const unsigned char *__restrict__ need, int coarse_shift,
+                unsigned rank_bit, int *__restrict__ err)
 {
   __shared__ __align__(16) unsigned char s_raw[2][kRayThreads * sizeof(Ray)];
   const long ntiles = (nrays + kRayThreads - 1) / kRayThreads;
@@ -99,7 +100,12 @@ ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab 
         ray.phi = 0.0; ray.alpha[0] = 0.0; ray.alpha[1] = 0.0;
         ray.U[0] = 0.0; ray.U[1] = 0.0; ray.U[2] = 0.0; ray.U[3] = 0.0;
       }
-      if (mode & 2) ray_interp_accumulate_fast(ray, order, tab, maps.p[0], maps.p[1], maps.p[2], maps.p[3], maps.p[4], maps.p[5]);
+      if (mode & 2) {
+        const long p0 = ray_interp_accumulate_fast(ray, order, tab, maps.p[0], maps.p[1], maps.p[2], maps.p[3], maps.p[4], maps.p[5]);
+        // sharded runs: the stencil must lie inside the part of the sky this rank received (the reference aborts on a
+        // missing map cell, shtpoissonsolve.c:683-689; here the flag is raised and the host aborts)
+        if (need && !(need[ring2nest(p0, order) >> coarse_shift] & rank_bit)) atomicOr(err, 1);
+      }
       if (mode & 4) ray_propagate(ray, wp, wpm1, wpm2);
       s_rays[threadIdx.x] = ray;
     }
@@ -112,7 +118,7 @@ ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab 
 }
 
 int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long order, double wp, double wpm1,
-                    double wpm2, int mode, cudaStream_t st)
+                    double wpm2, int mode, cudaStream_t st, const unsigned char *d_need, long coarse_order, int rank, int *d_err)
 {
   if (nrays <= 0) return 0;
   RayMaps m;
@@ -126,7 +132,9 @@ int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long 
   }
   const long nblocks = std::min<long>(ntiles, (long)sms * 4);
   const RingTab *tab = (mode & 2) ? ring_table(order, st) : nullptr;
-  ray_step_kernel<<<(unsigned)nblocks, kRayThreads, 0, st>>>(d_rays, nrays, m, tab, order, wp, wpm1, wpm2, mode);
+  if (d_need && (coarse_order > order || !d_err)) d_need = nullptr;
+  ray_step_kernel<<<(unsigned)nblocks, kRayThreads, 0, st>>>(d_rays, nrays, m, tab, order, wp, wpm1, wpm2, mode, d_need,
+                                                             (int)(2 * (order - coarse_order)), 1u << rank, d_err);
   CLB_CUDA_CHECK(cudaGetLastError());
   return 1;
 }

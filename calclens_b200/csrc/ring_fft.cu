@@ -864,24 +864,36 @@ int launch_load_density(const ShtPlan *p, const float *src, float *dst, float pr
 // Fused exchange of the derivative maps: every rank stores the rings it synthesised into every peer's map buffers
 // (NVLink peer stores), replacing the ring -> domain shuffle of map_shuffle.c:22-631 by a broadcast of ring sets.
 struct PeerMaps { float *p[8][6]; };
+// need[c] (optional): bit q set when rank q's ray domain, grown by the halo margin, touches coarse NEST cell c
+// (clb_domain_masks); a group of four pixels goes only to the ranks whose bit is set for its cell(s).
 __global__ void ring_broadcast_kernel(MapPtrs local, PeerMaps peers, int nranks, int rank, RingGeomDev geo,
-                                      const int *__restrict__ rp_loc)
+                                      const int *__restrict__ rp_loc, const unsigned char *__restrict__ need, long order,
+                                      int coarse_shift)
 {
   const int rp = rp_loc[blockIdx.x >> 1];
   const int hemi = blockIdx.x & 1;
-  const int field = blockIdx.y;
   const long start = hemi ? geo.startS[rp] : geo.startN[rp];
   if (start < 0) return;
   const int n4 = geo.nphi[rp] >> 2;
-  const float4 *src = reinterpret_cast<const float4 *>(local.p[field] + start);
   for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-    const float4 v = src[i];
-    for (int q = 0; q < nranks; ++q)
-      if (q != rank) reinterpret_cast<float4 *>(peers.p[q][field] + start)[i] = v;
+    unsigned m = 0xffu;
+    if (need) {
+      const long pix = start + 4L * i;
+      m = need[ring2nest(pix, order) >> coarse_shift] | need[ring2nest(pix + 3, order) >> coarse_shift];
+    }
+    m &= ~(1u << rank);
+    if (!m) continue;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+      const float4 v = reinterpret_cast<const float4 *>(local.p[f] + start)[i];
+      for (int q = 0; q < nranks; ++q)
+        if ((m >> q) & 1u) reinterpret_cast<float4 *>(peers.p[q][f] + start)[i] = v;
+    }
   }
 }
 
-int launch_maps_broadcast(const ShtPlan *p, float *const local_maps[6], float *const *peer_maps, cudaStream_t st)
+int launch_maps_broadcast(const ShtPlan *p, float *const local_maps[6], float *const *peer_maps,
+                          const unsigned char *d_need, long coarse_order, cudaStream_t st)
 {
   if (p->nranks <= 1 || p->nrp_loc == 0) return 0;
   if (p->nranks > 8) { fprintf(stderr, "calclens_b200: map broadcast supports up to 8 ranks per node\n"); abort(); }
@@ -889,8 +901,9 @@ int launch_maps_broadcast(const ShtPlan *p, float *const local_maps[6], float *c
   for (int k = 0; k < 6; ++k) loc.p[k] = local_maps[k];
   for (int q = 0; q < 8; ++q)
     for (int k = 0; k < 6; ++k) peers.p[q][k] = (q < p->nranks) ? peer_maps[q * 6 + k] : nullptr;
-  dim3 grid(2 * p->nrp_loc, 6);
-  ring_broadcast_kernel<<<grid, 256, 0, st>>>(loc, peers, p->nranks, p->rank, geom_of(p), p->d_rp_loc);
+  if (d_need && coarse_order > p->order) d_need = nullptr;
+  ring_broadcast_kernel<<<2 * p->nrp_loc, 256, 0, st>>>(loc, peers, p->nranks, p->rank, geom_of(p), p->d_rp_loc, d_need,
+                                                        p->order, (int)(2 * (p->order - coarse_order)));
   CLB_CUDA_CHECK(cudaGetLastError());
   return 1;
 }

@@ -92,7 +92,8 @@ class LensPlaneSolver:
     """One rank's share of the per-plane hot path.  ``dist_group`` = None for a single GPU, otherwise an initialised
     torch.distributed process group (NCCL) with one rank per GPU."""
 
-    def __init__(self, sht_order, lmax=None, ray_order=None, ring_weights=None, dist_group=None, device=None, fused=True):
+    def __init__(self, sht_order, lmax=None, ray_order=None, ring_weights=None, dist_group=None, device=None, fused=True,
+                 halo_deg=1.0):
         import torch.distributed as dist
         self.dist = dist if dist_group is not None else None
         self.group = dist_group
@@ -122,6 +123,9 @@ class LensPlaneSolver:
         self._staged = None        # (host map, scalings, buffer index, ready event) of a prefetched plane
         self._dens_free = [None, None]   # event after the last kernel that read each density buffer
         self.fused = False
+        self.halo_deg = float(halo_deg)
+        self._need = None          # device mask of the coarse cells each rank needs (fused exchange only)
+        self._err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._peer_bufs = []
         if self.nranks > 1 and fused:
             self._setup_peer_exchange()
@@ -179,6 +183,17 @@ class LensPlaneSolver:
         self.maps.zero_()
         self.g_send = self.b_send = None   # producers store into the owners' receive buffers
         self._tiny = torch.zeros(1, dtype=torch.float32, device=self.device)
+        # halo-limited map broadcast: a pixel goes to the ranks whose ray domain, grown by halo_deg, can reach it.
+        # Cells of a coarse NEST grid stand in for the reference's halo bundle cells (raytrace_utils.c:116-161); the
+        # margin adds two coarse cell radii (a HEALPix pixel's radius is < 1.2 x its mean spacing).
+        self.coarse_order = 5
+        if self.halo_deg > 0 and self.order >= self.coarse_order:
+            spacing = math.sqrt(4.0 * math.pi / (12 << (2 * self.coarse_order)))
+            margin = math.radians(self.halo_deg) + 2.0 * 1.2 * spacing
+            mask = np.zeros(12 << (2 * self.coarse_order), dtype=np.uint8)
+            L.clb_domain_masks(self.ray_order, self.nranks, self.coarse_order, margin, mask.ctypes.data)
+            self._need = torch.from_numpy(mask).to(self.device)
+            self.need_fraction = float(np.unpackbits(mask[:, None], axis=1)[:, -self.nranks:].sum()) / (mask.size * self.nranks)
         self.fused = True
         self.dist.barrier(group=self.group)
 
@@ -236,7 +251,8 @@ class LensPlaneSolver:
             self._stream_barrier(); mark("a2a_b")
             p.ring_synthesis(self.b_recv, self.maps); mark("fft_synthesis")
             ptrs = (C.c_void_p * 6)(*[self.maps[k].data_ptr() for k in range(6)])
-            self.lib.clb_maps_broadcast_dev(p._h, ptrs, self._peer_maps, self._stream())
+            self.lib.clb_maps_broadcast_dev(p._h, ptrs, self._peer_maps, None if self._need is None else self._need.data_ptr(),
+                                            self.coarse_order, self._stream())
             self._stream_barrier(); mark("map_allreduce")
             return self.maps
         p.ring_analysis(dens, self.g_send); mark("fft_analysis")
@@ -261,7 +277,8 @@ class LensPlaneSolver:
             self._stream_barrier()
             p.ring_synthesis(self.b_recv, self.maps)
             ptrs = (C.c_void_p * 6)(*[self.maps[k].data_ptr() for k in range(6)])
-            self.lib.clb_maps_broadcast_dev(p._h, ptrs, self._peer_maps, self._stream())
+            self.lib.clb_maps_broadcast_dev(p._h, ptrs, self._peer_maps, None if self._need is None else self._need.data_ptr(),
+                                            self.coarse_order, self._stream())
             self._stream_barrier()
             return self.maps
         p.legendre_synthesis(alm_re, alm_im, self.b_send)
@@ -277,8 +294,19 @@ class LensPlaneSolver:
         """zero + interpolate + propagate: rayprop_sphere(planeRadPlus1, planeRad, planeRadMinus1) as called at
         raytrace.c:262, preceded by the reset of raytrace.c:213-230 and the interpolation of shtpoissonsolve.c:666-702."""
         ptrs = (C.c_void_p * 6)(*[self.maps[k].data_ptr() for k in range(6)])
+        if self._need is not None:
+            self.lib.clb_ray_step_checked_dev(self.rays.data_ptr(), self.nrays, ptrs, self.order, float(wpp1), float(wp),
+                                              float(wpm1), MODE_ZERO | MODE_INTERP | MODE_PROP, self._need.data_ptr(),
+                                              self.coarse_order, self.rank, self._err.data_ptr(), self._stream())
+            return
         self.lib.clb_ray_step_dev(self.rays.data_ptr(), self.nrays, ptrs, self.order, float(wpp1), float(wp), float(wpm1),
                                   MODE_ZERO | MODE_INTERP | MODE_PROP, self._stream())
+
+    def check_halo(self):
+        """Raise if a ray left the part of the sky this rank receives (the reference aborts on a missing map cell,
+        shtpoissonsolve.c:683-689); synchronises."""
+        if self._need is not None and int(self._err.item()) != 0:
+            raise RuntimeError("calclens_b200: a ray left its domain + halo (%.2f deg); raise halo_deg" % self.halo_deg)
 
     def prefetch(self, counts_map, premul, densmul, backdens):
         """Start loading the NEXT plane's density on the copy stream while the current plane computes: the host map is
@@ -318,7 +346,9 @@ class LensPlaneSolver:
         self.lib.clb_ray_summary_dev(self.rays.data_ptr(), self.nrays, self.summary.data_ptr(), self._stream())
         if self.nranks > 1:
             self.dist.all_reduce(self.summary, group=self.group)
-        return self.summary.cpu().numpy()
+        out = self.summary.cpu().numpy()
+        self.check_halo()
+        return out
 
     def rays_host(self):
         from .rays import rays_from_device

@@ -73,15 +73,26 @@ int clb_ring_synthesis_dev(const clb_sht_plan *plan, const double *b_recv, float
  *                                  Afterwards clb_ring_analysis_dev ignores g_send and clb_legendre_synthesis_dev
  *                                  ignores b_send: results land in the owners' receive buffers.  The host orders
  *                                  producer and consumer stages with a stream barrier across ranks.
- *   clb_maps_broadcast_dev       : store this rank's rings of the six maps into every peer's maps
- *                                  (peer_maps[q*6+k] = map k of rank q, up to 8 ranks) ---- */
+ *   clb_maps_broadcast_dev       : store this rank's rings of the six maps into the peers' maps
+ *                                  (peer_maps[q*6+k] = map k of rank q, up to 8 ranks);
+ *                                  need (device, may be NULL = every pixel to every rank) and coarse_order come from
+ *                                  clb_domain_masks: pixels go only to the ranks whose ray domain + halo covers them
+ *   clb_domain_masks (host)      : mask[12*4^coarse_order], bit q set when rank q needs the cell -- the counterpart of
+ *                                  the reference's halo ("buffer") bundle cells, raytrace_utils.c:116-161 ---- */
 void *clb_peer_alloc(long bytes);
 void clb_peer_free(void *p);
 void clb_peer_export(void *p, void *handle64);
 void *clb_peer_import(const void *handle64);
 void clb_peer_release(void *p);
 void clb_sht_plan_set_peers(clb_sht_plan *plan, void *const *g_recv_ptrs, void *const *b_recv_ptrs);
-int clb_maps_broadcast_dev(const clb_sht_plan *plan, float *const local_maps[6], float *const *peer_maps, void *stream);
+int clb_maps_broadcast_dev(const clb_sht_plan *plan, float *const local_maps[6], float *const *peer_maps,
+                           const unsigned char *need, long coarse_order, void *stream);
+void clb_domain_masks(long ray_order, int nranks, long coarse_order, double margin_rad, unsigned char *mask);
+/* clb_ray_step_dev that also verifies, per ray, that its interpolation stencil lies inside the cells this rank received
+ * (*err |= 1 otherwise; the reference aborts on a missing map cell, shtpoissonsolve.c:683-689) */
+int clb_ray_step_checked_dev(void *rays, long nrays, const float *const maps[6], long map_order, double wp, double wpm1,
+                             double wpm2, int mode, const unsigned char *need, long coarse_order, int rank, int *err,
+                             void *stream);
 
 /* ---- density scaling of shtpoissonsolve.c:426,454-502 (full-sky: no vacuum cells):
  * map = (map * premul) * densmul - backdens, all in float like the reference ---- */
