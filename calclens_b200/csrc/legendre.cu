@@ -31,6 +31,17 @@ static_assert(kLB == kSeedAlign, "l-blocks must line up with the seed alignment"
 // the same degree, so one start degree per warp (analysis: per CTA) wastes ~1 % of the work and the whole warp runs
 // branch-free: rings that start later carry mu = 0 until their seed is injected at their own (16-aligned) start.
 
+constexpr int kAnaTile = 32;      // degrees of recurrence coefficients per shared-memory tile of the analysis kernel
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 // ---------------------------------------------------------------------------------------------------------------
 // analysis
 // ---------------------------------------------------------------------------------------------------------------
@@ -53,10 +64,10 @@ legendre_analysis_kernel(const double2 *__restrict__ g_recv, const long *__restr
   static_assert(R % 2 == 0 || R == 1, "start blocks are packed two per register");
   constexpr int V = 2 * KB;   // v[i] = re(l0+i), v[KB+i] = im(l0+i)
   constexpr int NP = (R + 1) / 2;
-  __shared__ double s_A[kLegWarps][2][KB];
+  __shared__ __align__(16) double s_A[kLegWarps][2][kAnaTile];
 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int chunk = blockIdx.x * kLegWarps + w, mi = blockIdx.y;
+  const int chunk = blockIdx.x * (blockDim.x >> 5) + w, mi = blockIdx.y;
   if (chunk * 32 * R >= nrp) return;     // whole warp beyond the last ring pair (no barriers in this kernel)
   const int m = m_loc[mi];
   unsigned sb[NP];            // start block (ls - m) / 16 of ring j in the (j & 1) half of sb[j / 2]; 0xffff = never
@@ -93,59 +104,66 @@ legendre_analysis_kernel(const double2 *__restrict__ g_recv, const long *__restr
     for (int l = m + lane; l < lz; l += 32) out[l - m] = make_double2(0.0, 0.0);
     if (lsw == kNoStart) return;
   }
-  const double *Arow = Atab + row_off[mi];     // rows are zero padded beyond lmax+1 (kRowPad)
+  // recurrence coefficients A_l stream through a private double-buffered tile of kAnaTile degrees (cp.async);
+  // rows are zero padded beyond lmax+1 (kRowPad), so whole tiles can be read and computed without bounds checks
+  const double *Arow = Atab + row_off[mi] + (lsw - m);
   double *sA = &s_A[w][0][0];
-  if (lane < KB) sA[lane] = Arow[lsw - m + lane];
-  __syncwarp();
+  if (lane < kAnaTile / 2) cp_async16(sA + 2 * lane, Arow + 2 * lane);
+  cp_async_commit();
   int cur = 0;
-  for (int l0 = lsw; l0 <= lmax; l0 += KB) {
-    double a_next = 0.0;
-    if (lane < KB) a_next = __ldg(&Arow[l0 + KB - m + lane]);
-    if (l0 <= lsmax && (l0 - m) % kSeedAlign == 0) {     // start-up phase of this warp: inject the seeds of rings starting here
-      const unsigned blk = (unsigned)(l0 - m) / kSeedAlign;
-#pragma unroll
-      for (int j = 0; j < R; ++j)
-        if (((sb[j / 2] >> (16 * (j & 1))) & 0xffffu) == blk) {
-          const double2 sd = seed_tab[(size_t)mi * nrp + rp0 + j * 32];
-          mp[j] = sd.x; mc[j] = sd.y;
-        }
-    }
-    double v[V];
-#pragma unroll
-    for (int i = 0; i < V; ++i) v[i] = 0.0;
-    const double *sa = sA + cur * KB;
-#pragma unroll
-    for (int i = 0; i < KB; ++i) {
-      const double a = sa[i];
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-        const double mu = mc[j];
-        if (i & 1) { v[i] = fma(mu, gmx[j], v[i]); v[KB + i] = fma(mu, gmy[j], v[KB + i]); }
-        else       { v[i] = fma(mu, gpx[j], v[i]); v[KB + i] = fma(mu, gpy[j], v[KB + i]); }
-        const double mn = fma(x[j] * a, mu, -mp[j]);
-        mp[j] = mu; mc[j] = mn;
-      }
-    }
-    // warp transpose-reduce: afterwards lane L holds the warp total of v[L % V]
-#pragma unroll
-    for (int s = V / 2; s >= 1; s >>= 1) {
-      const bool upper = (lane & s) != 0;
-#pragma unroll
-      for (int k = 0; k < s; ++k) {
-        const double send = upper ? v[k] : v[k + s];
-        const double keep = upper ? v[k + s] : v[k];
-        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-      }
-    }
-    if (V == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
-    const double ti = __shfl_down_sync(0xffffffffu, v[0], KB);   // imaginary part lives KB lanes up
-    if (lane < KB) {
-      if (l0 + lane <= lmax) out[l0 - m + lane] = make_double2(v[0], ti);
-      sA[(cur ^ 1) * KB + lane] = a_next;
-    }
-    cur ^= 1;
+  for (int lt = lsw; lt <= lmax; lt += kAnaTile, cur ^= 1) {
+    Arow += kAnaTile;
+    if (lane < kAnaTile / 2) cp_async16(sA + (cur ^ 1) * kAnaTile + 2 * lane, Arow + 2 * lane);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncwarp();
+    const double *sa = sA + cur * kAnaTile;
+#pragma unroll
+    for (int b = 0; b < kAnaTile / KB; ++b) {
+      const int l0 = lt + b * KB;
+      if (l0 > lmax) break;
+      if ((b * KB) % kSeedAlign == 0 && l0 <= lsmax) {   // start-up phase of this warp: inject the seeds of rings starting here
+        const unsigned blk = (unsigned)(l0 - m) / kSeedAlign;
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (((sb[j / 2] >> (16 * (j & 1))) & 0xffffu) == blk) {
+            const double2 sd = seed_tab[(size_t)mi * nrp + rp0 + j * 32];
+            mp[j] = sd.x; mc[j] = sd.y;
+          }
+      }
+      double v[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < KB; ++i) {
+        const double a = sa[b * KB + i];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const double mu = mc[j];
+          if (i & 1) { v[i] = fma(mu, gmx[j], v[i]); v[KB + i] = fma(mu, gmy[j], v[KB + i]); }
+          else       { v[i] = fma(mu, gpx[j], v[i]); v[KB + i] = fma(mu, gpy[j], v[KB + i]); }
+          const double mn = fma(x[j] * a, mu, -mp[j]);
+          mp[j] = mu; mc[j] = mn;
+        }
+      }
+      // warp transpose-reduce: afterwards lane L holds the warp total of v[L % V]
+#pragma unroll
+      for (int s = V / 2; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int k = 0; k < s; ++k) {
+          const double send = upper ? v[k] : v[k + s];
+          const double keep = upper ? v[k + s] : v[k];
+          v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+      }
+      if (V == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+      const double ti = __shfl_down_sync(0xffffffffu, v[0], KB);   // imaginary part lives KB lanes up
+      if (lane < KB && l0 + lane <= lmax) out[l0 - m + lane] = make_double2(v[0], ti);
+    }
+    __syncwarp();   // everyone is done with this tile before the next iteration's copy overwrites it
   }
+  cp_async_wait<0>();
 }
 
 // sum the ring chunks in a fixed order, undo the recurrence scaling (lambda = c mu) and apply the Poisson filter
@@ -221,15 +239,6 @@ __global__ void synthesis_coef_kernel(const double *__restrict__ alm_re, const d
   }
 }
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
-{
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
 // One warp = 32*R adjacent ring pairs of one m, independent of the other warps of its CTA (no block barrier): it
 // streams the per-degree coefficient records {A, P, D, K} of its own degree range through a private double-buffered
 // shared-memory tile (cp.async, 1 KB per 16 degrees) and reads them back as broadcast LDS.128 -- two per degree for
@@ -251,7 +260,7 @@ legendre_synthesis_kernel(const double *__restrict__ coef, const long *__restric
   double mp[R], mc[R], x[R];
   double acc[R][12];   // [parity(0 even,1 odd)*6 + {Pre,Pim,Dre,Dim,Kre,Kim}]
   int lsmin = kNoStart;
-  const int rp0 = (c * kLegWarps + w) * 32 * R + lane;
+  const int rp0 = (c * (blockDim.x >> 5) + w) * 32 * R + lane;
 #pragma unroll
   for (int j = 0; j < R; ++j) {
     const int rp = rp0 + j * 32;
@@ -343,14 +352,16 @@ legendre_synthesis_kernel(const double *__restrict__ coef, const long *__restric
 // ---------------------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------------------
+int g_leg_warps_per_cta = 4;      // warps are independent in both Legendre kernels; clb_set_tuning(3, 1|2|4)
 int g_syn_rings_per_thread = 4;   // tunable through clb_set_tuning(0, .)
 int g_ana_rings_per_thread = 8;   // tunable through clb_set_tuning(1, .): 8 (blocks of 8 degrees) or 4, 2, 1 (16 degrees)
 
 template <int R, int KB, int NB>
 static void launch_ana_t(const ShtPlan *p, const double2 *g_recv, int nchunk, cudaStream_t st)
 {
-  dim3 grid((nchunk + kLegWarps - 1) / kLegWarps, p->nm_loc);
-  legendre_analysis_kernel<R, KB, NB><<<grid, kLegThreads, 0, st>>>(
+  const int warps = g_leg_warps_per_cta;
+  dim3 grid((nchunk + warps - 1) / warps, p->nm_loc);
+  legendre_analysis_kernel<R, KB, NB><<<grid, 32 * warps, 0, st>>>(
       g_recv, p->d_g_off, p->d_g_stride, p->d_A, p->d_row_off, p->d_ls_ana, p->d_seed, p->d_cth, p->d_m_loc,
       p->d_alm_off, reinterpret_cast<double2 *>(p->d_part), p->alm_total, p->nrp, (int)p->lmax);
 }
@@ -394,11 +405,12 @@ int launch_legendre_synthesis(ShtPlan *p, const double *d_alm_re, const double *
                                                (int)p->lmax, p->d_coef);
   CLB_CUDA_CHECK(cudaGetLastError());
   int R = g_syn_rings_per_thread;
-  while (R > 1 && p->nrp < kLegThreads * R) R >>= 1;
-  const int nchunk = (p->nrp + R * kLegThreads - 1) / (R * kLegThreads);
+  while (R > 1 && p->nrp < 32 * R) R >>= 1;
+  const int warps = g_leg_warps_per_cta;
+  const int nchunk = (p->nrp + R * 32 * warps - 1) / (R * 32 * warps);
   dim3 grid(nchunk, p->nm_loc);
 #define CLB_SYN_LAUNCH(RR)                                                                                           \
-  legendre_synthesis_kernel<RR><<<grid, kLegThreads, 0, st>>>(p->d_coef, p->d_row_off, p->d_ls_syn, p->d_seed, p->d_cth, \
+  legendre_synthesis_kernel<RR><<<grid, 32 * warps, 0, st>>>(p->d_coef, p->d_row_off, p->d_ls_syn, p->d_seed, p->d_cth, \
                                                               p->d_sth, p->d_m_loc, p->d_b_off, p->d_b_stride, d_b_send, \
                                                               p->d_rp_bptr, p->nrp, (int)p->lmax)
   switch (R) {

@@ -133,6 +133,82 @@ __global__ void __launch_bounds__(128, NB) ana_k(double *out, int iters, double 
   out[blockIdx.x * blockDim.x + threadIdx.x] = tot + mc[0] + mc[R - 1];
 }
 
+// analysis-like with the warp reduce of block b software-pipelined into the compute of block b+1:
+// stage s of the transpose-reduce runs between degrees s and s+1 of the next block, so shuffle latency hides
+// behind FP64 work.  Blocks are processed in pairs so the roles of the two accumulator sets alternate without moves.
+template <int R, int NB>
+__global__ void __launch_bounds__(128, NB) ana_pipe_k(double *out, int iters, double a0)
+{
+  constexpr int KB = 8, V = 16;
+  __shared__ double sA[2][KB];
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x < KB) { sA[0][threadIdx.x] = 1.0 + 1e-3 * threadIdx.x + a0; sA[1][threadIdx.x] = 1.0 - 1e-3 * threadIdx.x + a0; }
+  __syncthreads();
+  double mp[R], mc[R], x[R], gpx[R], gpy[R], gmx[R], gmy[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    mp[j] = 0.1 * j; mc[j] = 0.2 + threadIdx.x * 1e-4; x[j] = 0.3 + j * 0.01;
+    gpx[j] = 1 + j; gpy[j] = 2 + j; gmx[j] = 3 + j; gmy[j] = 4 + j + a0;
+  }
+  double tot = 0;
+  double va[V], vb[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { va[i] = 0.0; vb[i] = 0.0; }
+  auto compute_i = [&](double (&v)[V], const double *sa, int i) {
+    const double a = sa[i];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const double mu = mc[j];
+      if (i & 1) { v[i] = fma(mu, gmx[j], v[i]); v[KB + i] = fma(mu, gmy[j], v[KB + i]); }
+      else       { v[i] = fma(mu, gpx[j], v[i]); v[KB + i] = fma(mu, gpy[j], v[KB + i]); }
+      const double mn = fma(x[j] * a, mu, -mp[j]);
+      mp[j] = mu; mc[j] = mn;
+    }
+  };
+  auto reduce_stage = [&](double (&v)[V], int st) {   // st = 0..3: s = 8,4,2,1 ; st = 4: final xor 16 ; then consume
+    if (st < 4) {
+      const int s = 8 >> st;
+      const bool upper = (lane & s) != 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (k < s) {
+          const double send = upper ? v[k] : v[k + s];
+          const double keep = upper ? v[k + s] : v[k];
+          v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+      }
+    } else if (st == 4) {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+    } else if (st == 5) {
+      tot += v[0];
+    }
+  };
+  for (int it = 0; it < iters; it += 2) {
+    const double *sa = sA[0];
+    // block A: accumulate into va while reducing vb (previous block)
+#pragma unroll
+    for (int i = 0; i < KB; ++i) {
+      if (i == 0) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) va[k] = 0.0;   // folded into the first FMAs by the compiler
+      }
+      compute_i(va, sa, i);
+      if (i < 6) reduce_stage(vb, i);
+    }
+    sa = sA[1];
+#pragma unroll
+    for (int i = 0; i < KB; ++i) {
+      if (i == 0) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) vb[k] = 0.0;
+      }
+      compute_i(vb, sa, i);
+      if (i < 6) reduce_stage(va, i);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = tot + mc[0] + mc[R - 1];
+}
+
 template <typename F>
 static float timeit(F f)
 {
@@ -206,6 +282,14 @@ int main()
       ms = timeit([&] { ana_k<8, 8, 0, 2><<<ctas2, 128>>>(out, it3, 1e-9); }); printf(" %6.2f", 8.0 * 8 * 8 * it3 * ctas2 * 128 / ms * 1e-9);
       ms = timeit([&] { ana_k<8, 8, 1, 2><<<ctas2, 128>>>(out, it3, 1e-9); }); printf(" %6.2f", 8.0 * 8 * 8 * it3 * ctas2 * 128 / ms * 1e-9);
       ms = timeit([&] { ana_k<8, 8, 2, 2><<<ctas2, 128>>>(out, it3, 1e-9); }); printf(" %6.2f\n", 8.0 * 8 * 8 * it3 * ctas2 * 128 / ms * 1e-9);
+      printf("pipelined reduce R=8 KB=8 (3 CTAs/SM):");
+      ms = timeit([&] { ana_pipe_k<8, 3><<<ctas, 128>>>(out, it3, 1e-9); }); printf(" %6.2f\n", 8.0 * 8 * 8 * it3 * ctas * 128 / ms * 1e-9);
+      printf("pipelined reduce R=6 KB=8 (3 CTAs/SM):");
+      ms = timeit([&] { ana_pipe_k<6, 3><<<ctas, 128>>>(out, it3, 1e-9); }); printf(" %6.2f\n", 8.0 * 6 * 8 * it3 * ctas * 128 / ms * 1e-9);
+      printf("pipelined reduce R=8 KB=8 (4 CTAs/SM):");
+      ms = timeit([&] { ana_pipe_k<8, 4><<<sms * 4, 128>>>(out, it3, 1e-9); }); printf(" %6.2f\n", 8.0 * 8 * 8 * it3 * sms * 4 * 128 / ms * 1e-9);
+      printf("pipelined reduce R=12 KB=8 (2 CTAs/SM):");
+      ms = timeit([&] { ana_pipe_k<12, 2><<<ctas2, 128>>>(out, it3, 1e-9); }); printf(" %6.2f\n", 8.0 * 12 * 8 * it3 * ctas2 * 128 / ms * 1e-9);
       const int ctas4 = sms * 4;
       printf("4 CTAs/SM R=8 KB=8 (128 regs):");
       ms = timeit([&] { ana_k<8, 8, 0, 4><<<ctas4, 128>>>(out, it3, 1e-9); }); printf(" %6.2f", 8.0 * 8 * 8 * it3 * ctas4 * 128 / ms * 1e-9);
