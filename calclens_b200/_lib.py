@@ -42,7 +42,7 @@ def load():
         "clb_sht_plan_set_peers": (None, [vp, vp, vp]),
         "clb_maps_broadcast_dev": (C.c_int, [vp, vp, vp, vp, C.c_long, vp]),
         "clb_domain_masks": (None, [C.c_long, C.c_int, C.c_long, C.c_double, vp]),
-        "clb_ray_step_checked_dev": (C.c_int, [vp, C.c_long, vp, C.c_long, C.c_double, C.c_double, C.c_double, C.c_int, vp, C.c_long, C.c_int, vp, vp]),
+        "clb_ray_step_ex_dev": (C.c_int, [vp, C.c_long, vp, C.c_long, C.c_double, C.c_double, C.c_double, C.c_int, vp, C.c_long, C.c_int, vp, vp, vp]),
         "clb_ring_analysis_dev": (C.c_int, [vp, vp, vp, vp]),
         "clb_legendre_analysis_dev": (C.c_int, [vp, vp, vp, vp, C.c_int, vp]),
         "clb_legendre_synthesis_dev": (C.c_int, [vp, vp, vp, vp, vp]),

@@ -15,7 +15,7 @@ int launch_legendre_analysis(ShtPlan *p, const double2 *d_g_recv, double *d_alm_
 int launch_legendre_synthesis(ShtPlan *p, const double *d_alm_re, const double *d_alm_im, double2 *d_b_send, cudaStream_t st);
 int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long order, double wp, double wpm1, double wpm2,
                     int mode, cudaStream_t st, const unsigned char *d_need = nullptr, long coarse_order = 0, int rank = 0,
-                    int *d_err = nullptr);
+                    int *d_err = nullptr, double *d_sum6 = nullptr);
 int launch_ray_init(Ray *d_rays, long nrays, long first_nest, long ray_order, double binL_2, cudaStream_t st);
 int launch_ray_summary(const Ray *d_rays, long nrays, double *d_out6, cudaStream_t st);
 void launch_healpix_index(int what, long order, long n, const long *in, const double *th, const double *ph, long *out, cudaStream_t st);
@@ -248,12 +248,13 @@ int clb_ray_step_dev(void *rays, long nrays, const float *const maps[6], long ma
   int n = launch_ray_step(reinterpret_cast<Ray *>(rays), nrays, maps, map_order, wp, wpm1, wpm2, mode, (cudaStream_t)stream);
   g_launches += n; return n;
 }
-int clb_ray_step_checked_dev(void *rays, long nrays, const float *const maps[6], long map_order, double wp, double wpm1,
-                             double wpm2, int mode, const unsigned char *need, long coarse_order, int rank, int *err,
-                             void *stream)
+int clb_ray_step_ex_dev(void *rays, long nrays, const float *const maps[6], long map_order, double wp, double wpm1,
+                        double wpm2, int mode, const unsigned char *need, long coarse_order, int rank, int *err,
+                        double *sum6, void *stream)
 {
+  if ((mode & 2) && !maps) { fprintf(stderr, "calclens_b200: clb_ray_step_ex_dev mode 2 needs maps\n"); abort(); }
   int n = launch_ray_step(reinterpret_cast<Ray *>(rays), nrays, maps, map_order, wp, wpm1, wpm2, mode, (cudaStream_t)stream,
-                          need, coarse_order, rank, err);
+                          need, coarse_order, rank, err, sum6);
   g_launches += n; return n;
 }
 int clb_ray_init_dev(void *rays, long nrays, long first_nest, long ray_order, double binL_2, void *stream)

@@ -66,9 +66,14 @@ __device__ __forceinline__ void ray_cp_async16(void *smem, const void *gmem)
 __global__ void __launch_bounds__(kRayThreads, 4)
 ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab *__restrict__ tab, long order, double wp,
                 double wpm1, double wpm2, int mode, const unsigned char *__restrict__ need, int coarse_shift,
-                unsigned rank_bit, int *__restrict__ err)
+                unsigned rank_bit, int *__restrict__ err, double *__restrict__ sum6)
 {
   __shared__ __align__(16) unsigned char s_raw[2][kRayThreads * sizeof(Ray)];
+  __shared__ double s_sum[6][kRayThreads / 32];   // per-warp running sums of the plane summary (sum6 != nullptr)
+  if (sum6 && (threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s_sum[k][threadIdx.x >> 5] = 0.0;
+  }
   const long ntiles = (nrays + kRayThreads - 1) / kRayThreads;
   long tile = blockIdx.x;
   if (tile >= ntiles) return;
@@ -94,6 +99,7 @@ ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab 
     const long first = tile * kRayThreads;
     const int nblk = (int)min((long)kRayThreads, nrays - first);
     Ray *s_rays = reinterpret_cast<Ray *>(s_raw[buf]);
+    double ps[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (threadIdx.x < nblk) {
       Ray ray = s_rays[threadIdx.x];
       if (mode & 1) {
@@ -108,6 +114,22 @@ ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab 
       }
       if (mode & 4) ray_propagate(ray, wp, wpm1, wpm2);
       s_rays[threadIdx.x] = ray;
+      if (sum6) {   // same six sums as ray_summary_kernel, without a second pass over the ray array
+        ps[0] = 1.0 - 0.5 * (ray.A[0] + ray.A[3]);
+        ps[1] = 0.5 * (ray.A[3] - ray.A[0]);
+        ps[2] = -0.5 * (ray.A[1] + ray.A[2]);
+        ps[3] = ray.alpha[0] * ray.alpha[0] + ray.alpha[1] * ray.alpha[1];
+        ps[4] = ray.phi;
+        ps[5] = 0.5 * (ray.A[2] - ray.A[1]);
+      }
+    }
+    if (sum6) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        double v = ps[k];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) s_sum[k][threadIdx.x >> 5] += v;
+      }
     }
     __syncthreads();
     const int4 *ssrc = reinterpret_cast<const int4 *>(s_raw[buf]);
@@ -115,10 +137,15 @@ ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab 
     for (int i = threadIdx.x; i < nblk * kRayWords; i += kRayThreads) gdst[i] = ssrc[i];
     __syncthreads();   // the next iteration streams the tile after next into this buffer
   }
+  if (sum6 && (threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) atomicAdd(&sum6[k], s_sum[k][threadIdx.x >> 5]);
+  }
 }
 
 int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long order, double wp, double wpm1,
-                    double wpm2, int mode, cudaStream_t st, const unsigned char *d_need, long coarse_order, int rank, int *d_err)
+                    double wpm2, int mode, cudaStream_t st, const unsigned char *d_need, long coarse_order, int rank, int *d_err,
+                    double *d_sum6)
 {
   if (nrays <= 0) return 0;
   RayMaps m;
@@ -132,9 +159,11 @@ int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long 
   }
   const long nblocks = std::min<long>(ntiles, (long)sms * 4);
   const RingTab *tab = (mode & 2) ? ring_table(order, st) : nullptr;
+  if (d_sum6) CLB_CUDA_CHECK(cudaMemsetAsync(d_sum6, 0, 6 * sizeof(double), st));
   if (d_need && (coarse_order > order || !d_err)) d_need = nullptr;
   ray_step_kernel<<<(unsigned)nblocks, kRayThreads, 0, st>>>(d_rays, nrays, m, tab, order, wp, wpm1, wpm2, mode, d_need,
-                                                             (int)(2 * (order - coarse_order)), 1u << rank, d_err);
+                                                             (int)(2 * (order - coarse_order)), 1u << rank, d_err, d_sum6);
+  if (d_sum6) CLB_CUDA_CHECK(cudaGetLastError());
   CLB_CUDA_CHECK(cudaGetLastError());
   return 1;
 }

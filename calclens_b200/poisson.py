@@ -124,6 +124,7 @@ class LensPlaneSolver:
         self._dens_free = [None, None]   # event after the last kernel that read each density buffer
         self.fused = False
         self.halo_deg = float(halo_deg)
+        self.coarse_order = 5
         self._need = None          # device mask of the coarse cells each rank needs (fused exchange only)
         self._err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._peer_bufs = []
@@ -186,7 +187,6 @@ class LensPlaneSolver:
         # halo-limited map broadcast: a pixel goes to the ranks whose ray domain, grown by halo_deg, can reach it.
         # Cells of a coarse NEST grid stand in for the reference's halo bundle cells (raytrace_utils.c:116-161); the
         # margin adds two coarse cell radii (a HEALPix pixel's radius is < 1.2 x its mean spacing).
-        self.coarse_order = 5
         if self.halo_deg > 0 and self.order >= self.coarse_order:
             spacing = math.sqrt(4.0 * math.pi / (12 << (2 * self.coarse_order)))
             margin = math.radians(self.halo_deg) + 2.0 * 1.2 * spacing
@@ -290,17 +290,16 @@ class LensPlaneSolver:
             self.dist.all_reduce(self.maps, group=self.group)
         return self.maps
 
-    def ray_update(self, wpp1, wp, wpm1):
+    def ray_update(self, wpp1, wp, wpm1, with_summary=False):
         """zero + interpolate + propagate: rayprop_sphere(planeRadPlus1, planeRad, planeRadMinus1) as called at
-        raytrace.c:262, preceded by the reset of raytrace.c:213-230 and the interpolation of shtpoissonsolve.c:666-702."""
+        raytrace.c:262, preceded by the reset of raytrace.c:213-230 and the interpolation of shtpoissonsolve.c:666-702.
+        with_summary: also accumulate the six plane sums into self.summary (same kernel, no second pass)."""
         ptrs = (C.c_void_p * 6)(*[self.maps[k].data_ptr() for k in range(6)])
-        if self._need is not None:
-            self.lib.clb_ray_step_checked_dev(self.rays.data_ptr(), self.nrays, ptrs, self.order, float(wpp1), float(wp),
-                                              float(wpm1), MODE_ZERO | MODE_INTERP | MODE_PROP, self._need.data_ptr(),
-                                              self.coarse_order, self.rank, self._err.data_ptr(), self._stream())
-            return
-        self.lib.clb_ray_step_dev(self.rays.data_ptr(), self.nrays, ptrs, self.order, float(wpp1), float(wp), float(wpm1),
-                                  MODE_ZERO | MODE_INTERP | MODE_PROP, self._stream())
+        need = None if self._need is None else self._need.data_ptr()
+        self.lib.clb_ray_step_ex_dev(self.rays.data_ptr(), self.nrays, ptrs, self.order, float(wpp1), float(wp), float(wpm1),
+                                     MODE_ZERO | MODE_INTERP | MODE_PROP, need, self.coarse_order if need else 0, self.rank,
+                                     self._err.data_ptr() if need else None,
+                                     self.summary.data_ptr() if with_summary else None, self._stream())
 
     def check_halo(self):
         """Raise if a ray left the part of the sky this rank receives (the reference aborts on a missing map cell,
@@ -337,13 +336,12 @@ class LensPlaneSolver:
         ev = torch.cuda.Event(); ev.record()
         self._dens_free[k] = ev
         self._staged = (None, None, k, None)
-        self.ray_update(wpp1, wp, wpm1)
+        self.ray_update(wpp1, wp, wpm1, with_summary=read_summary)
         if prefetch is not None:
             self.prefetch(*prefetch)
             self._staged = self._next_staged
         if not read_summary:
             return None
-        self.lib.clb_ray_summary_dev(self.rays.data_ptr(), self.nrays, self.summary.data_ptr(), self._stream())
         if self.nranks > 1:
             self.dist.all_reduce(self.summary, group=self.group)
         out = self.summary.cpu().numpy()

@@ -88,11 +88,13 @@ void clb_sht_plan_set_peers(clb_sht_plan *plan, void *const *g_recv_ptrs, void *
 int clb_maps_broadcast_dev(const clb_sht_plan *plan, float *const local_maps[6], float *const *peer_maps,
                            const unsigned char *need, long coarse_order, void *stream);
 void clb_domain_masks(long ray_order, int nranks, long coarse_order, double margin_rad, unsigned char *mask);
-/* clb_ray_step_dev that also verifies, per ray, that its interpolation stencil lies inside the cells this rank received
- * (*err |= 1 otherwise; the reference aborts on a missing map cell, shtpoissonsolve.c:683-689) */
-int clb_ray_step_checked_dev(void *rays, long nrays, const float *const maps[6], long map_order, double wp, double wpm1,
-                             double wpm2, int mode, const unsigned char *need, long coarse_order, int rank, int *err,
-                             void *stream);
+/* clb_ray_step_dev with two optional extras: (need, coarse_order, rank, err) verifies, per ray, that its interpolation
+ * stencil lies inside the cells this rank received (*err |= 1 otherwise; the reference aborts on a missing map cell,
+ * shtpoissonsolve.c:683-689); sum6 (device, 6 doubles) receives the sums of clb_ray_summary_dev without a second pass
+ * over the rays.  Any of need / err / sum6 may be NULL. */
+int clb_ray_step_ex_dev(void *rays, long nrays, const float *const maps[6], long map_order, double wp, double wpm1,
+                        double wpm2, int mode, const unsigned char *need, long coarse_order, int rank, int *err,
+                        double *sum6, void *stream);
 
 /* ---- density scaling of shtpoissonsolve.c:426,454-502 (full-sky: no vacuum cells):
  * map = (map * premul) * densmul - backdens, all in float like the reference ---- */

@@ -418,3 +418,98 @@ def test_multi_gpu_step_matches_single_gpu(clb):
            "--master-port", "29517", os.path.join(root, "tests", "dist_gpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "DIST CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_fused_exchange_emulated_on_one_gpu(clb, nranks):
+    """The fused exchange (clb_sht_plan_set_peers): N ranks' plans on one device, every rank's producing kernels store
+    straight into the owners' receive buffers (here plain device buffers standing in for NVLink peer mappings), maps
+    assembled with clb_maps_broadcast_dev.  Result must equal the single-rank result bit for bit."""
+    import torch
+    from calclens_b200 import _lib
+    L = _lib.load()
+    order, lmax = 5, 64
+    npix = 12 << (2 * order)
+    rng = np.random.default_rng(43)
+    dm = torch.from_numpy(rng.normal(size=npix).astype(np.float32)).cuda()
+    single = clb.HEALPixSHTPlan(order, lmax)
+    s_re, s_im = single.legendre_analysis(single.ring_analysis(dm), poisson_filter=True)
+    s_maps = single.ring_synthesis(single.legendre_synthesis(s_re, s_im)).cpu().numpy()
+    plans = [clb.HEALPixSHTPlan(order, lmax, nranks=nranks, rank=r) for r in range(nranks)]
+    g_recv = [torch.full((2 * max(p.g_recv_total, 1),), float("nan"), dtype=torch.float64, device="cuda") for p in plans]
+    b_recv = [torch.full((2 * max(p.b_recv_total, 1),), float("nan"), dtype=torch.float64, device="cuda") for p in plans]
+    maps = [torch.zeros((6, npix), dtype=torch.float32, device="cuda") for _ in plans]
+    g_arr = (C.c_void_p * nranks)(*[t.data_ptr() for t in g_recv])
+    b_arr = (C.c_void_p * nranks)(*[t.data_ptr() for t in b_recv])
+    peer_maps = (C.c_void_p * (6 * nranks))(*[maps[q][k].data_ptr() for q in range(nranks) for k in range(6)])
+    for p in plans:
+        L.clb_sht_plan_set_peers(p._h, g_arr, b_arr)
+    for p in plans:                                   # producers of g: every rank's ring FFT
+        L.clb_ring_analysis_dev(p._h, dm.data_ptr(), None, None)
+    alms = [p.legendre_analysis(g, poisson_filter=True) for p, g in zip(plans, g_recv)]
+    for p, (are, aim) in zip(plans, alms):            # producers of b: every rank's Legendre synthesis
+        L.clb_legendre_synthesis_dev(p._h, are.data_ptr(), aim.data_ptr(), None, None)
+    for r, p in enumerate(plans):
+        p.ring_synthesis(b_recv[r], maps[r])
+    for r, p in enumerate(plans):
+        ptrs = (C.c_void_p * 6)(*[maps[r][k].data_ptr() for k in range(6)])
+        L.clb_maps_broadcast_dev(p._h, ptrs, peer_maps, None, 0, None)
+    torch.cuda.synchronize()
+    for r in range(nranks):
+        assert not torch.isnan(g_recv[r][:2 * plans[r].g_recv_total]).any() and not torch.isnan(b_recv[r][:2 * plans[r].b_recv_total]).any()
+        assert np.array_equal(maps[r].cpu().numpy(), s_maps), "rank %d maps differ from the single-rank maps" % r
+    for p in plans + [single]:
+        p.destroy()
+
+
+def test_load_density_matches_scale_density(clb):
+    """clb_load_density_dev (pinned host or device source, own rings) == copy + clb_scale_density_dev"""
+    import torch
+    from calclens_b200 import _lib
+    L = _lib.load()
+    order = 6
+    npix = 12 << (2 * order)
+    rng = np.random.default_rng(5)
+    host = torch.from_numpy((8.0 * rng.lognormal(sigma=0.5, size=npix)).astype(np.float32)).pin_memory()
+    pm, dmul, bd = float(np.float32(0.37)), float(np.float32(2.5e-4)), float(np.float32(1.1e-3))
+    ref = host.cuda()
+    L.clb_scale_density_dev(ref.data_ptr(), npix, pm, dmul, bd, None)
+    plan = clb.HEALPixSHTPlan(order, 2 << order)
+    for src in (host, host.cuda()):
+        dst = torch.zeros(npix, dtype=torch.float32, device="cuda")
+        L.clb_load_density_dev(plan._h, src.data_ptr(), dst.data_ptr(), pm, dmul, bd, None)
+        torch.cuda.synchronize()
+        assert torch.equal(dst, ref)
+    # a rank of a sharded plan touches only its own rings
+    p1 = clb.HEALPixSHTPlan(order, 2 << order, nranks=2, rank=1)
+    dst = torch.full((npix,), -7.0, dtype=torch.float32, device="cuda")
+    L.clb_load_density_dev(p1._h, host.data_ptr(), dst.data_ptr(), pm, dmul, bd, None)
+    torch.cuda.synchronize()
+    touched = dst != -7.0
+    assert torch.equal(dst[touched], ref[touched]) and 0.3 < float(touched.float().mean()) < 0.7
+    plan.destroy(); p1.destroy()
+
+
+def test_solver_step_prefetch_and_fused_summary(clb):
+    """LensPlaneSolver.step with the next plane prefetched from pinned host memory gives the same rays as without, and
+    the summary accumulated inside the ray kernel equals the separate summary kernel."""
+    import torch
+    from calclens_b200 import poisson
+    order, lmax = 6, 128
+    npix = 12 << (2 * order)
+    rng = np.random.default_rng(17)
+    maps = [torch.from_numpy((8.0 * rng.lognormal(sigma=0.5, size=npix)).astype(np.float32)).pin_memory() for _ in range(3)]
+    sc = (np.float32(1.0), np.float32(2e-4), np.float32(8.0 * np.exp(0.125) * 2e-4))
+    planes = [(45.0, 15.0, 0.0), (75.0, 45.0, 15.0), (105.0, 75.0, 45.0)]
+    a = poisson.LensPlaneSolver(order, lmax, order); a.init_rays(15.0)
+    b = poisson.LensPlaneSolver(order, lmax, order); b.init_rays(15.0)
+    for k, pl in enumerate(planes):
+        sa = a.step(maps[k], *sc, *pl)
+        nxt = (maps[k + 1],) + sc if k + 1 < len(planes) else None
+        sb = b.step(maps[k], *sc, *pl, prefetch=nxt)
+        # the six sums are accumulated with atomics (order varies) over values that largely cancel
+        assert np.allclose(sa, sb, rtol=1e-9, atol=1e-13)
+        ref = torch.zeros(6, dtype=torch.float64, device="cuda")
+        a.lib.clb_ray_summary_dev(a.rays.data_ptr(), a.nrays, ref.data_ptr(), None)
+        assert np.allclose(sa, ref.cpu().numpy(), rtol=1e-9, atol=1e-13)
+    assert np.array_equal(a.rays_host().view(np.uint8), b.rays_host().view(np.uint8))

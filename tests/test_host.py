@@ -126,3 +126,29 @@ def test_triple_count_matches_survey_table():
     # Nside 256 / lmax 512 -> 5.60e7 triples with the cut
     t = bench.triple_count(256, 512)
     assert abs(t / 5.60e7 - 1) < 0.01
+
+
+def test_domain_masks_cover_domains_and_halo():
+    """clb_domain_masks (host code of the library, no GPU): every coarse cell is needed by the rank that owns its rays,
+    margins only ever add ranks, a zero margin gives exactly the owners, and the needed fraction stays near 1/N + halo."""
+    import ctypes as C
+    import math
+    from calclens_b200 import _lib
+    L = _lib.load()
+    ray_order, co = 9, 4
+    nc = 12 << (2 * co)
+    nray = 12 << (2 * ray_order)
+    for nranks in (2, 3, 8):
+        own = np.zeros(nc, dtype=np.uint8)
+        L.clb_domain_masks(ray_order, nranks, co, 0.0, own.ctypes.data)
+        lo = np.arange(nc, dtype=np.int64) << (2 * (ray_order - co))
+        hi = lo + (1 << (2 * (ray_order - co)))
+        for q in range(nranks):
+            qlo, qhi = (nray * q) // nranks, (nray * (q + 1)) // nranks
+            expect = (lo < qhi) & (qlo < hi)
+            assert np.array_equal(((own >> q) & 1).astype(bool), expect)
+        wide = np.zeros(nc, dtype=np.uint8)
+        L.clb_domain_masks(ray_order, nranks, co, math.radians(8.0), wide.ctypes.data)
+        assert np.all((wide & own) == own) and np.any(wide != own)
+        frac = np.unpackbits(wide[:, None], axis=1).sum() / (nc * nranks)
+        assert 1.0 / nranks < frac < 1.0 / nranks + 0.45
