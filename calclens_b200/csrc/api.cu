@@ -74,7 +74,7 @@ void clb_set_tuning(int what, int value)
 {
   if (what == 0 && value >= 1 && value <= 4) g_syn_rings_per_thread = value;
   if (what == 3 && (value == 1 || value == 2 || value == 4)) g_leg_warps_per_cta = value;
-  if (what == 2 && (value == 256 || value == 512 || value == 1024)) g_fft_threads_big = value;   // read at plan creation
+  if (what == 2 && (value == 256 || value == 512 || value == 768 || value == 1024)) g_fft_threads_big = value;   // read at plan creation
   if (what == 1 && (value == 1 || value == 2 || value == 4 || value == 6 || value == 8 || value == 10 || value == 12)) g_ana_rings_per_thread = value;
 }
 

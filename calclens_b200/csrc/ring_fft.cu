@@ -84,78 +84,127 @@ __device__ __forceinline__ double2 unit_pi(long num, long den)
 // ---------------------------------------------------------------------------------------------------------------
 // CTA-cooperative in-place FFTs on shared memory (all threads of the block must call)
 // ---------------------------------------------------------------------------------------------------------------
+// Both directions run K = 4 radix-2 stages per pass in registers (radix 16): a thread gathers the 16 elements of one
+// butterfly group, applies the four stages with twiddles W^j, W^2j, W^4j, W^8j formed from ONE table look-up by
+// squaring (times compile-time 16th roots of unity), and scatters them back -- a quarter of the shared-memory
+// passes and an eighth of the twiddle look-ups of a radix-2 sweep.  A pass over fewer stages (K = 1..3) takes up the
+// remainder of log2(M).  Any split into consecutive radix-2 stages leaves the same bit-reversed ordering.
+
+// exp(-2 pi i q / 2^n), q < 2^(n-1), n <= 4
+__device__ __forceinline__ double2 root16(int n, int q)
+{
+  constexpr double c8 = 0.92387953251128675613, s8 = 0.38268343236508977173, h = 0.70710678118654752440;
+  const int k = q << (4 - n);   // index into the 16th roots, k < 8
+  switch (k) {
+    case 0: return make_double2(1.0, 0.0);
+    case 1: return make_double2(c8, -s8);
+    case 2: return make_double2(h, -h);
+    case 3: return make_double2(s8, -c8);
+    case 4: return make_double2(0.0, -1.0);
+    case 5: return make_double2(-s8, -c8);
+    case 6: return make_double2(-h, -h);
+    default: return make_double2(-c8, -s8);
+  }
+}
+
+// forward (sign -1) pass over the K stages with block lengths 2^lg, 2^(lg-1), .., 2^(lg-K+1)
+template <int K>
+__device__ __forceinline__ void cta_dif_pass(double2 *a, int M, int lg, const double2 *__restrict__ tw, int logTW)
+{
+  constexpr int RR = 1 << K;
+  const int s = 1 << (lg - K);
+  const int sh = logTW - lg;
+  for (int idx = threadIdx.x; idx < (M >> K); idx += blockDim.x) {
+    const int j = idx & (s - 1);
+    const int base = ((idx >> (lg - K)) << lg) + j;
+    double2 x[RR];
+#pragma unroll
+    for (int q = 0; q < RR; ++q) x[q] = a[base + q * s];
+    double2 w = __ldg(&tw[(size_t)j << sh]);   // W_L^j
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+      constexpr int dummy = 0; (void)dummy;
+      const int half = RR >> (t + 1);
+#pragma unroll
+      for (int g = 0; g < RR; g += 2 * half) {
+#pragma unroll
+        for (int q = 0; q < half; ++q) {
+          const double2 u = x[g + q], v = x[g + q + half];
+          x[g + q] = cadd(u, v);
+          const double2 d = csub(u, v);
+          x[g + q + half] = cmul(d, q == 0 ? w : cmul(w, root16(K - t, q)));
+        }
+      }
+      w = cmul(w, w);
+    }
+#pragma unroll
+    for (int q = 0; q < RR; ++q) a[base + q * s] = x[q];
+  }
+  __syncthreads();
+}
+
+// inverse (sign +1) pass: the same K stages in reverse order, conjugate twiddles applied before the butterflies
+template <int K>
+__device__ __forceinline__ void cta_dit_pass(double2 *a, int M, int lg, const double2 *__restrict__ tw, int logTW)
+{
+  constexpr int RR = 1 << K;
+  const int s = 1 << (lg - K);
+  const int sh = logTW - lg;
+  for (int idx = threadIdx.x; idx < (M >> K); idx += blockDim.x) {
+    const int j = idx & (s - 1);
+    const int base = ((idx >> (lg - K)) << lg) + j;
+    double2 x[RR];
+#pragma unroll
+    for (int q = 0; q < RR; ++q) x[q] = a[base + q * s];
+    double2 wp[K];                             // W_L^(j 2^t)
+    wp[0] = __ldg(&tw[(size_t)j << sh]);
+#pragma unroll
+    for (int t = 1; t < K; ++t) wp[t] = cmul(wp[t - 1], wp[t - 1]);
+#pragma unroll
+    for (int t = K - 1; t >= 0; --t) {
+      const int half = RR >> (t + 1);
+#pragma unroll
+      for (int g = 0; g < RR; g += 2 * half) {
+#pragma unroll
+        for (int q = 0; q < half; ++q) {
+          const double2 u = x[g + q];
+          const double2 v = cmulc(x[g + q + half], q == 0 ? wp[t] : cmul(wp[t], root16(K - t, q)));
+          x[g + q] = cadd(u, v);
+          x[g + q + half] = csub(u, v);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < RR; ++q) a[base + q * s] = x[q];
+  }
+  __syncthreads();
+}
+
 // forward, sign -1, natural order in -> bit-reversed order out
 __device__ void cta_fft_dif(double2 *a, int logM, const double2 *__restrict__ tw, int logTW)
 {
   const int M = 1 << logM;
   int lg = logM;
-  if (lg & 1) {   // one radix-2 stage first so the rest is radix-4
-    const int span = M >> 1;
-    const int sh = logTW - lg;   // TW / (2*span)
-    for (int idx = threadIdx.x; idx < span; idx += blockDim.x) {
-      double2 u = a[idx], v = a[idx + span];
-      double2 w = __ldg(&tw[(size_t)idx << sh]);
-      a[idx] = cadd(u, v);
-      a[idx + span] = cmul(csub(u, v), w);
-    }
-    __syncthreads();
-    lg -= 1;
+  switch (lg & 3) {   // the remainder stages first, then radix-16 passes
+    case 1: cta_dif_pass<1>(a, M, lg, tw, logTW); lg -= 1; break;
+    case 2: cta_dif_pass<2>(a, M, lg, tw, logTW); lg -= 2; break;
+    case 3: cta_dif_pass<3>(a, M, lg, tw, logTW); lg -= 3; break;
+    default: break;
   }
-  // now blocks of length 1<<lg, processed by fused radix-2x2 stages
-  for (; lg >= 2; lg -= 2) {
-    const int s = 1 << (lg - 2);        // quarter length
-    const int sh1 = logTW - lg;         // W_{4s}^j  = tw[j << sh1]
-    for (int idx = threadIdx.x; idx < (M >> 2); idx += blockDim.x) {
-      const int j = idx & (s - 1);
-      const int base = ((idx >> (lg - 2)) << lg) + j;
-      double2 a0 = a[base], a1 = a[base + s], a2 = a[base + 2 * s], a3 = a[base + 3 * s];
-      double2 w1 = __ldg(&tw[(size_t)j << sh1]);
-      double2 w2 = __ldg(&tw[(size_t)j << (sh1 + 1)]);
-      double2 b0 = cadd(a0, a2), b2 = cmul(csub(a0, a2), w1);
-      double2 b1 = cadd(a1, a3), b3 = cmul(mul_mi(csub(a1, a3)), w1);
-      a[base] = cadd(b0, b1);
-      a[base + s] = cmul(csub(b0, b1), w2);
-      a[base + 2 * s] = cadd(b2, b3);
-      a[base + 3 * s] = cmul(csub(b2, b3), w2);
-    }
-    __syncthreads();
-  }
+  for (; lg >= 4; lg -= 4) cta_dif_pass<4>(a, M, lg, tw, logTW);
 }
 
 // inverse (unnormalised), sign +1, bit-reversed order in -> natural order out
 __device__ void cta_fft_dit_inv(double2 *a, int logM, const double2 *__restrict__ tw, int logTW)
 {
   const int M = 1 << logM;
-  int lg = 2;
-  for (; lg <= logM; lg += 2) {
-    const int s = 1 << (lg - 2);
-    const int sh1 = logTW - lg;
-    for (int idx = threadIdx.x; idx < (M >> 2); idx += blockDim.x) {
-      const int j = idx & (s - 1);
-      const int base = ((idx >> (lg - 2)) << lg) + j;
-      double2 a0 = a[base], a1 = a[base + s], a2 = a[base + 2 * s], a3 = a[base + 3 * s];
-      double2 w1 = __ldg(&tw[(size_t)j << sh1]);
-      double2 w2 = __ldg(&tw[(size_t)j << (sh1 + 1)]);
-      double2 t1 = cmulc(a1, w2), t3 = cmulc(a3, w2);
-      double2 b0 = cadd(a0, t1), b1 = csub(a0, t1), b2 = cadd(a2, t3), b3 = csub(a2, t3);
-      double2 u2 = cmulc(b2, w1), u3 = mul_pi(cmulc(b3, w1));
-      a[base] = cadd(b0, u2);
-      a[base + 2 * s] = csub(b0, u2);
-      a[base + s] = cadd(b1, u3);
-      a[base + 3 * s] = csub(b1, u3);
-    }
-    __syncthreads();
-  }
-  if (logM & 1) {
-    const int span = M >> 1;
-    const int sh = logTW - logM;
-    for (int idx = threadIdx.x; idx < span; idx += blockDim.x) {
-      double2 u = a[idx];
-      double2 v = cmulc(a[idx + span], __ldg(&tw[(size_t)idx << sh]));
-      a[idx] = cadd(u, v);
-      a[idx + span] = csub(u, v);
-    }
-    __syncthreads();
+  int lg = 4;
+  for (; lg <= logM - (logM & 3); lg += 4) cta_dit_pass<4>(a, M, lg, tw, logTW);
+  switch (logM & 3) {
+    case 1: cta_dit_pass<1>(a, M, logM, tw, logTW); break;
+    case 2: cta_dit_pass<2>(a, M, logM, tw, logTW); break;
+    case 3: cta_dit_pass<3>(a, M, logM, tw, logTW); break;
+    default: break;
   }
 }
 
@@ -266,7 +315,7 @@ struct RingGeomDev {
   const long *startN, *startS;
 };
 
-__global__ void ring_analysis_kernel(const float *__restrict__ map, double2 *__restrict__ g_send, RingGeomDev geo,
+__global__ void __launch_bounds__(512) ring_analysis_kernel(const float *__restrict__ map, double2 *__restrict__ g_send, RingGeomDev geo,
                                      const int *__restrict__ class_rp, const int *__restrict__ rp_to_local,
                                      const long *__restrict__ m_goff, int lmax, const signed char *__restrict__ rp_logM,
                                      const signed char *__restrict__ rp_blu, int Mmax,
@@ -467,7 +516,7 @@ struct MapPtrs { float *p[6]; };
 
 // Shared memory: bufA[M] | bufB[r+1] | tail.  tail = float2 park[r] (Bluestein) or float2 Y[2r+1] (power of two,
 // reused as park).  On the Bluestein path the bins Y overlay bufA[M/2..M), which is unused until the zero fill.
-__global__ void ring_synthesis_kernel(const double2 *__restrict__ b_recv, MapPtrs maps, RingGeomDev geo,
+__global__ void __launch_bounds__(512) ring_synthesis_kernel(const double2 *__restrict__ b_recv, MapPtrs maps, RingGeomDev geo,
                                       const int *__restrict__ class_rp, const int *__restrict__ rp_to_local,
                                       const long *__restrict__ m_boff, int nslot_loc, int lmax,
                                       const signed char *__restrict__ rp_logM, const signed char *__restrict__ rp_blu,

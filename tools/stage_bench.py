@@ -12,6 +12,7 @@ for a in sys.argv[3:]:
     if a.startswith("syn="): syn = [int(x) for x in a[4:].split(",")]
     elif a.startswith("ana="): ana = [int(x) for x in a[4:].split(",")]
     elif a.startswith("warps="): _lib.load().clb_set_tuning(3, int(a[6:]))
+    elif a.startswith("fft="): _lib.load().clb_set_tuning(2, int(a[4:]))
     else: reps = int(a)
 L = _lib.load()
 plan = clb.HEALPixSHTPlan(order, lmax)
