@@ -145,7 +145,8 @@ __device__ __forceinline__ void cta_dif_pass(double2 *a, int M, int lg, const do
 
 // inverse (sign +1) pass: the same K stages in reverse order, conjugate twiddles applied before the butterflies
 template <int K>
-__device__ __forceinline__ void cta_dit_pass(double2 *a, int M, int lg, const double2 *__restrict__ tw, int logTW)
+__device__ __forceinline__ void cta_dit_pass(double2 *a, int M, int lg, const double2 *__restrict__ tw, int logTW,
+                                             const double2 *__restrict__ premul = nullptr)
 {
   constexpr int RR = 1 << K;
   const int s = 1 << (lg - K);
@@ -156,6 +157,10 @@ __device__ __forceinline__ void cta_dit_pass(double2 *a, int M, int lg, const do
     double2 x[RR];
 #pragma unroll
     for (int q = 0; q < RR; ++q) x[q] = a[base + q * s];
+    if (premul) {   // pointwise product with a table in the same (bit-reversed) order, fused into the first pass
+#pragma unroll
+      for (int q = 0; q < RR; ++q) x[q] = cmul(x[q], __ldg(&premul[base + q * s]));
+    }
     double2 wp[K];                             // W_L^(j 2^t)
     wp[0] = __ldg(&tw[(size_t)j << sh]);
 #pragma unroll
@@ -195,15 +200,17 @@ __device__ void cta_fft_dif(double2 *a, int logM, const double2 *__restrict__ tw
 }
 
 // inverse (unnormalised), sign +1, bit-reversed order in -> natural order out
-__device__ void cta_fft_dit_inv(double2 *a, int logM, const double2 *__restrict__ tw, int logTW)
+// premul (optional): the spectrum is multiplied by this table (same order) on its way into the first pass
+__device__ void cta_fft_dit_inv(double2 *a, int logM, const double2 *__restrict__ tw, int logTW,
+                                const double2 *__restrict__ premul = nullptr)
 {
   const int M = 1 << logM;
   int lg = 4;
-  for (; lg <= logM - (logM & 3); lg += 4) cta_dit_pass<4>(a, M, lg, tw, logTW);
+  for (; lg <= logM - (logM & 3); lg += 4) { cta_dit_pass<4>(a, M, lg, tw, logTW, premul); premul = nullptr; }
   switch (logM & 3) {
-    case 1: cta_dit_pass<1>(a, M, logM, tw, logTW); break;
-    case 2: cta_dit_pass<2>(a, M, logM, tw, logTW); break;
-    case 3: cta_dit_pass<3>(a, M, logM, tw, logTW); break;
+    case 1: cta_dit_pass<1>(a, M, logM, tw, logTW, premul); break;
+    case 2: cta_dit_pass<2>(a, M, logM, tw, logTW, premul); break;
+    case 3: cta_dit_pass<3>(a, M, logM, tw, logTW, premul); break;
     default: break;
   }
 }
@@ -234,17 +241,27 @@ __device__ __forceinline__ int bitrev(int v, int bits) { return bits ? (int)(__b
 
 // Forward DFT of length r held in a[0..r) (natural order).  Bluestein path: caller has ALREADY multiplied by the
 // chirp and zero-filled a[r..M).  On return element k of the spectrum is dft_get(a, k, ...).
+// final_chirp = false leaves the last chirp product of the Bluestein path to the caller (dft_get_chirp).
 __device__ void cta_dft_r(double2 *a, int r, int logM, int bluestein, const double2 *__restrict__ chirp,
-                          const double2 *__restrict__ bhat, const double2 *__restrict__ tw, int logTW)
+                          const double2 *__restrict__ bhat, const double2 *__restrict__ tw, int logTW,
+                          bool final_chirp = true)
 {
   cta_fft_dif(a, logM, tw, logTW);
   if (!bluestein) return;
   const int M = 1 << logM;
+  // (fusing this product into the first inverse pass costs more than it saves: the pass reads 16 consecutive
+  // elements per thread, which turns the coalesced table read into 32 wavefronts per load)
   for (int k = threadIdx.x; k < M; k += blockDim.x) a[k] = cmul(a[k], __ldg(&bhat[k]));
   __syncthreads();
   cta_fft_dit_inv(a, logM, tw, logTW);
+  if (!final_chirp) return;
   for (int k = threadIdx.x; k < r; k += blockDim.x) a[k] = cmul(a[k], __ldg(&chirp[k]));
   __syncthreads();
+}
+__device__ __forceinline__ double2 dft_get_chirp(const double2 *a, int k, int logM, int bluestein,
+                                                 const double2 *__restrict__ chirp)
+{
+  return bluestein ? cmul(a[k], __ldg(&chirp[k])) : a[bitrev(k, logM)];
 }
 __device__ __forceinline__ double2 dft_get(const double2 *a, int k, int logM, int bluestein)
 {
@@ -390,9 +407,9 @@ __global__ void __launch_bounds__(512) ring_analysis_kernel(const float *__restr
       bufA[j] = z;
     }
     __syncthreads();
-    cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW);
+    cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW, pass != 0);
     if (pass == 0) {
-      for (int k = threadIdx.x; k < r; k += blockDim.x) bufB[k] = dft_get(bufA, k, logM, bluestein);
+      for (int k = threadIdx.x; k < r; k += blockDim.x) bufB[k] = dft_get_chirp(bufA, k, logM, bluestein, chirp);
       __syncthreads();
     }
   }
@@ -607,10 +624,10 @@ __global__ void __launch_bounds__(512) ring_synthesis_kernel(const double2 *__re
   __syncthreads();
   for (int k = r + threadIdx.x; k < M; k += blockDim.x) bufA[k] = make_double2(0.0, 0.0);
   __syncthreads();
-  cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW);
+  cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW, false);
   // S5: x^(0)_j = Re(res_j), x^(1)_j = -Im(res_j), rounded to float like the reference's c2r output
   for (int j = threadIdx.x; j < r; j += blockDim.x) {
-    double2 res = dft_get(bufA, j, logM, bluestein);
+    double2 res = dft_get_chirp(bufA, j, logM, bluestein, chirp);
     park[j] = make_float2(__double2float_rn(res.x), __double2float_rn(-res.y));
   }
   __syncthreads();
@@ -620,12 +637,12 @@ __global__ void __launch_bounds__(512) ring_synthesis_kernel(const double2 *__re
     bufA[j] = z;
   }
   __syncthreads();
-  cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW);
+  cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW, false);
   // S7: float4 of four consecutive pixels, 1/sin(theta) scalings        [alm2allmaps_transpose_mpi.c:1045-1051]
   const double sth = geo.sth[rp];
   float4 *out = reinterpret_cast<float4 *>(maps.p[field] + start);
   for (int j = threadIdx.x; j < r; j += blockDim.x) {
-    double2 res = dft_get(bufA, j, logM, bluestein);
+    double2 res = dft_get_chirp(bufA, j, logM, bluestein, chirp);
     float2 a = park[j];
     float v[4] = {a.x, a.y, __double2float_rn(res.x), __double2float_rn(-res.y)};
 #pragma unroll
