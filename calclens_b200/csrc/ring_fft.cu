@@ -70,6 +70,12 @@ __device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -
 __device__ __forceinline__ double2 mul_mi(double2 a) { return make_double2(a.y, -a.x); }   // a * (-i)
 __device__ __forceinline__ double2 mul_pi(double2 a) { return make_double2(-a.y, a.x); }   // a * (+i)
 
+// Work buffers of the CTA FFTs are stored XOR-swizzled: logical element i lives at i ^ ((i >> 4) & 15).  The last
+// radix-16 pass has every thread touch 16 consecutive elements (thread stride 256 bytes); unswizzled, the eight
+// threads of a quarter warp would hit the same four banks (8-way conflict on every 16-byte access).  The swizzle
+// permutes elements inside aligned runs of 16, so passes whose threads walk consecutive elements stay conflict free.
+__device__ __forceinline__ int swz(int i) { return i ^ ((i >> 4) & 15); }
+
 // exp(i * pi * num / den) for integers, exact argument reduction
 __device__ __forceinline__ double2 unit_pi(long num, long den)
 {
@@ -119,7 +125,7 @@ __device__ __forceinline__ void cta_dif_pass(double2 *a, int M, int lg, const do
     const int base = ((idx >> (lg - K)) << lg) + j;
     double2 x[RR];
 #pragma unroll
-    for (int q = 0; q < RR; ++q) x[q] = a[base + q * s];
+    for (int q = 0; q < RR; ++q) x[q] = a[swz(base + q * s)];
     double2 w = __ldg(&tw[(size_t)j << sh]);   // W_L^j
 #pragma unroll
     for (int t = 0; t < K; ++t) {
@@ -138,7 +144,7 @@ __device__ __forceinline__ void cta_dif_pass(double2 *a, int M, int lg, const do
       w = cmul(w, w);
     }
 #pragma unroll
-    for (int q = 0; q < RR; ++q) a[base + q * s] = x[q];
+    for (int q = 0; q < RR; ++q) a[swz(base + q * s)] = x[q];
   }
   __syncthreads();
 }
@@ -156,7 +162,7 @@ __device__ __forceinline__ void cta_dit_pass(double2 *a, int M, int lg, const do
     const int base = ((idx >> (lg - K)) << lg) + j;
     double2 x[RR];
 #pragma unroll
-    for (int q = 0; q < RR; ++q) x[q] = a[base + q * s];
+    for (int q = 0; q < RR; ++q) x[q] = a[swz(base + q * s)];
     if (premul) {   // pointwise product with a table in the same (bit-reversed) order, fused into the first pass
 #pragma unroll
       for (int q = 0; q < RR; ++q) x[q] = cmul(x[q], __ldg(&premul[base + q * s]));
@@ -180,7 +186,7 @@ __device__ __forceinline__ void cta_dit_pass(double2 *a, int M, int lg, const do
       }
     }
 #pragma unroll
-    for (int q = 0; q < RR; ++q) a[base + q * s] = x[q];
+    for (int q = 0; q < RR; ++q) a[swz(base + q * s)] = x[q];
   }
   __syncthreads();
 }
@@ -251,21 +257,21 @@ __device__ void cta_dft_r(double2 *a, int r, int logM, int bluestein, const doub
   const int M = 1 << logM;
   // (fusing this product into the first inverse pass costs more than it saves: the pass reads 16 consecutive
   // elements per thread, which turns the coalesced table read into 32 wavefronts per load)
-  for (int k = threadIdx.x; k < M; k += blockDim.x) a[k] = cmul(a[k], __ldg(&bhat[k]));
+  for (int k = threadIdx.x; k < M; k += blockDim.x) a[swz(k)] = cmul(a[swz(k)], __ldg(&bhat[k]));
   __syncthreads();
   cta_fft_dit_inv(a, logM, tw, logTW);
   if (!final_chirp) return;
-  for (int k = threadIdx.x; k < r; k += blockDim.x) a[k] = cmul(a[k], __ldg(&chirp[k]));
+  for (int k = threadIdx.x; k < r; k += blockDim.x) a[swz(k)] = cmul(a[swz(k)], __ldg(&chirp[k]));
   __syncthreads();
 }
 __device__ __forceinline__ double2 dft_get_chirp(const double2 *a, int k, int logM, int bluestein,
                                                  const double2 *__restrict__ chirp)
 {
-  return bluestein ? cmul(a[k], __ldg(&chirp[k])) : a[bitrev(k, logM)];
+  return bluestein ? cmul(a[swz(k)], __ldg(&chirp[k])) : a[swz(bitrev(k, logM))];
 }
 __device__ __forceinline__ double2 dft_get(const double2 *a, int k, int logM, int bluestein)
 {
-  return bluestein ? a[k] : a[bitrev(k, logM)];
+  return bluestein ? a[swz(k)] : a[swz(bitrev(k, logM))];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -282,20 +288,20 @@ __global__ void bluestein_table_kernel(const int *__restrict__ rlist, const long
   const int M = 1 << logM;
   double2 *chirp = chirp_all + chirp_off[r];
   double2 *bhat = bhat_all + bhat_off[r];
-  for (int k = threadIdx.x; k < M; k += blockDim.x) smem[k] = make_double2(0.0, 0.0);
+  for (int k = threadIdx.x; k < M; k += blockDim.x) smem[k] = make_double2(0.0, 0.0);   // (all of it: order irrelevant)
   __syncthreads();
   for (int j = threadIdx.x; j < r; j += blockDim.x) {
     long j2 = ((long)j * j) % (2L * r);
     double2 w = unit_pi(-j2, r);       // exp(-i pi j^2 / r)
     chirp[j] = w;
     double2 c = cconj(w);
-    smem[j] = c;
-    if (j) smem[M - j] = c;
+    smem[swz(j)] = c;
+    if (j) smem[swz(M - j)] = c;
   }
   __syncthreads();
   cta_fft_dif(smem, logM, tw, logTW);
   const double inv = 1.0 / (double)M;   // fold the inverse-FFT normalisation into the table (exact power of two)
-  for (int k = threadIdx.x; k < M; k += blockDim.x) bhat[k] = make_double2(smem[k].x * inv, smem[k].y * inv);
+  for (int k = threadIdx.x; k < M; k += blockDim.x) bhat[k] = make_double2(smem[swz(k)].x * inv, smem[swz(k)].y * inv);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -404,7 +410,7 @@ __global__ void __launch_bounds__(512) ring_analysis_kernel(const float *__restr
         z = make_double2((double)xa, (double)xb);
         if (bluestein) z = cmul(z, __ldg(&chirp[j]));
       }
-      bufA[j] = z;
+      bufA[swz(j)] = z;
     }
     __syncthreads();
     cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW, pass != 0);
@@ -619,10 +625,10 @@ __global__ void __launch_bounds__(512) ring_synthesis_kernel(const double2 *__re
     double2 v1 = cconj(cadd(T0, mul_pi(U1)));
     double2 v2 = cconj(cadd(U2, mul_pi(U3)));
     bufB[k0] = v2;
-    bufA[k0] = bluestein ? cmul(v1, __ldg(&chirp[k0])) : v1;
+    bufA[swz(k0)] = bluestein ? cmul(v1, __ldg(&chirp[k0])) : v1;
   }
   __syncthreads();
-  for (int k = r + threadIdx.x; k < M; k += blockDim.x) bufA[k] = make_double2(0.0, 0.0);
+  for (int k = r + threadIdx.x; k < M; k += blockDim.x) bufA[swz(k)] = make_double2(0.0, 0.0);
   __syncthreads();
   cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW, false);
   // S5: x^(0)_j = Re(res_j), x^(1)_j = -Im(res_j), rounded to float like the reference's c2r output
@@ -634,7 +640,7 @@ __global__ void __launch_bounds__(512) ring_synthesis_kernel(const double2 *__re
   for (int j = threadIdx.x; j < M; j += blockDim.x) {
     double2 z = make_double2(0.0, 0.0);
     if (j < r) { z = bufB[j]; if (bluestein) z = cmul(z, __ldg(&chirp[j])); }
-    bufA[j] = z;
+    bufA[swz(j)] = z;
   }
   __syncthreads();
   cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW, false);
