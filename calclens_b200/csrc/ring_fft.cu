@@ -74,7 +74,14 @@ __device__ __forceinline__ double2 mul_pi(double2 a) { return make_double2(-a.y,
 // radix-16 pass has every thread touch 16 consecutive elements (thread stride 256 bytes); unswizzled, the eight
 // threads of a quarter warp would hit the same four banks (8-way conflict on every 16-byte access).  The swizzle
 // permutes elements inside aligned runs of 16, so passes whose threads walk consecutive elements stay conflict free.
-__device__ __forceinline__ int swz(int i) { return i ^ ((i >> 4) & 15); }
+// The power-of-two path also reads its result in bit-reversed order (consecutive threads differ in the TOP bits of
+// the index), so the top three bits are folded into the swizzle as well (only bits >= 4 feed the XOR: a bijection).
+__device__ __forceinline__ int swz(int i, int logM)
+{
+  int x = (i >> 4) & 15;
+  if (logM >= 7) x ^= (i >> (logM - 3)) & 7;
+  return i ^ x;
+}
 
 // exp(i * pi * num / den) for integers, exact argument reduction
 __device__ __forceinline__ double2 unit_pi(long num, long den)
@@ -115,17 +122,22 @@ __device__ __forceinline__ double2 root16(int n, int q)
 
 // forward (sign -1) pass over the K stages with block lengths 2^lg, 2^(lg-1), .., 2^(lg-K+1)
 template <int K>
-__device__ __forceinline__ void cta_dif_pass(double2 *a, int M, int lg, const double2 *__restrict__ tw, int logTW)
+__device__ __forceinline__ void cta_dif_pass(double2 *a, int M, int lg, const double2 *__restrict__ tw, int logTW,
+                                             double2 *a2 = nullptr)
 {
   constexpr int RR = 1 << K;
   const int s = 1 << (lg - K);
   const int sh = logTW - lg;
-  for (int idx = threadIdx.x; idx < (M >> K); idx += blockDim.x) {
+  const int logM = 31 - __clz(M);
+  const int nbf = M >> K;                      // butterflies per array; a2 (optional) is a second, independent array
+  for (int it = threadIdx.x; it < (a2 ? 2 * nbf : nbf); it += blockDim.x) {
+    double2 *arr = (it >= nbf) ? a2 : a;
+    const int idx = (it >= nbf) ? it - nbf : it;
     const int j = idx & (s - 1);
     const int base = ((idx >> (lg - K)) << lg) + j;
     double2 x[RR];
 #pragma unroll
-    for (int q = 0; q < RR; ++q) x[q] = a[swz(base + q * s)];
+    for (int q = 0; q < RR; ++q) x[q] = arr[swz(base + q * s, logM)];
     double2 w = __ldg(&tw[(size_t)j << sh]);   // W_L^j
 #pragma unroll
     for (int t = 0; t < K; ++t) {
@@ -144,7 +156,7 @@ __device__ __forceinline__ void cta_dif_pass(double2 *a, int M, int lg, const do
       w = cmul(w, w);
     }
 #pragma unroll
-    for (int q = 0; q < RR; ++q) a[swz(base + q * s)] = x[q];
+    for (int q = 0; q < RR; ++q) arr[swz(base + q * s, logM)] = x[q];
   }
   __syncthreads();
 }
@@ -157,12 +169,13 @@ __device__ __forceinline__ void cta_dit_pass(double2 *a, int M, int lg, const do
   constexpr int RR = 1 << K;
   const int s = 1 << (lg - K);
   const int sh = logTW - lg;
+  const int logM = 31 - __clz(M);
   for (int idx = threadIdx.x; idx < (M >> K); idx += blockDim.x) {
     const int j = idx & (s - 1);
     const int base = ((idx >> (lg - K)) << lg) + j;
     double2 x[RR];
 #pragma unroll
-    for (int q = 0; q < RR; ++q) x[q] = a[swz(base + q * s)];
+    for (int q = 0; q < RR; ++q) x[q] = a[swz(base + q * s, logM)];
     if (premul) {   // pointwise product with a table in the same (bit-reversed) order, fused into the first pass
 #pragma unroll
       for (int q = 0; q < RR; ++q) x[q] = cmul(x[q], __ldg(&premul[base + q * s]));
@@ -186,23 +199,24 @@ __device__ __forceinline__ void cta_dit_pass(double2 *a, int M, int lg, const do
       }
     }
 #pragma unroll
-    for (int q = 0; q < RR; ++q) a[swz(base + q * s)] = x[q];
+    for (int q = 0; q < RR; ++q) a[swz(base + q * s, logM)] = x[q];
   }
   __syncthreads();
 }
 
 // forward, sign -1, natural order in -> bit-reversed order out
-__device__ void cta_fft_dif(double2 *a, int logM, const double2 *__restrict__ tw, int logTW)
+// a2 (optional): a second array of the same length transformed in the same passes
+__device__ void cta_fft_dif(double2 *a, int logM, const double2 *__restrict__ tw, int logTW, double2 *a2 = nullptr)
 {
   const int M = 1 << logM;
   int lg = logM;
   switch (lg & 3) {   // the remainder stages first, then radix-16 passes
-    case 1: cta_dif_pass<1>(a, M, lg, tw, logTW); lg -= 1; break;
-    case 2: cta_dif_pass<2>(a, M, lg, tw, logTW); lg -= 2; break;
-    case 3: cta_dif_pass<3>(a, M, lg, tw, logTW); lg -= 3; break;
+    case 1: cta_dif_pass<1>(a, M, lg, tw, logTW, a2); lg -= 1; break;
+    case 2: cta_dif_pass<2>(a, M, lg, tw, logTW, a2); lg -= 2; break;
+    case 3: cta_dif_pass<3>(a, M, lg, tw, logTW, a2); lg -= 3; break;
     default: break;
   }
-  for (; lg >= 4; lg -= 4) cta_dif_pass<4>(a, M, lg, tw, logTW);
+  for (; lg >= 4; lg -= 4) cta_dif_pass<4>(a, M, lg, tw, logTW, a2);
 }
 
 // inverse (unnormalised), sign +1, bit-reversed order in -> natural order out
@@ -257,21 +271,21 @@ __device__ void cta_dft_r(double2 *a, int r, int logM, int bluestein, const doub
   const int M = 1 << logM;
   // (fusing this product into the first inverse pass costs more than it saves: the pass reads 16 consecutive
   // elements per thread, which turns the coalesced table read into 32 wavefronts per load)
-  for (int k = threadIdx.x; k < M; k += blockDim.x) a[swz(k)] = cmul(a[swz(k)], __ldg(&bhat[k]));
+  for (int k = threadIdx.x; k < M; k += blockDim.x) a[swz(k, logM)] = cmul(a[swz(k, logM)], __ldg(&bhat[k]));
   __syncthreads();
   cta_fft_dit_inv(a, logM, tw, logTW);
   if (!final_chirp) return;
-  for (int k = threadIdx.x; k < r; k += blockDim.x) a[swz(k)] = cmul(a[swz(k)], __ldg(&chirp[k]));
+  for (int k = threadIdx.x; k < r; k += blockDim.x) a[swz(k, logM)] = cmul(a[swz(k, logM)], __ldg(&chirp[k]));
   __syncthreads();
 }
 __device__ __forceinline__ double2 dft_get_chirp(const double2 *a, int k, int logM, int bluestein,
                                                  const double2 *__restrict__ chirp)
 {
-  return bluestein ? cmul(a[swz(k)], __ldg(&chirp[k])) : a[swz(bitrev(k, logM))];
+  return bluestein ? cmul(a[swz(k, logM)], __ldg(&chirp[k])) : a[swz(bitrev(k, logM), logM)];
 }
 __device__ __forceinline__ double2 dft_get(const double2 *a, int k, int logM, int bluestein)
 {
-  return bluestein ? a[swz(k)] : a[swz(bitrev(k, logM))];
+  return bluestein ? a[swz(k, logM)] : a[swz(bitrev(k, logM), logM)];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -295,13 +309,13 @@ __global__ void bluestein_table_kernel(const int *__restrict__ rlist, const long
     double2 w = unit_pi(-j2, r);       // exp(-i pi j^2 / r)
     chirp[j] = w;
     double2 c = cconj(w);
-    smem[swz(j)] = c;
-    if (j) smem[swz(M - j)] = c;
+    smem[swz(j, logM)] = c;
+    if (j) smem[swz(M - j, logM)] = c;
   }
   __syncthreads();
   cta_fft_dif(smem, logM, tw, logTW);
   const double inv = 1.0 / (double)M;   // fold the inverse-FFT normalisation into the table (exact power of two)
-  for (int k = threadIdx.x; k < M; k += blockDim.x) bhat[k] = make_double2(smem[swz(k)].x * inv, smem[swz(k)].y * inv);
+  for (int k = threadIdx.x; k < M; k += blockDim.x) bhat[k] = make_double2(smem[swz(k, logM)].x * inv, smem[swz(k, logM)].y * inv);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -410,7 +424,7 @@ __global__ void __launch_bounds__(512) ring_analysis_kernel(const float *__restr
         z = make_double2((double)xa, (double)xb);
         if (bluestein) z = cmul(z, __ldg(&chirp[j]));
       }
-      bufA[swz(j)] = z;
+      bufA[swz(j, logM)] = z;
     }
     __syncthreads();
     cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW, pass != 0);
@@ -482,6 +496,12 @@ __device__ __forceinline__ float2 fold_bin(const double2 *__restrict__ b_recv, c
   // negative-m terms (t odd) add conj(b).  Sign: skfact = -1 when the ring is shifted and the wrap count is odd
   // (wrap count = j for the positive term of round j, j+1 for the negative one).
   float re = 0.f, im = 0.f;
+  // common case (every ring with more than lmax pixels, except near its Nyquist bin): only m = k lands in this bin
+  if (n - k > lmax && (k > 0 || n > lmax)) {
+    if (k > lmax) return make_float2(0.f, 0.f);
+    const double2 b = __ldg(&b_recv[m_boff[k] + fslot]);
+    return make_float2(__double2float_rn(__dadd_rn(0.0, b.x)), __double2float_rn(__dadd_rn(0.0, b.y)));
+  }
   auto term_m = [&](int t) -> long {
     if (k == 0) return (long)((t + 1) >> 1) * n;
     return (long)((t + 1) >> 1) * n + ((t & 1) ? -k : k);
@@ -624,32 +644,44 @@ __global__ void __launch_bounds__(512) ring_synthesis_kernel(const double2 *__re
     double2 U1 = cmul(T1, E1), U2 = cmul(T2, E2), U3 = cmul(T3, E3);
     double2 v1 = cconj(cadd(T0, mul_pi(U1)));
     double2 v2 = cconj(cadd(U2, mul_pi(U3)));
-    bufB[k0] = v2;
-    bufA[swz(k0)] = bluestein ? cmul(v1, __ldg(&chirp[k0])) : v1;
+    if (bluestein) { bufB[k0] = v2; bufA[swz(k0, logM)] = cmul(v1, __ldg(&chirp[k0])); }
+    else { bufB[swz(k0, logM)] = v2; bufA[swz(k0, logM)] = v1; }
   }
   __syncthreads();
-  for (int k = r + threadIdx.x; k < M; k += blockDim.x) bufA[swz(k)] = make_double2(0.0, 0.0);
-  __syncthreads();
-  cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW, false);
-  // S5: x^(0)_j = Re(res_j), x^(1)_j = -Im(res_j), rounded to float like the reference's c2r output
-  for (int j = threadIdx.x; j < r; j += blockDim.x) {
-    double2 res = dft_get_chirp(bufA, j, logM, bluestein, chirp);
-    park[j] = make_float2(__double2float_rn(res.x), __double2float_rn(-res.y));
+  if (!bluestein) {
+    // power-of-two ring: both length-r transforms run in the same passes (all threads busy, half the barriers)
+    cta_fft_dif(bufA, logM, tw, logTW, bufB);
+  } else {
+    for (int k = r + threadIdx.x; k < M; k += blockDim.x) bufA[swz(k, logM)] = make_double2(0.0, 0.0);
+    __syncthreads();
+    cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW, false);
+    // S5: x^(0)_j = Re(res_j), x^(1)_j = -Im(res_j), rounded to float like the reference's c2r output
+    for (int j = threadIdx.x; j < r; j += blockDim.x) {
+      double2 res = dft_get_chirp(bufA, j, logM, bluestein, chirp);
+      park[j] = make_float2(__double2float_rn(res.x), __double2float_rn(-res.y));
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+      double2 z = make_double2(0.0, 0.0);
+      if (j < r) z = cmul(bufB[j], __ldg(&chirp[j]));
+      bufA[swz(j, logM)] = z;
+    }
+    __syncthreads();
+    cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW, false);
   }
-  __syncthreads();
-  for (int j = threadIdx.x; j < M; j += blockDim.x) {
-    double2 z = make_double2(0.0, 0.0);
-    if (j < r) { z = bufB[j]; if (bluestein) z = cmul(z, __ldg(&chirp[j])); }
-    bufA[swz(j)] = z;
-  }
-  __syncthreads();
-  cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW, false);
   // S7: float4 of four consecutive pixels, 1/sin(theta) scalings        [alm2allmaps_transpose_mpi.c:1045-1051]
   const double sth = geo.sth[rp];
   float4 *out = reinterpret_cast<float4 *>(maps.p[field] + start);
   for (int j = threadIdx.x; j < r; j += blockDim.x) {
-    double2 res = dft_get_chirp(bufA, j, logM, bluestein, chirp);
-    float2 a = park[j];
+    double2 res;
+    float2 a;
+    if (bluestein) { res = dft_get_chirp(bufA, j, logM, bluestein, chirp); a = park[j]; }
+    else {
+      const int jr = swz(bitrev(j, logM), logM);
+      const double2 r1 = bufA[jr];
+      res = bufB[jr];
+      a = make_float2(__double2float_rn(r1.x), __double2float_rn(-r1.y));
+    }
     float v[4] = {a.x, a.y, __double2float_rn(res.x), __double2float_rn(-res.y)};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
