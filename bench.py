@@ -54,7 +54,10 @@ def work_model(nside, lmax, nrays):
     rings = 4 * nside - 1
     return dict(
         tri=tri,
-        flops_analysis=8.0 * tri, flops_synthesis=20.0 * tri,
+        # analysis: recurrence (DMUL + DFMA) + two accumulate DFMA per triple = 8 flop.  synthesis: SURVEY.md section 8d
+        # counts 20 (recurrence + four complex sums); the three-sum formulation used here needs
+        # 16, and that is the figure the roofline uses -- work that a better algorithm does not need is not "achieved"
+        flops_analysis=8.0 * tri, flops_synthesis=16.0 * tri, flops_synthesis_survey=20.0 * tri,
         bytes_fft_analysis=4.0 * npix + 16.0 * rings * (lmax + 1),
         bytes_fft_synthesis=6.0 * (16.0 * rings * (lmax + 1) + 4.0 * npix),
         bytes_rays=448.0 * nrays)
@@ -410,13 +413,19 @@ def main():
         ach_syn = wm["flops_synthesis"] / world / (stage_ms["legendre_synthesis"] * 1e-3) / 1e12
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(HERE, "profiles", "r01_traffic.json"))).get("legendre_synthesis_dram_bytes_per_launch")
+            tj = json.load(open(os.path.join(HERE, "profiles", "r01_traffic.json")))
+            if world == 1 and a.nside == 4096 and a.lmax == 8192:
+                traffic = tj.get("legendre_synthesis", {}).get("dram_bytes_per_launch")
         except Exception:
             pass
         roofline = {"kernel": "legendre_synthesis_kernel (dominant)", "bound": "fp64", "achieved": ach_syn, "peak": fp64_peak, "unit": "TFLOP/s",
                     "frac": ach_syn / fp64_peak, "traffic": traffic,
                     "peak_source": fp64_src, "algorithmic_flops_per_launch": wm["flops_synthesis"] / world,
-                    "note": "algorithmic 20 flop per (m, ring pair, l) triple (SURVEY.md 8d); the kernel executes 16 (three complex sums + 2-instruction recurrence)"}
+                    "note": "FP64 FMA-pipe roofline (not tensor: B200's DMMA rate equals its DFMA rate and the recurrence is serial per ring). "
+                            "algorithmic = 16 flop per (m, ring pair, l) triple of the reference's lmin cut: 2-instruction recurrence + three "
+                            "complex sums (DESIGN.md section 4); with SURVEY.md 8d's four-sum count of 20 the same time gives %.2f TFLOP/s. "
+                            "traffic = dram bytes of one launch from profiles/ (ncu --set full)" % (
+                                wm["flops_synthesis_survey"] / world / (stage_ms["legendre_synthesis"] * 1e-3) / 1e12)}
         stages = {
             "legendre_analysis": {"bound": "fp64", "achieved": wm["flops_analysis"] / world / (stage_ms["legendre_analysis"] * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s"},
             "fft_analysis": {"bound": "hbm", "achieved": wm["bytes_fft_analysis"] / world / (stage_ms["fft_analysis"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"},
