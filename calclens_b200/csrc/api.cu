@@ -25,7 +25,7 @@ int launch_maps_broadcast(const ShtPlan *p, float *const local_maps[6], float *c
                           const unsigned char *d_need, long coarse_order, cudaStream_t st);
 int launch_load_density(const ShtPlan *p, const float *src, float *dst, float premul, float densmul, float backdens,
                         cudaStream_t st);
-extern int g_syn_rings_per_thread, g_ana_rings_per_thread, g_fft_threads_big, g_leg_warps_per_cta;
+extern int g_syn_rings_per_thread, g_ana_rings_per_thread, g_fft_threads_big, g_leg_warps_per_cta, g_fft_force_scratch;
 
 static long g_launches = 0;
 
@@ -73,6 +73,7 @@ long clb_launch_count(void) { return g_launches; }
 void clb_set_tuning(int what, int value)
 {
   if (what == 0 && value >= 1 && value <= 4) g_syn_rings_per_thread = value;
+  if (what == 4) g_fft_force_scratch = value ? 1 : 0;
   if (what == 3 && (value == 1 || value == 2 || value == 4)) g_leg_warps_per_cta = value;
   if (what == 2 && (value == 256 || value == 512 || value == 768 || value == 1024)) g_fft_threads_big = value;   // read at plan creation
   if (what == 1 && (value == 1 || value == 2 || value == 4 || value == 6 || value == 8 || value == 10 || value == 12)) g_ana_rings_per_thread = value;

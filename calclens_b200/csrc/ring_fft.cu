@@ -51,6 +51,9 @@ struct FftTables {
   signed char *d_rp_logM = nullptr;   // [nrp] work length per ring pair
   signed char *d_rp_blu = nullptr;    // [nrp] 1: Bluestein
   std::vector<FftClass> classes;
+  // rings whose work buffers exceed an SM's shared memory (r > 4095) run from a global scratch buffer
+  double2 *d_scratch = nullptr;
+  size_t scratch_bytes = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -291,31 +294,36 @@ __device__ __forceinline__ double2 dft_get(const double2 *a, int k, int logM, in
 // ---------------------------------------------------------------------------------------------------------------
 // plan-time: Bluestein chirp spectra
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void bluestein_table_kernel(const int *__restrict__ rlist, const long *__restrict__ chirp_off,
+__global__ void __launch_bounds__(512) bluestein_table_kernel(const int *__restrict__ rlist, int nr, const long *__restrict__ chirp_off,
                                        const long *__restrict__ bhat_off, double2 *__restrict__ chirp_all,
-                                       double2 *__restrict__ bhat_all, const double2 *__restrict__ tw, int logTW)
+                                       double2 *__restrict__ bhat_all, const double2 *__restrict__ tw, int logTW,
+                                       double2 *scratch, long stride)
 {
-  extern __shared__ double2 smem[];
-  const int r = rlist[blockIdx.x];
-  int logM = 0;
-  while ((1 << logM) < 2 * r - 1) ++logM;
-  const int M = 1 << logM;
-  double2 *chirp = chirp_all + chirp_off[r];
-  double2 *bhat = bhat_all + bhat_off[r];
-  for (int k = threadIdx.x; k < M; k += blockDim.x) smem[k] = make_double2(0.0, 0.0);   // (all of it: order irrelevant)
-  __syncthreads();
-  for (int j = threadIdx.x; j < r; j += blockDim.x) {
-    long j2 = ((long)j * j) % (2L * r);
-    double2 w = unit_pi(-j2, r);       // exp(-i pi j^2 / r)
-    chirp[j] = w;
-    double2 c = cconj(w);
-    smem[swz(j, logM)] = c;
-    if (j) smem[swz(M - j, logM)] = c;
+  extern __shared__ double2 smem_dyn[];
+  double2 *smem = scratch ? scratch + (long)blockIdx.x * stride : smem_dyn;   // large rings: global scratch
+  for (int item = blockIdx.x; item < nr; item += gridDim.x) {
+    const int r = rlist[item];
+    int logM = 0;
+    while ((1 << logM) < 2 * r - 1) ++logM;
+    const int M = 1 << logM;
+    double2 *chirp = chirp_all + chirp_off[r];
+    double2 *bhat = bhat_all + bhat_off[r];
+    for (int k = threadIdx.x; k < M; k += blockDim.x) smem[k] = make_double2(0.0, 0.0);   // (all of it: order irrelevant)
+    __syncthreads();
+    for (int j = threadIdx.x; j < r; j += blockDim.x) {
+      long j2 = ((long)j * j) % (2L * r);
+      double2 w = unit_pi(-j2, r);       // exp(-i pi j^2 / r)
+      chirp[j] = w;
+      double2 c = cconj(w);
+      smem[swz(j, logM)] = c;
+      if (j) smem[swz(M - j, logM)] = c;
+    }
+    __syncthreads();
+    cta_fft_dif(smem, logM, tw, logTW);
+    const double inv = 1.0 / (double)M;   // fold the inverse-FFT normalisation into the table (exact power of two)
+    for (int k = threadIdx.x; k < M; k += blockDim.x) bhat[k] = make_double2(smem[swz(k, logM)].x * inv, smem[swz(k, logM)].y * inv);
+    __syncthreads();
   }
-  __syncthreads();
-  cta_fft_dif(smem, logM, tw, logTW);
-  const double inv = 1.0 / (double)M;   // fold the inverse-FFT normalisation into the table (exact power of two)
-  for (int k = threadIdx.x; k < M; k += blockDim.x) bhat[k] = make_double2(smem[swz(k, logM)].x * inv, smem[swz(k, logM)].y * inv);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -352,18 +360,28 @@ struct RingGeomDev {
   const long *startN, *startS;
 };
 
-__global__ void __launch_bounds__(512) ring_analysis_kernel(const float *__restrict__ map, double2 *__restrict__ g_send, RingGeomDev geo,
-                                     const int *__restrict__ class_rp, const int *__restrict__ rp_to_local,
-                                     const long *__restrict__ m_goff, int lmax, const signed char *__restrict__ rp_logM,
-                                     const signed char *__restrict__ rp_blu, int Mmax,
-                                     const long *__restrict__ chirp_off, const long *__restrict__ bhat_off,
-                                     const double2 *__restrict__ chirp_all, const double2 *__restrict__ bhat_all,
-                                     const double2 *__restrict__ tw, int logTW, const double2 *__restrict__ phase_all,
-                                     const long *__restrict__ phase_off, double2 *const *__restrict__ m_gptr)
+struct AnaArgs {
+  const float *map; double2 *g_send; RingGeomDev geo;
+  const int *class_rp, *rp_to_local; const long *m_goff; int lmax;
+  const signed char *rp_logM, *rp_blu; int Mmax;
+  const long *chirp_off, *bhat_off; const double2 *chirp_all, *bhat_all, *tw; int logTW;
+  const double2 *phase_all; const long *phase_off; double2 *const *m_gptr;
+};
+
+// work = 2 * (index into the class's ring-pair list) + hemisphere; smem = the CTA's work buffers (shared memory, or a
+// private slice of a global scratch buffer for rings whose buffers exceed an SM's shared memory)
+__device__ __forceinline__ void ring_analysis_body(const AnaArgs &A, double2 *smem, int work)
 {
-  extern __shared__ double2 smem[];
-  const int rp = class_rp[blockIdx.x >> 1];
-  const int hemi = blockIdx.x & 1;
+  const float *__restrict__ map = A.map; double2 *__restrict__ g_send = A.g_send; const RingGeomDev &geo = A.geo;
+  const int *__restrict__ class_rp = A.class_rp, *__restrict__ rp_to_local = A.rp_to_local;
+  const long *__restrict__ m_goff = A.m_goff; const int lmax = A.lmax;
+  const signed char *__restrict__ rp_logM = A.rp_logM, *__restrict__ rp_blu = A.rp_blu; const int Mmax = A.Mmax;
+  const long *__restrict__ chirp_off = A.chirp_off, *__restrict__ bhat_off = A.bhat_off;
+  const double2 *__restrict__ chirp_all = A.chirp_all, *__restrict__ bhat_all = A.bhat_all, *__restrict__ tw = A.tw;
+  const int logTW = A.logTW; const double2 *__restrict__ phase_all = A.phase_all;
+  const long *__restrict__ phase_off = A.phase_off; double2 *const *__restrict__ m_gptr = A.m_gptr;
+  const int rp = class_rp[work >> 1];
+  const int hemi = work & 1;
   const int n = geo.nphi[rp];
   const int r = n >> 2;
   const int logM = rp_logM[rp], bluestein = rp_blu[rp];
@@ -483,6 +501,21 @@ __global__ void __launch_bounds__(512) ring_analysis_kernel(const float *__restr
   }
 }
 
+__global__ void __launch_bounds__(512) ring_analysis_kernel(AnaArgs A)
+{
+  extern __shared__ double2 smem[];
+  ring_analysis_body(A, smem, blockIdx.x);
+}
+// persistent variant: work buffers in global scratch (L2 resident), a CTA walks several rings
+__global__ void __launch_bounds__(512) ring_analysis_scratch_kernel(AnaArgs A, double2 *scratch, long stride, int nwork)
+{
+  double2 *buf = scratch + (long)blockIdx.x * stride;
+  for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
+    ring_analysis_body(A, buf, work);
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // synthesis kernel: one CTA per (ring pair in class, hemisphere, field)
 // ---------------------------------------------------------------------------------------------------------------
@@ -559,19 +592,27 @@ struct MapPtrs { float *p[6]; };
 
 // Shared memory: bufA[M] | bufB[r+1] | tail.  tail = float2 park[r] (Bluestein) or float2 Y[2r+1] (power of two,
 // reused as park).  On the Bluestein path the bins Y overlay bufA[M/2..M), which is unused until the zero fill.
-__global__ void __launch_bounds__(512) ring_synthesis_kernel(const double2 *__restrict__ b_recv, MapPtrs maps, RingGeomDev geo,
-                                      const int *__restrict__ class_rp, const int *__restrict__ rp_to_local,
-                                      const long *__restrict__ m_boff, int nslot_loc, int lmax,
-                                      const signed char *__restrict__ rp_logM, const signed char *__restrict__ rp_blu,
-                                      int Mmax, int rmax, const long *__restrict__ chirp_off,
-                                      const long *__restrict__ bhat_off, const double2 *__restrict__ chirp_all,
-                                      const double2 *__restrict__ bhat_all, const double2 *__restrict__ tw, int logTW,
-                                      const double2 *__restrict__ phase_all, const long *__restrict__ phase_off)
+struct SynArgs {
+  const double2 *b_recv; MapPtrs maps; RingGeomDev geo;
+  const int *class_rp, *rp_to_local; const long *m_boff; int nslot_loc, lmax;
+  const signed char *rp_logM, *rp_blu; int Mmax, rmax;
+  const long *chirp_off, *bhat_off; const double2 *chirp_all, *bhat_all, *tw; int logTW;
+  const double2 *phase_all; const long *phase_off;
+};
+
+__device__ __forceinline__ void ring_synthesis_body(const SynArgs &A, double2 *smem, int work, int field)
 {
-  extern __shared__ double2 smem[];
-  const int field = blockIdx.y;
-  const int rp = class_rp[blockIdx.x >> 1];
-  const int hemi = blockIdx.x & 1;
+  const double2 *__restrict__ b_recv = A.b_recv; const MapPtrs &maps = A.maps; const RingGeomDev &geo = A.geo;
+  const int *__restrict__ class_rp = A.class_rp, *__restrict__ rp_to_local = A.rp_to_local;
+  const long *__restrict__ m_boff = A.m_boff; const int nslot_loc = A.nslot_loc, lmax = A.lmax;
+  const signed char *__restrict__ rp_logM = A.rp_logM, *__restrict__ rp_blu = A.rp_blu;
+  const int Mmax = A.Mmax, rmax = A.rmax;
+  const long *__restrict__ chirp_off = A.chirp_off, *__restrict__ bhat_off = A.bhat_off;
+  const double2 *__restrict__ chirp_all = A.chirp_all, *__restrict__ bhat_all = A.bhat_all, *__restrict__ tw = A.tw;
+  const int logTW = A.logTW; const double2 *__restrict__ phase_all = A.phase_all;
+  const long *__restrict__ phase_off = A.phase_off;
+  const int rp = class_rp[work >> 1];
+  const int hemi = work & 1;
   const long start = hemi ? geo.startS[rp] : geo.startN[rp];
   if (start < 0) return;
   const int n = geo.nphi[rp];
@@ -703,6 +744,20 @@ __global__ void __launch_bounds__(512) ring_synthesis_kernel(const double2 *__re
   }
 }
 
+__global__ void __launch_bounds__(512) ring_synthesis_kernel(SynArgs A)
+{
+  extern __shared__ double2 smem[];
+  ring_synthesis_body(A, smem, blockIdx.x, blockIdx.y);
+}
+__global__ void __launch_bounds__(512) ring_synthesis_scratch_kernel(SynArgs A, double2 *scratch, long stride, int nwork)
+{
+  double2 *buf = scratch + (long)blockIdx.x * stride;
+  for (int item = blockIdx.x; item < 6 * nwork; item += gridDim.x) {
+    ring_synthesis_body(A, buf, item / 6, item % 6);
+    __syncthreads();
+  }
+}
+
 // cot(theta) cross terms, one CTA per (local ring pair, hemisphere)    [alm2allmaps_transpose_mpi.c:1097-1147]
 __global__ void ring_cot_terms_kernel(MapPtrs maps, RingGeomDev geo, const int *__restrict__ rp_loc)
 {
@@ -729,6 +784,8 @@ __global__ void ring_cot_terms_kernel(MapPtrs maps, RingGeomDev geo, const int *
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
+constexpr size_t kMaxSmem = 227 * 1024;
+int g_fft_force_scratch = 0;    // clb_set_tuning(4, 1): run every ring FFT from global scratch (tests the large-ring path at small Nside)
 int g_fft_threads_big = 512;   // threads per CTA for work lengths >= 4096 (clb_set_tuning(2, .))
 
 template <typename T>
@@ -750,13 +807,33 @@ static RingGeomDev geom_of(const ShtPlan *p)
   return g;
 }
 
+static double2 *fft_scratch(FftTables *t, size_t bytes)
+{
+  if (bytes > t->scratch_bytes) {
+    if (t->d_scratch) cudaFree(t->d_scratch);
+    CLB_CUDA_CHECK(cudaMalloc(&t->d_scratch, bytes));
+    t->scratch_bytes = bytes;
+  }
+  return t->d_scratch;
+}
+static int scratch_ctas()
+{
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    CLB_CUDA_CHECK(cudaGetDevice(&dev));
+    CLB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return sms * 2;
+}
+
 void fft_tables_destroy(ShtPlan *p)
 {
   FftTables *t = p->fft;
   if (!t) return;
   for (auto &c : t->classes) cudaFree(c.d_rp);
   cudaFree(t->d_tw); cudaFree(t->d_chirp_off); cudaFree(t->d_bhat_off); cudaFree(t->d_chirp); cudaFree(t->d_bhat);
-  cudaFree(t->d_phase); cudaFree(t->d_phase_off); cudaFree(t->d_rp_logM); cudaFree(t->d_rp_blu);
+  cudaFree(t->d_phase); cudaFree(t->d_phase_off); cudaFree(t->d_rp_logM); cudaFree(t->d_rp_blu); cudaFree(t->d_scratch);
   delete t;
   p->fft = nullptr;
 }
@@ -837,13 +914,21 @@ void fft_tables_create(ShtPlan *p)
     CLB_CUDA_CHECK(cudaMalloc(&d_rlist, sizeof(int) * need_r.size()));
     CLB_CUDA_CHECK(cudaMemcpy(d_rlist, need_r.data(), sizeof(int) * need_r.size(), cudaMemcpyHostToDevice));
     size_t smem = sizeof(double2) << maxLogM;
-    static size_t attr_blu = 0;
-    if (smem > attr_blu) {
-      CLB_CUDA_CHECK(cudaFuncSetAttribute(bluestein_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_blu = smem;
+    if (smem <= kMaxSmem && !g_fft_force_scratch) {
+      static size_t attr_blu = 0;
+      if (smem > attr_blu) {
+        CLB_CUDA_CHECK(cudaFuncSetAttribute(bluestein_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_blu = smem;
+      }
+      bluestein_table_kernel<<<(unsigned)need_r.size(), 256, smem>>>(d_rlist, (int)need_r.size(), t->d_chirp_off, t->d_bhat_off,
+                                                                     t->d_chirp, t->d_bhat, t->d_tw, t->logTW, nullptr, 0);
+    } else {
+      const int ctas = std::min<int>((int)need_r.size(), scratch_ctas());
+      const long stride = 1L << maxLogM;
+      double2 *scr = fft_scratch(t, (size_t)ctas * stride * sizeof(double2));
+      bluestein_table_kernel<<<ctas, 512>>>(d_rlist, (int)need_r.size(), t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat,
+                                           t->d_tw, t->logTW, scr, stride);
     }
-    bluestein_table_kernel<<<(unsigned)need_r.size(), 256, smem>>>(d_rlist, t->d_chirp_off, t->d_bhat_off, t->d_chirp,
-                                                                   t->d_bhat, t->d_tw, t->logTW);
     CLB_CUDA_CHECK(cudaGetLastError());
     CLB_CUDA_CHECK(cudaDeviceSynchronize());
     cudaFree(d_rlist);
@@ -869,10 +954,11 @@ void fft_tables_create(ShtPlan *p)
     CLB_CUDA_CHECK(cudaMemcpy(c.d_rp, members[k].data(), sizeof(int) * c.count, cudaMemcpyHostToDevice));
     t->classes.push_back(c);
   }
-  if (max_ana > 227 * 1024 || max_syn > 227 * 1024) {
-    fprintf(stderr, "calclens_b200: ring FFT needs %zu bytes of shared memory (Nside=%ld); the single-CTA ring FFT "
-                    "supports Nside <= 4096\n", std::max(max_ana, max_syn), nside);
-    abort();
+  // classes that do not fit an SM's shared memory use the persistent global-scratch kernels instead
+  max_ana = max_syn = 0;
+  for (const auto &c : t->classes) {
+    if (c.smem_ana <= kMaxSmem) max_ana = std::max(max_ana, c.smem_ana);
+    if (c.smem_syn <= kMaxSmem) max_syn = std::max(max_syn, c.smem_syn);
   }
   // the attribute is per function, not per plan: several plans may be alive (one per emulated rank, or one per
   // resolution), so it is only ever raised
@@ -892,13 +978,20 @@ int *plan_rp_to_local(const ShtPlan *p);
 
 int launch_ring_analysis(const ShtPlan *p, const float *d_map, double2 *d_g_send, cudaStream_t st)
 {
-  const FftTables *t = p->fft;
+  FftTables *t = p->fft;
   int launches = 0;
   for (const auto &c : t->classes) {
-    ring_analysis_kernel<<<2 * c.count, c.threads, c.smem_ana, st>>>(
-        d_map, d_g_send, geom_of(p), c.d_rp, plan_rp_to_local(p), p->d_m_goff, (int)p->lmax, t->d_rp_logM, t->d_rp_blu,
-        1 << c.logM, t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat, t->d_tw, t->logTW, t->d_phase, t->d_phase_off,
-        p->d_m_gptr);
+    AnaArgs A{d_map, d_g_send, geom_of(p), c.d_rp, plan_rp_to_local(p), p->d_m_goff, (int)p->lmax, t->d_rp_logM, t->d_rp_blu,
+              1 << c.logM, t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat, t->d_tw, t->logTW, t->d_phase, t->d_phase_off,
+              p->d_m_gptr};
+    if (c.smem_ana <= kMaxSmem && !g_fft_force_scratch) {
+      ring_analysis_kernel<<<2 * c.count, c.threads, c.smem_ana, st>>>(A);
+    } else {
+      const int nwork = 2 * c.count, ctas = std::min(nwork, scratch_ctas());
+      const long stride = (long)((c.smem_ana + 255) / 256) * 16;   // double2 elements, 256-byte aligned slices
+      double2 *scr = fft_scratch(t, (size_t)ctas * stride * sizeof(double2));
+      ring_analysis_scratch_kernel<<<ctas, 512, 0, st>>>(A, scr, stride, nwork);
+    }
     ++launches;
   }
   CLB_CUDA_CHECK(cudaGetLastError());
@@ -907,16 +1000,23 @@ int launch_ring_analysis(const ShtPlan *p, const float *d_map, double2 *d_g_send
 
 int launch_ring_synthesis(const ShtPlan *p, const double2 *d_b_recv, float *const d_maps[6], cudaStream_t st)
 {
-  const FftTables *t = p->fft;
+  FftTables *t = p->fft;
   MapPtrs mp;
   for (int k = 0; k < 6; ++k) mp.p[k] = d_maps[k];
   int launches = 0;
   for (const auto &c : t->classes) {
-    dim3 grid(2 * c.count, 6);
-    ring_synthesis_kernel<<<grid, c.threads, c.smem_syn, st>>>(
-        d_b_recv, mp, geom_of(p), c.d_rp, plan_rp_to_local(p), p->d_m_boff, 2 * p->nrp_loc, (int)p->lmax, t->d_rp_logM,
-        t->d_rp_blu, 1 << c.logM, c.rmax, t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat, t->d_tw, t->logTW,
-        t->d_phase, t->d_phase_off);
+    SynArgs A{d_b_recv, mp, geom_of(p), c.d_rp, plan_rp_to_local(p), p->d_m_boff, 2 * p->nrp_loc, (int)p->lmax, t->d_rp_logM,
+              t->d_rp_blu, 1 << c.logM, c.rmax, t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat, t->d_tw, t->logTW,
+              t->d_phase, t->d_phase_off};
+    if (c.smem_syn <= kMaxSmem && !g_fft_force_scratch) {
+      dim3 grid(2 * c.count, 6);
+      ring_synthesis_kernel<<<grid, c.threads, c.smem_syn, st>>>(A);
+    } else {
+      const int nwork = 2 * c.count, ctas = std::min(6 * nwork, scratch_ctas());
+      const long stride = (long)((c.smem_syn + 255) / 256) * 16;
+      double2 *scr = fft_scratch(t, (size_t)ctas * stride * sizeof(double2));
+      ring_synthesis_scratch_kernel<<<ctas, 512, 0, st>>>(A, scr, stride, nwork);
+    }
     ++launches;
   }
   ring_cot_terms_kernel<<<2 * p->nrp_loc, 256, 0, st>>>(mp, geom_of(p), p->d_rp_loc);

@@ -513,3 +513,30 @@ def test_solver_step_prefetch_and_fused_summary(clb):
         a.lib.clb_ray_summary_dev(a.rays.data_ptr(), a.nrays, ref.data_ptr(), None)
         assert np.allclose(sa, ref.cpu().numpy(), rtol=1e-9, atol=1e-13)
     assert np.array_equal(a.rays_host().view(np.uint8), b.rays_host().view(np.uint8))
+
+
+def test_global_scratch_ring_fft_matches_shared_memory_path(clb):
+    """Rings whose FFT work buffers exceed an SM's shared memory (r > 4095, i.e. Nside 8192) run from a global scratch
+    buffer with persistent CTAs.  Forced on at a small Nside, that path must reproduce the shared-memory path bit for
+    bit (same arithmetic, different memory)."""
+    import torch
+    from calclens_b200 import _lib
+    L = _lib.load()
+    order, lmax = 6, 150
+    npix = 12 << (2 * order)
+    rng = np.random.default_rng(99)
+    dm = torch.from_numpy(rng.normal(size=npix).astype(np.float32)).cuda()
+    out = []
+    try:
+        for force in (0, 1):
+            L.clb_set_tuning(4, force)
+            plan = clb.HEALPixSHTPlan(order, lmax)
+            g = plan.ring_analysis(dm)
+            are, aim = plan.legendre_analysis(g, poisson_filter=True)
+            b = plan.legendre_synthesis(are, aim)
+            maps = plan.ring_synthesis(b)
+            out.append((g.clone(), maps.clone()))
+            plan.destroy()
+    finally:
+        L.clb_set_tuning(4, 0)
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])

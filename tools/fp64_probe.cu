@@ -22,7 +22,7 @@ __global__ void dfma_k(double *out, int iters, double a, double b)
 
 // synthesis-like: R rings, per degree 2 LDS.128 (broadcast) + R*(6 acc FMA + DMUL + DFMA)
 template <int R>
-__global__ void __launch_bounds__(128, (R >= 4) ? 3 : 4) syn_k(double *out, int iters, double a)
+__global__ void __launch_bounds__(128, (R >= 5) ? 2 : (R >= 4) ? 3 : 4) syn_k(double *out, int iters, double a)
 {
   __shared__ __align__(16) double tiles[2][16 * 8];
   tiles[0][threadIdx.x] = 1e-3 * (threadIdx.x % 7) + a;
@@ -258,6 +258,15 @@ int main()
       printf(" %6.2f", 16.0 * 4 * 16 * it2 * sms * warps * 32 / ms * 1e-9);
     }
     printf("\n");
+  }
+  {
+    float ms;
+    ms = timeit([&] { syn_k<5><<<sms * 2, 128>>>(out, it2, 1e-9); });
+    printf("synthesis-like R=5, 8 warps/SM: %6.2f\n", 16.0 * 5 * 16 * it2 * sms * 2 * 128 / ms * 1e-9);
+    ms = timeit([&] { syn_k<6><<<sms * 2, 128>>>(out, it2, 1e-9); });
+    printf("synthesis-like R=6, 8 warps/SM: %6.2f\n", 16.0 * 6 * 16 * it2 * sms * 2 * 128 / ms * 1e-9);
+    ms = timeit([&] { syn_k<4><<<sms * 2, 128>>>(out, it2, 1e-9); });
+    printf("synthesis-like R=4, 8 warps/SM: %6.2f\n", 16.0 * 4 * 16 * it2 * sms * 2 * 128 / ms * 1e-9);
   }
   printf("analysis-like loop at 12 warps/SM (8 flop per ring-degree): TFLOP/s, modes none / shuffle reduce / smem reduce\n");
   {

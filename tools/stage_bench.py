@@ -13,6 +13,7 @@ for a in sys.argv[3:]:
     elif a.startswith("ana="): ana = [int(x) for x in a[4:].split(",")]
     elif a.startswith("warps="): _lib.load().clb_set_tuning(3, int(a[6:]))
     elif a.startswith("fft="): _lib.load().clb_set_tuning(2, int(a[4:]))
+    elif a.startswith("scratch="): _lib.load().clb_set_tuning(4, int(a[8:]))
     else: reps = int(a)
 L = _lib.load()
 plan = clb.HEALPixSHTPlan(order, lmax)
