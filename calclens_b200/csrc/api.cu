@@ -20,7 +20,7 @@ int launch_ray_init(Ray *d_rays, long nrays, long first_nest, long ray_order, do
 int launch_ray_summary(const Ray *d_rays, long nrays, double *d_out6, cudaStream_t st);
 void launch_healpix_index(int what, long order, long n, const long *in, const double *th, const double *ph, long *out, cudaStream_t st);
 void launch_healpix_interpol(long order, long n, const double *vec, long *pix, double *wgt, cudaStream_t st);
-void sht_plan_set_peers(ShtPlan *p, void *const *g_recv_ptrs, void *const *b_recv_ptrs);
+void sht_plan_set_peers(ShtPlan *p, void *const *g_send_ptrs, void *const *b_recv_ptrs);
 int launch_maps_broadcast(const ShtPlan *p, float *const local_maps[6], float *const *peer_maps,
                           const unsigned char *d_need, long coarse_order, cudaStream_t st);
 int launch_load_density(const ShtPlan *p, const float *src, float *dst, float premul, float densmul, float backdens,
@@ -163,9 +163,9 @@ void *clb_peer_import(const void *handle64)
   return p;
 }
 void clb_peer_release(void *p) { if (p) CLB_CUDA_CHECK(cudaIpcCloseMemHandle(p)); }
-void clb_sht_plan_set_peers(clb_sht_plan *plan, void *const *g_recv_ptrs, void *const *b_recv_ptrs)
+void clb_sht_plan_set_peers(clb_sht_plan *plan, void *const *g_send_ptrs, void *const *b_recv_ptrs)
 {
-  sht_plan_set_peers(P(plan), g_recv_ptrs, b_recv_ptrs);
+  sht_plan_set_peers(P(plan), g_send_ptrs, b_recv_ptrs);
 }
 int clb_maps_broadcast_dev(const clb_sht_plan *plan, float *const local_maps[6], float *const *peer_maps,
                            const unsigned char *need, long coarse_order, void *stream)

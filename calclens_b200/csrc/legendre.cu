@@ -53,8 +53,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // warps of an m in a fixed order (deterministic).
 template <int R, int KB, int NB>
 __global__ void __launch_bounds__(kLegThreads, NB)
-legendre_analysis_kernel(const double2 *__restrict__ g_recv, const long *__restrict__ g_off,
-                         const int *__restrict__ g_stride, const double *__restrict__ Atab,
+legendre_analysis_kernel(const double2 *__restrict__ g_recv, const double2 *const *__restrict__ rp_gsrc,
+                         const long *__restrict__ g_off, const int *__restrict__ g_stride, const double *__restrict__ Atab,
                          const long *__restrict__ row_off, const int *__restrict__ ls_tab,
                          const double2 *__restrict__ seed_tab, const double *__restrict__ cth_rp,
                          const int *__restrict__ m_loc, const long *__restrict__ alm_off, double2 *__restrict__ part,
@@ -83,7 +83,8 @@ legendre_analysis_kernel(const double2 *__restrict__ g_recv, const long *__restr
     int ls = kNoStart;
     if (rp < nrp) ls = ls_tab[(size_t)mi * nrp + rp];
     if (ls != kNoStart) {
-      const double2 *g = g_recv + g_off[rp] + (long)mi * g_stride[rp];
+      // source: this rank's receive buffer, or (fused exchange) the ring owner's send buffer over NVLink
+      const double2 *g = (rp_gsrc ? rp_gsrc[rp] : g_recv + g_off[rp]) + (long)mi * g_stride[rp];
       const double2 gn = g[0], gs = g[1];
       gpx[j] = gn.x + gs.x; gpy[j] = gn.y + gs.y;     // G+ = gN + gS multiplies even l+m
       gmx[j] = gn.x - gs.x; gmy[j] = gn.y - gs.y;     // G- = gN - gS multiplies odd l+m
@@ -362,7 +363,7 @@ static void launch_ana_t(const ShtPlan *p, const double2 *g_recv, int nchunk, cu
   const int warps = g_leg_warps_per_cta;
   dim3 grid((nchunk + warps - 1) / warps, p->nm_loc);
   legendre_analysis_kernel<R, KB, NB><<<grid, 32 * warps, 0, st>>>(
-      g_recv, p->d_g_off, p->d_g_stride, p->d_A, p->d_row_off, p->d_ls_ana, p->d_seed, p->d_cth, p->d_m_loc,
+      g_recv, p->d_rp_gsrc, p->d_g_off, p->d_g_stride, p->d_A, p->d_row_off, p->d_ls_ana, p->d_seed, p->d_cth, p->d_m_loc,
       p->d_alm_off, reinterpret_cast<double2 *>(p->d_part), p->alm_total, p->nrp, (int)p->lmax);
 }
 

@@ -365,7 +365,7 @@ struct AnaArgs {
   const int *class_rp, *rp_to_local; const long *m_goff; int lmax;
   const signed char *rp_logM, *rp_blu; int Mmax;
   const long *chirp_off, *bhat_off; const double2 *chirp_all, *bhat_all, *tw; int logTW;
-  const double2 *phase_all; const long *phase_off; double2 *const *m_gptr;
+  const double2 *phase_all; const long *phase_off;
 };
 
 // work = 2 * (index into the class's ring-pair list) + hemisphere; smem = the CTA's work buffers (shared memory, or a
@@ -379,7 +379,7 @@ __device__ __forceinline__ void ring_analysis_body(const AnaArgs &A, double2 *sm
   const long *__restrict__ chirp_off = A.chirp_off, *__restrict__ bhat_off = A.bhat_off;
   const double2 *__restrict__ chirp_all = A.chirp_all, *__restrict__ bhat_all = A.bhat_all, *__restrict__ tw = A.tw;
   const int logTW = A.logTW; const double2 *__restrict__ phase_all = A.phase_all;
-  const long *__restrict__ phase_off = A.phase_off; double2 *const *__restrict__ m_gptr = A.m_gptr;
+  const long *__restrict__ phase_off = A.phase_off;
   const int rp = class_rp[work >> 1];
   const int hemi = work & 1;
   const int n = geo.nphi[rp];
@@ -390,8 +390,7 @@ __device__ __forceinline__ void ring_analysis_body(const AnaArgs &A, double2 *sm
   const long start = hemi ? geo.startS[rp] : geo.startN[rp];
   const int slot = 2 * rp_to_local[rp] + hemi;
   if (start < 0) {   // equator has no southern partner: its slot carries zeros
-    for (int m = threadIdx.x; m <= lmax; m += blockDim.x)
-      (m_gptr ? m_gptr[m] : g_send + m_goff[m])[slot] = make_double2(0.0, 0.0);
+    for (int m = threadIdx.x; m <= lmax; m += blockDim.x) g_send[m_goff[m] + slot] = make_double2(0.0, 0.0);
     return;
   }
   double2 *bufA = smem;          // [M]
@@ -496,8 +495,7 @@ __device__ __forceinline__ void ring_analysis_body(const AnaArgs &A, double2 *sm
       double t1 = __dadd_rn(__dmul_rn(gr, p1), __dmul_rn(gi, p0));
       gr = t0; gi = t1;
     }
-    // destination: this rank's send buffer, or (fused exchange) the m owner's receive buffer over NVLink
-    (m_gptr ? m_gptr[m] : g_send + m_goff[m])[slot] = make_double2(gr, gi);
+    g_send[m_goff[m] + slot] = make_double2(gr, gi);
   }
 }
 
@@ -982,8 +980,7 @@ int launch_ring_analysis(const ShtPlan *p, const float *d_map, double2 *d_g_send
   int launches = 0;
   for (const auto &c : t->classes) {
     AnaArgs A{d_map, d_g_send, geom_of(p), c.d_rp, plan_rp_to_local(p), p->d_m_goff, (int)p->lmax, t->d_rp_logM, t->d_rp_blu,
-              1 << c.logM, t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat, t->d_tw, t->logTW, t->d_phase, t->d_phase_off,
-              p->d_m_gptr};
+              1 << c.logM, t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat, t->d_tw, t->logTW, t->d_phase, t->d_phase_off};
     if (c.smem_ana <= kMaxSmem && !g_fft_force_scratch) {
       ring_analysis_kernel<<<2 * c.count, c.threads, c.smem_ana, st>>>(A);
     } else {

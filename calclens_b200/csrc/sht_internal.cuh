@@ -72,8 +72,8 @@ struct ShtPlan {
   long *d_alm_off = nullptr;
   // fused exchange over peer memory (clb_sht_plan_set_peers): destination of every m's g block / every ring pair's b
   // block inside the owning rank's receive buffer (NVLink peer pointers, or local ones for this rank's own share)
-  double2 **d_m_gptr = nullptr;    // [lmax+1]
-  double2 **d_rp_bptr = nullptr;   // [nrp]
+  const double2 **d_rp_gsrc = nullptr;   // [nrp] analysis PULLS g: where ring pair rp's block lives in its owner's send buffer
+  double2 **d_rp_bptr = nullptr;         // [nrp] synthesis PUSHES b: ring pair rp's block in its owner's receive buffer
   // FFT tables
   struct FftTables *fft = nullptr;
 };

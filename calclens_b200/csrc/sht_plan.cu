@@ -268,42 +268,39 @@ void sht_plan_destroy(ShtPlan *p)
   void *ptrs[] = {p->d_cth, p->d_sth, p->d_logsth, p->d_weight, p->d_nphi, p->d_shifted, p->d_startN, p->d_startS,
                   p->d_rp_loc, p->d_m_loc, p->d_m_goff, p->d_m_boff, p->d_g_off, p->d_b_off, p->d_g_stride,
                   p->d_b_stride, p->d_rp_to_local, p->d_row_off, p->d_alm_off, p->d_A, p->d_c, p->d_coef,
-                  p->d_ls_ana, p->d_ls_syn, p->d_seed, p->d_part, p->d_m_gptr, p->d_rp_bptr};
+                  p->d_ls_ana, p->d_ls_syn, p->d_seed, p->d_part, (void *)p->d_rp_gsrc, p->d_rp_bptr};
   for (void *q : ptrs) if (q) cudaFree(q);
   delete p;
 }
 
 int *plan_rp_to_local(const ShtPlan *p) { return p->d_rp_to_local; }
 
-// Fused exchange: instead of filling a local send buffer that an all-to-all then moves, the producing kernels store
-// straight into the consumer's receive buffer.  g_recv_ptrs[q] / b_recv_ptrs[q] are the base addresses of rank q's
-// receive buffers as seen from this process (peer mappings; this rank's own buffers for q == rank).  The block this
-// rank fills inside rank q's buffer starts where q's all-to-all receive displacement for this rank would be.
-void sht_plan_set_peers(ShtPlan *p, void *const *g_recv_ptrs, void *const *b_recv_ptrs)
+// Fused exchange over peer memory.  g (analysis): every rank's ring FFT fills its own send buffer with coalesced
+// local stores, and the Legendre stage of the m owner READS the (north, south) pairs of 32 adjacent ring pairs -- 1 KB
+// contiguous per warp -- straight out of the ring owner's buffer over NVLink.  b (synthesis): the Legendre epilogue
+// WRITES its 128-byte runs straight into the ring owner's receive buffer.  g_send_ptrs[q] / b_recv_ptrs[q] are the
+// base addresses of rank q's buffers as seen from this process (peer mappings; this rank's own buffers for q == rank).
+void sht_plan_set_peers(ShtPlan *p, void *const *g_send_ptrs, void *const *b_recv_ptrs)
 {
   const int nrp = p->nrp, me = p->rank;
-  const long lmax = p->lmax;
-  std::vector<int> rp_local_idx(nrp), m_local_idx(lmax + 1), cnt_rp(p->nranks, 0), cnt_m(p->nranks, 0);
+  std::vector<int> rp_local_idx(nrp), cnt_rp(p->nranks, 0);
   for (int rp = 0; rp < nrp; ++rp) rp_local_idx[rp] = cnt_rp[p->rp_owner[rp]]++;
-  for (long m = 0; m <= lmax; ++m) m_local_idx[m] = cnt_m[p->m_owner[m]]++;
-  const long nslot_mine = 2L * p->nrp_loc;
-  std::vector<double2 *> gptr(lmax + 1), bptr(nrp);
-  for (long m = 0; m <= lmax; ++m) {
-    const int q = p->m_owner[m];
-    long rbase = 0;   // q receives nm_of_rank[q] * 2 * nrp_of_rank[r] elements from every rank r < me first
-    for (int r = 0; r < me; ++r) rbase += (long)p->nm_of_rank[q] * 2L * p->nrp_of_rank[r];
-    gptr[m] = reinterpret_cast<double2 *>(g_recv_ptrs[q]) + rbase + (long)m_local_idx[m] * nslot_mine;
-  }
+  std::vector<const double2 *> gsrc(nrp);
+  std::vector<double2 *> bptr(nrp);
   for (int rp = 0; rp < nrp; ++rp) {
     const int q = p->rp_owner[rp];
     const long nslot_q = 2L * p->nrp_of_rank[q];
-    long rbase = 0;   // q receives nm_of_rank[r] * 6 * nslot_q elements from every rank r < me first
-    for (int r = 0; r < me; ++r) rbase += (long)p->nm_of_rank[r] * 6L * nslot_q;
+    long sbase = 0, rbase = 0;
+    for (int r = 0; r < me; ++r) {
+      sbase += (long)p->nm_of_rank[r] * nslot_q;        // q's send block for rank r: nm_of_rank[r] * nslot_q elements
+      rbase += (long)p->nm_of_rank[r] * 6L * nslot_q;   // q's receive block from rank r
+    }
+    gsrc[rp] = reinterpret_cast<const double2 *>(g_send_ptrs[q]) + sbase + 2L * rp_local_idx[rp];
     bptr[rp] = reinterpret_cast<double2 *>(b_recv_ptrs[q]) + rbase + 2L * rp_local_idx[rp];
   }
-  if (p->d_m_gptr) cudaFree(p->d_m_gptr);
+  if (p->d_rp_gsrc) cudaFree(p->d_rp_gsrc);
   if (p->d_rp_bptr) cudaFree(p->d_rp_bptr);
-  p->d_m_gptr = to_device(gptr);
+  p->d_rp_gsrc = to_device(gsrc);
   p->d_rp_bptr = to_device(bptr);
 }
 

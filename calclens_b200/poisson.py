@@ -149,7 +149,7 @@ class LensPlaneSolver:
         and hand the peer pointers to the plan (clb_sht_plan_set_peers).  Falls back to the NCCL exchange, on all
         ranks together, if any mapping fails."""
         p, L = self.plan, self.lib
-        sizes = [16 * max(p.g_recv_total, 1), 16 * max(p.b_recv_total, 1), 4 * 6 * self.npix]
+        sizes = [16 * max(p.g_send_total, 1), 16 * max(p.b_recv_total, 1), 4 * 6 * self.npix]   # g send, b receive, maps
         own = [L.clb_peer_alloc(n) for n in sizes]
         handles = []
         for ptr in own:
@@ -178,11 +178,12 @@ class LensPlaneSolver:
         b_arr = (C.c_void_p * self.nranks)(*[peers[q][1] for q in range(self.nranks)])
         L.clb_sht_plan_set_peers(p._h, g_arr, b_arr)
         self._peer_maps = (C.c_void_p * (6 * self.nranks))(*[peers[q][2] + 4 * self.npix * k for q in range(self.nranks) for k in range(6)])
-        self.g_recv = self._dev_view(own[0], (2 * max(p.g_recv_total, 1),), torch.float64)
+        self.g_send = self._dev_view(own[0], (2 * max(p.g_send_total, 1),), torch.float64)
+        self.g_recv = None         # analysis reads g from the ring owners' send buffers
         self.b_recv = self._dev_view(own[1], (2 * max(p.b_recv_total, 1),), torch.float64)
         self.maps = self._dev_view(own[2], (6, self.npix), torch.float32)
         self.maps.zero_()
-        self.g_send = self.b_send = None   # producers store into the owners' receive buffers
+        self.b_send = None         # synthesis stores b into the ring owners' receive buffers
         self._tiny = torch.zeros(1, dtype=torch.float32, device=self.device)
         # halo-limited map broadcast: a pixel goes to the ranks whose ray domain, grown by halo_deg, can reach it.
         # Cells of a coarse NEST grid stand in for the reference's halo bundle cells (raytrace_utils.c:116-161); the
@@ -243,9 +244,10 @@ class LensPlaneSolver:
         if self.fused:
             # producers store into the consumers' buffers over NVLink; barriers order producer and consumer stages
             self._stream_barrier()   # every rank is done with the previous plane's g, b and maps
-            self.lib.clb_ring_analysis_dev(p._h, dens.data_ptr(), None, self._stream()); mark("fft_analysis")
+            p.ring_analysis(dens, self.g_send); mark("fft_analysis")
             self._stream_barrier(); mark("a2a_g")
-            p.legendre_analysis(self.g_recv, self.alm_re, self.alm_im, poisson_filter=True); mark("legendre_analysis")
+            self.lib.clb_legendre_analysis_dev(p._h, None, self.alm_re.data_ptr(), self.alm_im.data_ptr(), 1, self._stream())
+            mark("legendre_analysis")
             self.lib.clb_legendre_synthesis_dev(p._h, self.alm_re.data_ptr(), self.alm_im.data_ptr(), None, self._stream())
             mark("legendre_synthesis")
             self._stream_barrier(); mark("a2a_b")

@@ -68,11 +68,13 @@ int clb_ring_synthesis_dev(const clb_sht_plan *plan, const double *b_recv, float
  *   clb_peer_alloc/export/import : device buffers other ranks may map (CUDA IPC; the 64-byte handle travels through
  *                                  whatever the host uses for bootstrap -- MPI_Allgather in CALCLENS, the
  *                                  torch.distributed store here); import returns NULL when peer access is unavailable
- *   clb_sht_plan_set_peers       : g_recv_ptrs[q] / b_recv_ptrs[q] = rank q's receive buffers (sizes
- *                                  clb_sht_plan_query(6) / (8) complex doubles on rank q) as mapped into this process.
- *                                  Afterwards clb_ring_analysis_dev ignores g_send and clb_legendre_synthesis_dev
- *                                  ignores b_send: results land in the owners' receive buffers.  The host orders
- *                                  producer and consumer stages with a stream barrier across ranks.
+ *   clb_sht_plan_set_peers       : g_send_ptrs[q] = rank q's g SEND buffer (clb_sht_plan_query(5) complex doubles on
+ *                                  rank q), b_recv_ptrs[q] = rank q's b RECEIVE buffer (clb_sht_plan_query(8)), as
+ *                                  mapped into this process.  Afterwards clb_legendre_analysis_dev ignores g_recv and
+ *                                  reads g straight out of the ring owners' send buffers (1 KB coalesced NVLink reads),
+ *                                  and clb_legendre_synthesis_dev ignores b_send and stores b into the ring owners'
+ *                                  receive buffers.  The host orders producer and consumer stages with a stream
+ *                                  barrier across ranks.
  *   clb_maps_broadcast_dev       : store this rank's rings of the six maps into the peers' maps
  *                                  (peer_maps[q*6+k] = map k of rank q, up to 8 ranks);
  *                                  need (device, may be NULL = every pixel to every rank) and coarse_order come from
@@ -84,7 +86,7 @@ void clb_peer_free(void *p);
 void clb_peer_export(void *p, void *handle64);
 void *clb_peer_import(const void *handle64);
 void clb_peer_release(void *p);
-void clb_sht_plan_set_peers(clb_sht_plan *plan, void *const *g_recv_ptrs, void *const *b_recv_ptrs);
+void clb_sht_plan_set_peers(clb_sht_plan *plan, void *const *g_send_ptrs, void *const *b_recv_ptrs);
 int clb_maps_broadcast_dev(const clb_sht_plan *plan, float *const local_maps[6], float *const *peer_maps,
                            const unsigned char *need, long coarse_order, void *stream);
 void clb_domain_masks(long ray_order, int nranks, long coarse_order, double margin_rad, unsigned char *mask);

@@ -436,17 +436,21 @@ def test_fused_exchange_emulated_on_one_gpu(clb, nranks):
     s_re, s_im = single.legendre_analysis(single.ring_analysis(dm), poisson_filter=True)
     s_maps = single.ring_synthesis(single.legendre_synthesis(s_re, s_im)).cpu().numpy()
     plans = [clb.HEALPixSHTPlan(order, lmax, nranks=nranks, rank=r) for r in range(nranks)]
-    g_recv = [torch.full((2 * max(p.g_recv_total, 1),), float("nan"), dtype=torch.float64, device="cuda") for p in plans]
+    g_send = [torch.full((2 * max(p.g_send_total, 1),), float("nan"), dtype=torch.float64, device="cuda") for p in plans]
     b_recv = [torch.full((2 * max(p.b_recv_total, 1),), float("nan"), dtype=torch.float64, device="cuda") for p in plans]
     maps = [torch.zeros((6, npix), dtype=torch.float32, device="cuda") for _ in plans]
-    g_arr = (C.c_void_p * nranks)(*[t.data_ptr() for t in g_recv])
+    g_arr = (C.c_void_p * nranks)(*[t.data_ptr() for t in g_send])
     b_arr = (C.c_void_p * nranks)(*[t.data_ptr() for t in b_recv])
     peer_maps = (C.c_void_p * (6 * nranks))(*[maps[q][k].data_ptr() for q in range(nranks) for k in range(6)])
     for p in plans:
         L.clb_sht_plan_set_peers(p._h, g_arr, b_arr)
-    for p in plans:                                   # producers of g: every rank's ring FFT
-        L.clb_ring_analysis_dev(p._h, dm.data_ptr(), None, None)
-    alms = [p.legendre_analysis(g, poisson_filter=True) for p, g in zip(plans, g_recv)]
+    for p, g in zip(plans, g_send):                   # every rank's ring FFT fills its own send buffer ...
+        p.ring_analysis(dm, g)
+    alms = []
+    for p in plans:                                   # ... and every rank's Legendre analysis pulls from the owners' buffers
+        are = torch.empty(max(p.Nlm, 1), dtype=torch.float64, device="cuda"); aim = torch.empty_like(are)
+        L.clb_legendre_analysis_dev(p._h, None, are.data_ptr(), aim.data_ptr(), 1, None)
+        alms.append((are, aim))
     for p, (are, aim) in zip(plans, alms):            # producers of b: every rank's Legendre synthesis
         L.clb_legendre_synthesis_dev(p._h, are.data_ptr(), aim.data_ptr(), None, None)
     for r, p in enumerate(plans):
@@ -456,7 +460,7 @@ def test_fused_exchange_emulated_on_one_gpu(clb, nranks):
         L.clb_maps_broadcast_dev(p._h, ptrs, peer_maps, None, 0, None)
     torch.cuda.synchronize()
     for r in range(nranks):
-        assert not torch.isnan(g_recv[r][:2 * plans[r].g_recv_total]).any() and not torch.isnan(b_recv[r][:2 * plans[r].b_recv_total]).any()
+        assert not torch.isnan(g_send[r][:2 * plans[r].g_send_total]).any() and not torch.isnan(b_recv[r][:2 * plans[r].b_recv_total]).any()
         assert np.array_equal(maps[r].cpu().numpy(), s_maps), "rank %d maps differ from the single-rank maps" % r
     for p in plans + [single]:
         p.destroy()
