@@ -52,6 +52,8 @@ def load():
         "clb_ray_step_dev": (C.c_int, [vp, C.c_long, vp, C.c_long, C.c_double, C.c_double, C.c_double, C.c_int, vp]),
         "clb_ray_init_dev": (C.c_int, [vp, C.c_long, C.c_long, C.c_long, C.c_double, vp]),
         "clb_ray_summary_dev": (C.c_int, [vp, C.c_long, vp, vp]),
+        "clb_ray_output_dev": (C.c_int, [vp, vp, C.c_long, C.c_long, vp]),
+        "clb_deposit_ngp_dev": (C.c_int, [vp, vp, C.c_long, C.c_long, vp, vp]),
         "clb_map2alm": (None, [vp, vp, vp, vp, C.c_int]),
         "clb_alm2allmaps": (None, [vp, vp, vp, vp]),
         "clb_map2alm_mapvec": (None, [vp, vp, vp, vp, vp, vp]),

@@ -18,6 +18,8 @@ int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long 
                     int *d_err = nullptr, double *d_sum6 = nullptr);
 int launch_ray_init(Ray *d_rays, long nrays, long first_nest, long ray_order, double binL_2, cudaStream_t st);
 int launch_ray_summary(const Ray *d_rays, long nrays, double *d_out6, cudaStream_t st);
+int launch_ray_output(const Ray *d_rays, Ray *d_out, long nrays, long ray_order, cudaStream_t st);
+int launch_deposit_ngp(const float *d_pos, const float *d_mass, long nparts, long order, float *d_ringmap, cudaStream_t st);
 void launch_healpix_index(int what, long order, long n, const long *in, const double *th, const double *ph, long *out, cudaStream_t st);
 void launch_healpix_interpol(long order, long n, const double *vec, long *pix, double *wgt, cudaStream_t st);
 void sht_plan_set_peers(ShtPlan *p, void *const *g_send_ptrs, void *const *b_recv_ptrs);
@@ -266,6 +268,17 @@ int clb_ray_init_dev(void *rays, long nrays, long first_nest, long ray_order, do
 int clb_ray_summary_dev(const void *rays, long nrays, double *out6, void *stream)
 {
   int n = launch_ray_summary(reinterpret_cast<const Ray *>(rays), nrays, out6, (cudaStream_t)stream);
+  g_launches += n; return n;
+}
+int clb_ray_output_dev(const void *rays, void *out_rays, long nrays, long ray_order, void *stream)
+{
+  int n = launch_ray_output(reinterpret_cast<const Ray *>(rays), reinterpret_cast<Ray *>(out_rays), nrays, ray_order,
+                            (cudaStream_t)stream);
+  g_launches += n; return n;
+}
+int clb_deposit_ngp_dev(const float *pos, const float *mass, long nparts, long order, float *ringmap, void *stream)
+{
+  int n = launch_deposit_ngp(pos, mass, nparts, order, ringmap, (cudaStream_t)stream);
   g_launches += n; return n;
 }
 void clb_healpix_index_dev(int what, long order, long n, const long *in, const double *theta, const double *phi,

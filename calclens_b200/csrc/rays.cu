@@ -221,6 +221,66 @@ int launch_ray_summary(const Ray *d_rays, long nrays, double *d_out6, cudaStream
   return 1;
 }
 
+// write_rays' pre-output transform (rayio.c:300-312) into a separate output array (the device-resident rays keep
+// their current-position basis): A, Aprev parallel transported from the ray's position to the centre of the pixel it
+// is observed in (paratrans_ray_curr2obs, rot_paratrans.c:274-302), then alpha, A, Aprev, U rotated from the
+// (theta, phi) to the (ra, dec) basis (rot_ray_ang2radec, rot_paratrans.c:375-411).
+__global__ void ray_output_kernel(const Ray *__restrict__ rays, Ray *__restrict__ out, long nrays, long ray_order)
+{
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrays) return;
+  Ray r = rays[i];
+  double obs[3], c, s, T[2][2], RT[2][2];
+  nest2vec(r.nest, ray_order, obs);
+  paratrans_angle(r.n, obs, c, s);   // the reference evaluates the same angle once per tensor
+  T[0][0] = r.Aprev[0]; T[0][1] = r.Aprev[1]; T[1][0] = r.Aprev[2]; T[1][1] = r.Aprev[3];
+  transport_tensor(T, c, s, RT);
+  r.Aprev[0] = RT[0][0]; r.Aprev[1] = RT[0][1]; r.Aprev[2] = RT[1][0]; r.Aprev[3] = RT[1][1];
+  T[0][0] = r.A[0]; T[0][1] = r.A[1]; T[1][0] = r.A[2]; T[1][1] = r.A[3];
+  transport_tensor(T, c, s, RT);
+  r.A[0] = RT[0][0]; r.A[1] = RT[0][1]; r.A[2] = RT[1][0]; r.A[3] = RT[1][1];
+  const double a0 = r.alpha[0], a1 = r.alpha[1];
+  r.alpha[0] = a1; r.alpha[1] = -1.0 * a0;
+  double *M[3] = {r.A, r.Aprev, r.U};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double m00 = M[k][0], m01 = M[k][1], m10 = M[k][2], m11 = M[k][3];
+    M[k][0] = m11; M[k][2] = -1.0 * m01; M[k][1] = -1.0 * m10; M[k][3] = m00;
+  }
+  out[i] = r;
+}
+int launch_ray_output(const Ray *d_rays, Ray *d_out, long nrays, long ray_order, cudaStream_t st)
+{
+  if (nrays <= 0) return 0;
+  ray_output_kernel<<<(unsigned)((nrays + 127) / 128), 128, 0, st>>>(d_rays, d_out, nrays, ray_order);
+  CLB_CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
+// NGP particle deposit (shtpoissonsolve.c:128-150, NGPSHTDENS): val += (float)(mass/MASS_SCALE) in the pixel
+// ang2nest(vec2ang(pos), poissonOrder), written to a RING-ordered map (the reference deposits into NEST-ordered local
+// cells and shuffles them to rings, map_shuffle.c:633).  The pixel index is bit-exact; float atomics make the sum
+// independent of the particle order exactly when all particles of a pixel carry the same mass (the usual case: every
+// partial sum k*m is then formed by the same sequence of additions), otherwise it agrees to float round-off.
+__global__ void deposit_ngp_kernel(const float *__restrict__ pos, const float *__restrict__ mass, long nparts, long order,
+                                   float *__restrict__ ringmap)
+{
+  for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < nparts; k += (long)gridDim.x * blockDim.x) {
+    double vec[3] = {(double)pos[3 * k], (double)pos[3 * k + 1], (double)pos[3 * k + 2]}, theta, phi;
+    vec2ang(vec, theta, phi);
+    const long pix = nest2ring(ang2nest(theta, phi, order), order);
+    atomicAdd(&ringmap[pix], (float)(mass[k] / 1e10));   // MASS_SCALE
+  }
+}
+int launch_deposit_ngp(const float *d_pos, const float *d_mass, long nparts, long order, float *d_ringmap, cudaStream_t st)
+{
+  if (nparts <= 0) return 0;
+  const long blocks = std::min<long>((nparts + 255) / 256, 148L * 16);
+  deposit_ngp_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_pos, d_mass, nparts, order, d_ringmap);
+  CLB_CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
 // ---- small utility kernels used by tests: device versions of the indexing functions ----
 __global__ void healpix_index_kernel(int what, long order, long n, const long *__restrict__ in, const double *__restrict__ th,
                                      const double *__restrict__ ph, long *__restrict__ out)

@@ -119,6 +119,16 @@ int clb_ray_init_dev(void *rays, long nrays, long first_nest, long ray_order, do
 /* six sums over the rays (convergence, shear 1/2, |alpha|^2, phi, rotation): the per-plane scalar a host reads back */
 int clb_ray_summary_dev(const void *rays, long nrays, double *out6, void *stream);
 
+/* ---- the callers either side of the path ("next" rows) ----
+ * write_rays' pre-output transform (rayio.c:300-312: paratrans_ray_curr2obs + rot_ray_ang2radec,
+ * rot_paratrans.c:274-302,375-411) from the device-resident rays into out_rays (device, same layout), which the host
+ * copies back and hands to the unchanged FITS/binary writer; the resident rays are left untouched (the reference
+ * undoes the transform after writing, rayio.c:340-352). */
+int clb_ray_output_dev(const void *rays, void *out_rays, long nrays, long ray_order, void *stream);
+/* NGP particle deposit of shtpoissonsolve.c:128-150: ringmap[pix(pos)] += (float)(mass/1e10), pos = 3 floats per particle
+ * (Part.pos, raytrace.h:246-253), ringmap RING-ordered and zeroed by the caller; feeds clb_load_density_dev */
+int clb_deposit_ngp_dev(const float *pos, const float *mass, long nparts, long order, float *ringmap, void *stream);
+
 /* ---- host-pointer entry points (single rank; transfers inside) ---- */
 /* map2alm_mpi on a RING-ordered map (healpix_shtrans.h:67) */
 void clb_map2alm(clb_sht_plan *plan, const float *ringmap, double *alm_re, double *alm_im, int apply_poisson_filter);

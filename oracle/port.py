@@ -42,6 +42,8 @@ def lib():
         L.port_ang2nest.restype = C.c_long; L.port_ang2nest.argtypes = [C.c_double, C.c_double, C.c_long]
         L.port_nest2vec.restype = None; L.port_nest2vec.argtypes = [C.c_long, vp, C.c_long]
         L.port_get_interpol.restype = None; L.port_get_interpol.argtypes = [C.c_double, C.c_double, vp, vp, C.c_long]
+        L.port_ray_output.restype = None; L.port_ray_output.argtypes = [vp, C.c_long, C.c_long]
+        L.port_deposit_ngp.restype = None; L.port_deposit_ngp.argtypes = [vp, vp, C.c_long, C.c_long, vp]
         L.port_sizeof_ray.restype = C.c_long
         assert L.port_sizeof_ray() == 176
         _lib = L
@@ -90,6 +92,18 @@ def init_rays(ray_order, binL_2, first=0, n=None):
     rays = np.zeros(n, dtype=RAY_DTYPE)
     lib().port_init_rays(rays.ctypes.data, first, n, ray_order, binL_2)
     return rays
+
+
+def ray_output(rays, ray_order):
+    assert rays.dtype == RAY_DTYPE and rays.flags.c_contiguous
+    lib().port_ray_output(rays.ctypes.data, rays.size, ray_order)
+
+
+def deposit_ngp(pos, mass, order):
+    pos = np.ascontiguousarray(pos, dtype=np.float32); mass = np.ascontiguousarray(mass, dtype=np.float32)
+    out = np.zeros(12 << (2 * order), dtype=np.float32)
+    lib().port_deposit_ngp(pos.ctypes.data, mass.ctypes.data, mass.size, order, out.ctypes.data)
+    return out
 
 
 def plmgen(lmax, cth, sth, m):

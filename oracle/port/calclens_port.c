@@ -611,4 +611,40 @@ void port_init_rays(ray_t *rays, long first, long n, long ray_order, double binL
     rays[i].A[0] = 1.0; rays[i].A[3] = 1.0; rays[i].Aprev[0] = 1.0; rays[i].Aprev[3] = 1.0;
   }
 }
+/* rayio.c:300-312: paratrans_ray_curr2obs (rot_paratrans.c:274-302) then rot_ray_ang2radec (:375-411) */
+void port_ray_output(ray_t *rays, long nrays, long ray_order)
+{
+  for (long i = 0; i < nrays; ++i) {
+    ray_t *r = &rays[i];
+    double obs[3], c, s, T[2][2], R[2][2];
+    port_nest2vec(r->nest, obs, ray_order);
+    para_angle(r->n, obs, &c, &s);        /* the reference evaluates the same angle for Aprev and for A */
+    T[0][0] = r->Aprev[0]; T[0][1] = r->Aprev[1]; T[1][0] = r->Aprev[2]; T[1][1] = r->Aprev[3];
+    para_tensor(T, c, s, R);
+    r->Aprev[0] = R[0][0]; r->Aprev[1] = R[0][1]; r->Aprev[2] = R[1][0]; r->Aprev[3] = R[1][1];
+    T[0][0] = r->A[0]; T[0][1] = r->A[1]; T[1][0] = r->A[2]; T[1][1] = r->A[3];
+    para_tensor(T, c, s, R);
+    r->A[0] = R[0][0]; r->A[1] = R[0][1]; r->A[2] = R[1][0]; r->A[3] = R[1][1];
+    /* (theta, phi) -> (ra, dec): alpha -> (alpha_phi, -alpha_theta); M -> [[M11, -M10], [-M01, M00]] */
+    double a0 = r->alpha[0], a1 = r->alpha[1];
+    r->alpha[0] = a1; r->alpha[1] = -1.0 * a0;
+    double *M[3] = {r->A, r->Aprev, r->U};
+    for (int k = 0; k < 3; ++k) {
+      double m00 = M[k][0], m01 = M[k][1], m10 = M[k][2], m11 = M[k][3];
+      M[k][0] = m11; M[k][2] = -1.0 * m01; M[k][1] = -1.0 * m10; M[k][3] = m00;
+    }
+  }
+}
+
+/* shtpoissonsolve.c:128-150 (NGPSHTDENS): val += (float)(mass/MASS_SCALE) at ang2nest(vec2ang(pos)); RING map out */
+void port_deposit_ngp(const float *pos, const float *mass, long nparts, long order, float *ringmap)
+{
+  for (long k = 0; k < nparts; ++k) {
+    double vec[3] = {(double)pos[3 * k], (double)pos[3 * k + 1], (double)pos[3 * k + 2]}, theta, phi;
+    vec2ang_(vec, &theta, &phi);
+    long nest = port_ang2nest(theta, phi, order);
+    ringmap[port_nest2ring(nest, order)] += (float)(mass[k] / 1e10);
+  }
+}
+
 long port_sizeof_ray(void) { return (long)sizeof(ray_t); }

@@ -42,6 +42,8 @@ def lib():
         L.ref_plmgen.restype = C.c_long; L.ref_plmgen.argtypes = [C.c_long, C.c_double, C.c_double, C.c_long, C.c_void_p]
         L.ref_sizeof_ray.restype = C.c_long
         L.ref_init_rays.restype = None; L.ref_init_rays.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_double]
+        L.ref_ray_output.restype = None; L.ref_ray_output.argtypes = [C.c_void_p, C.c_long, C.c_long]
+        L.ref_deposit_ngp.restype = None; L.ref_deposit_ngp.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_void_p]
         assert L.ref_sizeof_ray() == 176
         # HEALPix helpers straight from healpix_utils.c
         L.ring2nest.restype = C.c_long; L.ring2nest.argtypes = [C.c_long, C.c_long]
@@ -121,6 +123,20 @@ def init_rays(ray_order, binL_2, first=0, n=None):
     rays = np.zeros(n, dtype=RAY_DTYPE)
     lib().ref_init_rays(rays.ctypes.data, first, n, ray_order, binL_2)
     return rays
+
+
+def ray_output(rays, ray_order):
+    """write_rays' pre-output transform (rayio.c:300-312) in place: paratrans_ray_curr2obs + rot_ray_ang2radec."""
+    assert rays.dtype == RAY_DTYPE and rays.flags.c_contiguous
+    lib().ref_ray_output(rays.ctypes.data, rays.size, ray_order)
+
+
+def deposit_ngp(pos, mass, order):
+    """NGP deposit of shtpoissonsolve.c:128-150 -> RING float32 map (sequential float accumulation)."""
+    pos = np.ascontiguousarray(pos, dtype=np.float32); mass = np.ascontiguousarray(mass, dtype=np.float32)
+    out = np.zeros(12 << (2 * order), dtype=np.float32)
+    lib().ref_deposit_ngp(pos.ctypes.data, mass.ctypes.data, mass.size, order, out.ctypes.data)
+    return out
 
 
 NAME = "reference (oracle/_ref)"

@@ -186,4 +186,31 @@ void ref_init_rays(HEALPixRay *rays, long first, long n, long ray_order, double 
   }
 }
 
+/* write_rays' pre-output transform (rayio.c:300-312): parallel transport A, Aprev from the ray's current position to
+ * the pixel it is observed in, then switch every ray quantity from the (theta, phi) to the (ra, dec) basis */
+void ref_ray_output(HEALPixRay *rays, long Nrays, long ray_order)
+{
+  long i;
+  rayTraceData.rayOrder = ray_order;
+  for (i = 0; i < Nrays; ++i) {
+    paratrans_ray_curr2obs(&rays[i]);
+    rot_ray_ang2radec(&rays[i]);
+  }
+}
+
+/* NGP particle deposit, the loop of shtpoissonsolve.c:128-150 (NGPSHTDENS) on a full-sky single-rank domain, written
+ * to a RING-ordered float map: mapCells[...].val += (float)(mass/MASS_SCALE) at ang2nest(vec2ang(pos), poissonOrder).
+ * pos = 3 floats per particle (Part.pos, raytrace.h:246-253). */
+void ref_deposit_ngp(const float *pos, const float *mass, long Nparts, long order, float *ringmap)
+{
+  long k;
+  for (k = 0; k < Nparts; ++k) {
+    double vec[3], theta, phi;
+    vec[0] = (double)pos[3 * k]; vec[1] = (double)pos[3 * k + 1]; vec[2] = (double)pos[3 * k + 2];
+    vec2ang(vec, &theta, &phi);
+    long mapNest = ang2nest(theta, phi, order);
+    ringmap[nest2ring(mapNest, order)] += (float)(mass[k] / MASS_SCALE);
+  }
+}
+
 long ref_sizeof_ray(void) { return (long)sizeof(HEALPixRay); }

@@ -544,3 +544,59 @@ def test_global_scratch_ring_fft_matches_shared_memory_path(clb):
     finally:
         L.clb_set_tuning(4, 0)
     assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+
+
+def test_ray_output_transform_vs_oracle(clb, oracle):
+    """write_rays' pre-output transform (rayio.c:300-312) on the device vs the reference's paratrans_ray_curr2obs +
+    rot_ray_ang2radec; the resident rays must stay untouched."""
+    import torch
+    from calclens_b200 import _lib
+    L = _lib.load()
+    order = 5
+    rng = np.random.default_rng(23)
+    rays = oracle.init_rays(order, 15.0)
+    rays["n"] += rng.normal(size=rays["n"].shape) * 0.02          # rays have drifted from their observed pixel
+    for f, n in (("A", 4), ("Aprev", 4), ("U", 4), ("alpha", 2)):
+        rays[f] += rng.normal(size=(rays.size, n)) * 0.05
+    ro = rays.copy()
+    oracle.ray_output(ro, order)
+    d_in = torch.from_numpy(rays.view(np.uint8).reshape(-1).copy()).cuda()
+    d_out = torch.zeros_like(d_in)
+    L.clb_ray_output_dev(d_in.data_ptr(), d_out.data_ptr(), rays.size, order, None)
+    torch.cuda.synchronize()
+    rg = d_out.cpu().numpy().view(rays.dtype)
+    assert np.array_equal(d_in.cpu().numpy(), rays.view(np.uint8).reshape(-1))
+    assert np.array_equal(rg["nest"], ro["nest"]) and np.array_equal(rg["n"], ro["n"]) and np.array_equal(rg["U"], ro["U"])
+    assert_rays_match(rg, ro)
+
+
+def test_ngp_deposit_vs_oracle(clb, oracle):
+    """NGP particle deposit (shtpoissonsolve.c:128-150): bit-exact pixel assignment; with equal-mass particles the
+    float sums are order independent and must match the sequential reference loop bit for bit."""
+    import torch
+    from calclens_b200 import _lib
+    L = _lib.load()
+    order = 6
+    npix = 12 << (2 * order)
+    rng = np.random.default_rng(29)
+    n = 400000
+    pos = rng.normal(size=(n, 3)).astype(np.float32) * np.float32(300.0)
+    pos[:6] = [[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, 1, 0], [-1, 0, 0], [1e-3, -1e-3, 1]]   # poles, axes, near-pole
+    mass = np.full(n, 3.7e9, dtype=np.float32)
+    want = oracle.deposit_ngp(pos, mass, order)
+    dm = torch.zeros(npix, dtype=torch.float32, device="cuda")
+    dp = torch.from_numpy(pos).cuda(); dmass = torch.from_numpy(mass).cuda()
+    L.clb_deposit_ngp_dev(dp.data_ptr(), dmass.data_ptr(), n, order, dm.data_ptr(), None)
+    torch.cuda.synchronize()
+    got = dm.cpu().numpy()
+    assert np.array_equal(got, want)
+    assert abs(float(got.sum()) - n * 0.37) < 1e-3 * n * 0.37
+    # unequal masses: same pixels, sums to float round-off
+    mass2 = (3.7e9 * (0.5 + rng.random(n))).astype(np.float32)
+    want2 = oracle.deposit_ngp(pos, mass2, order)
+    dm.zero_()
+    L.clb_deposit_ngp_dev(dp.data_ptr(), torch.from_numpy(mass2).cuda().data_ptr(), n, order, dm.data_ptr(), None)
+    torch.cuda.synchronize()
+    got2 = dm.cpu().numpy()
+    assert np.array_equal(got2 != 0, want2 != 0)
+    assert np.allclose(got2, want2, rtol=2e-6, atol=0)

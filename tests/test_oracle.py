@@ -135,3 +135,25 @@ def test_point_mass_sign_and_scale(g_sht):
             g = np.hypot(maps[1][p], maps[2][p])
             ratios.append(g / (S / (4 * np.pi) / np.tan(d / 2)))
     assert 0.85 < np.mean(ratios) < 1.15
+
+
+def test_port_matches_reference_on_next_rows():
+    """The restatement of the two 'next' rows (ray output transform, NGP deposit) is bit-identical to the reference
+    functions compiled in oracle/_ref (paratrans_ray_curr2obs, rot_ray_ang2radec, vec2ang + ang2nest)."""
+    from oracle import port, ref
+    if not ref.available():
+        import pytest
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(1)
+    order = 5
+    pos = rng.normal(size=(20000, 3)).astype(np.float32)
+    pos[:3] = [[0, 0, 1], [0, 0, -1], [1, 0, 0]]
+    mass = (3.7e9 * (0.5 + rng.random(20000))).astype(np.float32)
+    assert np.array_equal(ref.deposit_ngp(pos, mass, order), port.deposit_ngp(pos, mass, order))
+    rays = ref.init_rays(4, 15.0)
+    rays["n"] += rng.normal(size=rays["n"].shape) * 0.01
+    for f, n in (("A", 4), ("Aprev", 4), ("U", 4), ("alpha", 2)):
+        rays[f] += rng.normal(size=(rays.size, n)) * 0.05
+    r1 = rays.copy(); r2 = rays.copy()
+    ref.ray_output(r1, 4); port.ray_output(r2, 4)
+    assert r1.tobytes() == r2.tobytes()
