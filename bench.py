@@ -463,6 +463,7 @@ def main():
                 "setup_s": t_setup}
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
+    solver.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

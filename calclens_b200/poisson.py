@@ -116,7 +116,7 @@ class LensPlaneSolver:
             self.g_recv, self.b_recv = self.g_send, self.b_send
         self.alm_re = torch.empty(max(p.Nlm, 1), **f64)
         self.alm_im = torch.empty(max(p.Nlm, 1), **f64)
-        self.maps = torch.zeros((6, self.npix), dtype=torch.float32, device=self.device)
+        self.maps = None
         self.summary = torch.zeros(6, **f64)
         self._dens = [torch.zeros(self.npix, dtype=torch.float32, device=self.device) for _ in range(2)]
         self._copy_stream = torch.cuda.Stream(device=self.device, priority=-1)   # runs behind the compute kernels, gets SM slots first
@@ -130,6 +130,8 @@ class LensPlaneSolver:
         self._peer_bufs = []
         if self.nranks > 1 and fused:
             self._setup_peer_exchange()
+        if self.maps is None:
+            self.maps = torch.zeros((6, self.npix), dtype=torch.float32, device=self.device)
         self.rays = None
         self.nrays = 0
         self.first_nest = 0
@@ -197,6 +199,26 @@ class LensPlaneSolver:
             self.need_fraction = float(np.unpackbits(mask[:, None], axis=1)[:, -self.nranks:].sum()) / (mask.size * self.nranks)
         self.fused = True
         self.dist.barrier(group=self.group)
+
+    def close(self):
+        """Release the peer mappings and the library-owned buffers (after every rank has stopped using them)."""
+        if self._peer_bufs:
+            torch.cuda.synchronize()
+            if self.nranks > 1:
+                self.dist.barrier(group=self.group)
+            own, peers = self._peer_bufs
+            self.maps = self.g_send = self.b_recv = None
+            for q in range(self.nranks):
+                if q != self.rank:
+                    for ptr in peers[q]:
+                        if ptr:
+                            self.lib.clb_peer_release(ptr)
+            if self.nranks > 1:
+                self.dist.barrier(group=self.group)
+            for ptr in own:
+                self.lib.clb_peer_free(ptr)
+            self._peer_bufs = []
+            self.fused = False
 
     def _stream_barrier(self):
         """All ranks' work enqueued so far has completed before anything enqueued afterwards starts (stream ordered)."""

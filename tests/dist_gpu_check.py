@@ -62,6 +62,7 @@ def main():
         print("ray sums rel diff ok:", ok, sums[-1][:3], sums1[-1][:3])
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.broadcast(t, 0)
+    solver.close()
     dist.destroy_process_group()
     if t.item() != 1.0:
         sys.exit(1)
