@@ -274,6 +274,23 @@ __device__ __forceinline__ long ray_interp_accumulate_fast(Ray &ray, long order,
 }
 #endif
 
+// rayprop_sphere of a -DBORNAPPRX build (rayprop.c:40-62): the ray moves radially to the next shell and the A recursion
+// uses U alone (no U A product, no deflection, no transport)
+CLB_HD void ray_propagate_born(Ray &ray, double wp, double wpm1, double wpm2)
+{
+  double Ap[4];
+  ray.n[0] = ray.n[0] / wpm1 * wp;
+  ray.n[1] = ray.n[1] / wpm1 * wp;
+  ray.n[2] = ray.n[2] / wpm1 * wp;
+  for (int k = 0; k < 4; ++k)
+    Ap[k] = (1.0 - wpm1 * (wp - wpm2) / wp / (wpm1 - wpm2)) * ray.Aprev[k] + (wpm1 * (wp - wpm2) / wp / (wpm1 - wpm2)) * ray.A[k]
+            - ((wp - wpm1) / wp) * (ray.U[k]);
+  for (int k = 0; k < 4; ++k) { ray.Aprev[k] = ray.A[k]; ray.A[k] = Ap[k]; }
+  double r = sqrt(ray.n[0] * ray.n[0] + ray.n[1] * ray.n[1] + ray.n[2] * ray.n[2]);   // rayprop.c:183-187 (both builds)
+  r = wp / r;
+  ray.n[0] *= r; ray.n[1] *= r; ray.n[2] *= r;
+}
+
 // One lens-plane step of one ray: wp = w_{p+1}, wpm1 = w_p, wpm2 = w_{p-1} (the reference's argument names).
 //                                        [rayprop.c:18-189 rayprop_sphere (non-BORNAPPRX branch),
 //                                         rot_paratrans.c:17-45 generate_rotmat_axis_angle_countercw]

@@ -59,7 +59,7 @@ __device__ __forceinline__ void ray_cp_async16(void *smem, const void *gmem)
 }
 
 // mode bit 0: zero phi/alpha/U first (the driver's pre-solve reset, raytrace.c:213-230)
-// mode bit 1: interpolate + accumulate;  mode bit 2: propagate
+// mode bit 1: interpolate + accumulate;  mode bit 2: propagate;  mode bit 3 (with bit 2): Born-approximation propagate
 // Persistent CTAs walk the ray array in tiles of kRayThreads records; the next tile streams into the second
 // shared-memory buffer (cp.async) while the current one is being computed, and results leave through coalesced
 // 16-byte stores.
@@ -112,7 +112,10 @@ ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab 
         // missing map cell, shtpoissonsolve.c:683-689; here the flag is raised and the host aborts)
         if (need && !(need[ring2nest(p0, order) >> coarse_shift] & rank_bit)) atomicOr(err, 1);
       }
-      if (mode & 4) ray_propagate(ray, wp, wpm1, wpm2);
+      if (mode & 4) {
+        if (mode & 8) ray_propagate_born(ray, wp, wpm1, wpm2);
+        else ray_propagate(ray, wp, wpm1, wpm2);
+      }
       s_rays[threadIdx.x] = ray;
       if (sum6) {   // same six sums as ray_summary_kernel, without a second pass over the ray array
         ps[0] = 1.0 - 0.5 * (ray.A[0] + ray.A[3]);

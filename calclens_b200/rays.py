@@ -11,15 +11,15 @@ RAY_DTYPE = np.dtype([("nest", "<i8"), ("n", "<f8", 3), ("beta", "<f8", 3), ("al
                       ("A", "<f8", 4), ("Aprev", "<f8", 4), ("U", "<f8", 4), ("phi", "<f8")], align=False)
 assert RAY_DTYPE.itemsize == 176
 
-MODE_ZERO, MODE_INTERP, MODE_PROP = 1, 2, 4
+MODE_ZERO, MODE_INTERP, MODE_PROP, MODE_BORN = 1, 2, 4, 8
 
 
-def rayprop_sphere(wp, wpm1, wpm2, rays):
+def rayprop_sphere(wp, wpm1, wpm2, rays, born=False):
     """rayprop_sphere(wp, wpm1, wpm2, bundleCellInd) (rayprop.c:18) over a host array of HEALPixRay, in place.
     The reference is called once per bundle cell (raytrace.c:256-269); here the caller passes the cell's rays
-    (or all rays at once)."""
+    (or all rays at once).  born=True: the reference's -DBORNAPPRX build (rayprop.c:40-62)."""
     assert rays.dtype == RAY_DTYPE and rays.flags.c_contiguous
-    _lib.load().clb_ray_step(rays.ctypes.data, rays.size, None, 0, wp, wpm1, wpm2, MODE_PROP)
+    _lib.load().clb_ray_step(rays.ctypes.data, rays.size, None, 0, wp, wpm1, wpm2, MODE_PROP | (MODE_BORN if born else 0))
 
 
 def shearinterp_rays(maps, map_order, rays, zero_first=False):

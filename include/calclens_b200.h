@@ -109,7 +109,8 @@ int clb_load_density_dev(const clb_sht_plan *plan, const float *src, float *dst,
 
 /* ---- ray step.  mode bits: 1 zero phi/alpha/U (raytrace.c:213-230); 2 interpolate + accumulate
  * (shtpoissonsolve.c:666-702 with shearinterp_comp :1122-1204); 4 propagate = rayprop_sphere(wp, wpm1, wpm2, .)
- * (rayprop.c:18-189; argument names as in raytrace.h:431).  maps are needed only with bit 2. ---- */
+ * (rayprop.c:18-189; argument names as in raytrace.h:431); 8 (with 4) the -DBORNAPPRX form of it (rayprop.c:40-62).
+ * maps are needed only with bit 2. ---- */
 int clb_ray_step_dev(void *rays, long nrays, const float *const maps[6], long map_order, double wp, double wpm1,
                      double wpm2, int mode, void *stream);
 

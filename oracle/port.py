@@ -42,6 +42,7 @@ def lib():
         L.port_ang2nest.restype = C.c_long; L.port_ang2nest.argtypes = [C.c_double, C.c_double, C.c_long]
         L.port_nest2vec.restype = None; L.port_nest2vec.argtypes = [C.c_long, vp, C.c_long]
         L.port_get_interpol.restype = None; L.port_get_interpol.argtypes = [C.c_double, C.c_double, vp, vp, C.c_long]
+        L.port_rayprop_born.restype = None; L.port_rayprop_born.argtypes = [vp, C.c_long, C.c_double, C.c_double, C.c_double]
         L.port_ray_output.restype = None; L.port_ray_output.argtypes = [vp, C.c_long, C.c_long]
         L.port_deposit_ngp.restype = None; L.port_deposit_ngp.argtypes = [vp, vp, C.c_long, C.c_long, vp]
         L.port_sizeof_ray.restype = C.c_long
@@ -78,6 +79,11 @@ def alm2allmaps(order, lmax, are, aim):
 def rayprop(rays, wp, wpm1, wpm2):
     assert rays.dtype == RAY_DTYPE and rays.flags.c_contiguous
     lib().port_rayprop(rays.ctypes.data, rays.size, wp, wpm1, wpm2)
+
+
+def rayprop_born(rays, wp, wpm1, wpm2):
+    assert rays.dtype == RAY_DTYPE and rays.flags.c_contiguous
+    lib().port_rayprop_born(rays.ctypes.data, rays.size, wp, wpm1, wpm2)
 
 
 def shearinterp(poisson_order, bundle_order, maps, rays):

@@ -601,6 +601,23 @@ void port_rayprop(ray_t *rays, long nrays, double wp, double wpm1, double wpm2)
 }
 
 /* raytrace_utils.c:302-347 init_rays for NEST pixels first..first+n-1 */
+/* rayprop.c:40-62, the -DBORNAPPRX build of rayprop_sphere: rays move radially, A recursion without the U A product */
+void port_rayprop_born(ray_t *rays, long nrays, double wp, double wpm1, double wpm2)
+{
+  for (long i = 0; i < nrays; ++i) {
+    ray_t *r = &rays[i];
+    double Ap[4];
+    r->n[0] = r->n[0] / wpm1 * wp; r->n[1] = r->n[1] / wpm1 * wp; r->n[2] = r->n[2] / wpm1 * wp;
+    for (int k = 0; k < 4; ++k)
+      Ap[k] = (1.0 - wpm1 * (wp - wpm2) / wp / (wpm1 - wpm2)) * r->Aprev[k] + (wpm1 * (wp - wpm2) / wp / (wpm1 - wpm2)) * r->A[k]
+              - ((wp - wpm1) / wp) * (r->U[k]);
+    for (int k = 0; k < 4; ++k) { r->Aprev[k] = r->A[k]; r->A[k] = Ap[k]; }
+    double rr = sqrt(r->n[0] * r->n[0] + r->n[1] * r->n[1] + r->n[2] * r->n[2]);   /* :183-187, both builds */
+    rr = wp / rr;
+    r->n[0] *= rr; r->n[1] *= rr; r->n[2] *= rr;
+  }
+}
+
 void port_init_rays(ray_t *rays, long first, long n, long ray_order, double binL_2)
 {
   memset(rays, 0, sizeof(ray_t) * n);

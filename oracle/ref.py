@@ -42,6 +42,7 @@ def lib():
         L.ref_plmgen.restype = C.c_long; L.ref_plmgen.argtypes = [C.c_long, C.c_double, C.c_double, C.c_long, C.c_void_p]
         L.ref_sizeof_ray.restype = C.c_long
         L.ref_init_rays.restype = None; L.ref_init_rays.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_double]
+        L.ref_rayprop_born.restype = None; L.ref_rayprop_born.argtypes = [C.c_void_p, C.c_long, C.c_double, C.c_double, C.c_double]
         L.ref_ray_output.restype = None; L.ref_ray_output.argtypes = [C.c_void_p, C.c_long, C.c_long]
         L.ref_deposit_ngp.restype = None; L.ref_deposit_ngp.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_void_p]
         assert L.ref_sizeof_ray() == 176
@@ -92,6 +93,12 @@ def alm2allmaps(order, lmax, are, aim):
 def rayprop(rays, wp, wpm1, wpm2):
     assert rays.dtype == RAY_DTYPE and rays.flags.c_contiguous
     lib().ref_rayprop(rays.ctypes.data, rays.size, wp, wpm1, wpm2)
+
+
+def rayprop_born(rays, wp, wpm1, wpm2):
+    """rayprop_sphere of a -DBORNAPPRX build (rayprop.c:40-62)."""
+    assert rays.dtype == RAY_DTYPE and rays.flags.c_contiguous
+    lib().ref_rayprop_born(rays.ctypes.data, rays.size, wp, wpm1, wpm2)
 
 
 def shearinterp(poisson_order, bundle_order, maps, rays):

@@ -115,6 +115,20 @@ void ref_rayprop(HEALPixRay *rays, long Nrays, double wp, double wpm1, double wp
   bundleCells = save; NbundleCells = saveN;
 }
 
+/* the same with the reference built -DBORNAPPRX (rayprop.c:40-62): the Makefile compiles rayprop.c a second time under
+ * the symbol rayprop_sphere_born */
+void rayprop_sphere_born(double wp, double wpm1, double wpm2, long bundleCellInd);
+void ref_rayprop_born(HEALPixRay *rays, long Nrays, double wp, double wpm1, double wpm2)
+{
+  HEALPixBundleCell cell;
+  memset(&cell, 0, sizeof(cell));
+  cell.Nrays = Nrays; cell.rays = rays;
+  HEALPixBundleCell *save = bundleCells; long saveN = NbundleCells;
+  bundleCells = &cell; NbundleCells = 1;
+  rayprop_sphere_born(wp, wpm1, wpm2, 0);
+  bundleCells = save; NbundleCells = saveN;
+}
+
 /* shearinterp_comp + the caller's accumulation (shtpoissonsolve.c:666-702,1122-1204) on a full-sky domain:
  * every bundle cell is PRIMARY and owns its 4^(poissonOrder-bundleOrder) NEST-ordered map cells.
  * maps = six RING-ordered float maps in the ref_alm2allmaps order.  Returns the number of rays for which

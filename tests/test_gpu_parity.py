@@ -600,3 +600,18 @@ def test_ngp_deposit_vs_oracle(clb, oracle):
     got2 = dm.cpu().numpy()
     assert np.array_equal(got2 != 0, want2 != 0)
     assert np.allclose(got2, want2, rtol=2e-6, atol=0)
+
+
+def test_born_approximation_ray_step_vs_oracle(clb, oracle):
+    """the -DBORNAPPRX form of rayprop_sphere (rayprop.c:40-62), mode bit 8"""
+    order = 4
+    rng = np.random.default_rng(37)
+    rays = oracle.init_rays(order, 15.0)
+    for f, n in (("A", 4), ("Aprev", 4), ("U", 4), ("alpha", 2)):
+        rays[f] += rng.normal(size=(rays.size, n)) * 0.05
+    ro = rays.copy(); rg = rays.copy()
+    for (wp, wpm1, wpm2) in ((45.0, 15.0, 0.0), (75.0, 45.0, 15.0)):
+        oracle.rayprop_born(ro, wp, wpm1, wpm2)
+        clb.rayprop_sphere(wp, wpm1, wpm2, rg, born=True)
+    assert_rays_match(rg, ro)
+    assert np.array_equal(rg["beta"], ro["beta"]) and np.array_equal(rg["alpha"], ro["alpha"])

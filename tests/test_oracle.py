@@ -157,3 +157,7 @@ def test_port_matches_reference_on_next_rows():
     r1 = rays.copy(); r2 = rays.copy()
     ref.ray_output(r1, 4); port.ray_output(r2, 4)
     assert r1.tobytes() == r2.tobytes()
+    r1 = rays.copy(); r2 = rays.copy()
+    ref.rayprop_born(r1, 45.0, 15.0, 0.0); port.rayprop_born(r2, 45.0, 15.0, 0.0)
+    ref.rayprop_born(r1, 75.0, 45.0, 15.0); port.rayprop_born(r2, 75.0, 45.0, 15.0)
+    assert r1.tobytes() == r2.tobytes()
