@@ -615,3 +615,46 @@ def test_born_approximation_ray_step_vs_oracle(clb, oracle):
         clb.rayprop_sphere(wp, wpm1, wpm2, rg, born=True)
     assert_rays_match(rg, ro)
     assert np.array_equal(rg["beta"], ro["beta"]) and np.array_equal(rg["alpha"], ro["alpha"])
+
+
+def test_point_mass_plane_baseline_config0(clb, oracle):
+    """BASELINE configs[0]: the point-mass test plane (lensplanes/make_lensplanes_pointmass_test.c:156-192: one particle,
+    NGP-deposited into one pixel) at Nside=256, lmax=512, full-sky rays at Nside=512 -- one lens plane through the C ABI
+    against the reference, plus the analytic deflection |grad phi| = S/(4 pi) cot(d/2) (sign and
+    scale; an unsmoothed pixel truncated at lmax rings, so the median over rays is compared, not every ray)."""
+    from calclens_b200 import _lib
+    L = _lib.load()
+    order, lmax, ray_order = 8, 512, 9
+    npix = 12 << (2 * order)
+    counts = np.zeros(npix, dtype=np.float32)
+    pix = 5 * npix // 12 + 1234                       # an equatorial-belt pixel away from the poles
+    counts[pix] = 1.0
+    premul, densmul, backdens = np.float32(1.0), np.float32(3e-2), np.float32(0.0)   # NOBACKDENS, as in the test build
+    wpp1, wp, wpm1 = 45.0, 15.0, 0.0
+    ro = oracle.init_rays(ray_order, wp); rg = ro.copy()
+    ro["alpha"] = 0; ro["U"] = 0; ro["phi"] = 0
+    m = ((counts * premul) * densmul - backdens).astype(np.float32)
+    are, aim = oracle.map2alm(order, lmax, m)
+    are, aim = oracle.poisson_filter(lmax, are, aim)
+    maps = oracle.alm2allmaps(order, lmax, are, aim)
+    oracle.shearinterp(order, 2, maps, ro)
+    alpha_before_prop = ro["alpha"].copy()
+    n_before = ro["n"].copy()
+    oracle.rayprop(ro, wpp1, wp, wpm1)
+    plan = clb.HEALPixSHTPlan(order, lmax)
+    L.clb_lens_plane(plan._h, counts.ctypes.data, float(premul), float(densmul), float(backdens), rg.ctypes.data, rg.size,
+                     wpp1, wp, wpm1)
+    plan.destroy()
+    assert_rays_match(rg, ro)
+    # analytic check on the deflection the GPU path produced
+    S = float(densmul) * (4.0 * np.pi / npix)         # integral of the scaled map over the sphere
+    from oracle import port
+    c = np.zeros(3)
+    port.lib().port_nest2vec(port.ring2nest(pix, order), c.ctypes.data, order)
+    nhat = n_before / np.linalg.norm(n_before, axis=1)[:, None]
+    d = np.arccos(np.clip(nhat @ c, -1, 1))
+    sel = (d > 0.1) & (d < 2.5)
+    amp = np.linalg.norm(rg["alpha"], axis=1)         # alpha = -grad phi (shtpoissonsolve.c:693-694)
+    ratio = amp[sel] / (S / (4 * np.pi) / np.tan(d[sel] / 2))
+    assert 0.97 < np.median(ratio) < 1.03, np.median(ratio)
+    assert np.allclose(rg["alpha"], alpha_before_prop, rtol=0, atol=1e-8 * np.abs(alpha_before_prop).max())
