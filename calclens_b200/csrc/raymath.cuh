@@ -274,6 +274,81 @@ __device__ __forceinline__ long ray_interp_accumulate_fast(Ray &ray, long order,
 }
 #endif
 
+#if defined(__CUDACC__)
+// Plane constants of the A recursion, formed on the host with the reference's expressions (rayprop.c:134-139)
+struct PlaneCoef { double cprev, ccur, cu; };   // (1 - c), c, (wp - wpm1)/wp with c = wpm1 (wp - wpm2) / wp / (wpm1 - wpm2)
+
+// Fast device form of ray_propagate: the same mathematics with the normalisations shared -- |n x a| = |n| |alpha|
+// because a is tangent at n, |theta-hat numerator| = |n| |n_xy| -- and reciprocals multiplied instead of repeated
+// divisions.  Agrees with the line-by-line mirror above to ~1e-15 relative.
+__device__ __forceinline__ void ray_propagate_fast(Ray &ray, double wp, double wpm1, const PlaneCoef &pc)
+{
+  double np[3], betap[3], Ap[4];
+  const double nx = ray.n[0], ny = ray.n[1], nz = ray.n[2];
+  const double nxy2 = nx * nx + ny * ny;
+  const double n2 = nxy2 + nz * nz;
+  const double inv_n = 1.0 / sqrt(n2);
+  const double alpha2 = ray.alpha[0] * ray.alpha[0] + ray.alpha[1] * ray.alpha[1];
+  if (alpha2 > 0.0) {
+    const double alpha = sqrt(alpha2);
+    const double inv_nxy = 1.0 / sqrt(nxy2);
+    // a = alpha_theta theta-hat + alpha_phi phi-hat (unit vectors at n)
+    const double ct = ray.alpha[0] * inv_nxy * inv_n, cp = ray.alpha[1] * inv_nxy;
+    const double a0 = ct * (nz * nx) - cp * ny;
+    const double a1 = ct * (nz * ny) + cp * nx;
+    const double a2 = -ct * nxy2;
+    // unit rotation axis k = (n x a) / (|n| alpha)
+    const double ik = inv_n / alpha;
+    const double k0 = (ny * a2 - nz * a1) * ik, k1 = (nz * a0 - nx * a2) * ik, k2 = (nx * a1 - ny * a0) * ik;
+    double sn, cs;
+    sincos(alpha, &sn, &cs);
+    const double omc = 1.0 - cs;
+    // Rodrigues: beta' = beta cos + (k x beta) sin + k (k . beta)(1 - cos)     [rot_paratrans.c:17-45]
+    const double kb = (k0 * ray.beta[0] + k1 * ray.beta[1] + k2 * ray.beta[2]) * omc;
+    betap[0] = ray.beta[0] * cs + (k1 * ray.beta[2] - k2 * ray.beta[1]) * sn + k0 * kb;
+    betap[1] = ray.beta[1] * cs + (k2 * ray.beta[0] - k0 * ray.beta[2]) * sn + k1 * kb;
+    betap[2] = ray.beta[2] * cs + (k0 * ray.beta[1] - k1 * ray.beta[0]) * sn + k2 * kb;
+    const double qb = 2.0 * (nx * betap[0] + ny * betap[1] + nz * betap[2]);
+    const double qc = wpm1 * wpm1 - wp * wp;
+    const double q = -0.5 * (qb + copysign(sqrt(qb * qb - 4.0 * qc), qb));
+    double lambda = qc / q;
+    if (lambda < 0.0) lambda = q;
+    np[0] = nx + betap[0] * lambda; np[1] = ny + betap[1] * lambda; np[2] = nz + betap[2] * lambda;
+  } else {
+    betap[0] = ray.beta[0]; betap[1] = ray.beta[1]; betap[2] = ray.beta[2];
+    const double f = wp / wpm1;
+    np[0] = nx * f; np[1] = ny * f; np[2] = nz * f;
+  }
+#pragma unroll
+  for (int n = 0; n < 2; ++n)
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+      Ap[m + 2 * n] = pc.cprev * ray.Aprev[m + 2 * n] + pc.ccur * ray.A[m + 2 * n]
+                      - pc.cu * (ray.U[0 + 2 * n] * ray.A[m + 2 * 0] + ray.U[1 + 2 * n] * ray.A[m + 2 * 1]);
+  // transport A, Aprev from n to np; renormalise np to the shell radius
+  const double inv_np = 1.0 / sqrt(np[0] * np[0] + np[1] * np[1] + np[2] * np[2]);
+  const double v0[3] = {nx * inv_n, ny * inv_n, nz * inv_n}, v1[3] = {np[0] * inv_np, np[1] * inv_np, np[2] * inv_np};
+  const double inv_norm = 1.0 / sqrt((1.0 - v1[2]) * (1.0 + v1[2]) * (1.0 - v0[2]) * (1.0 + v0[2]));
+  double c, s;
+  paratrans_angle_unit(v0, v1, inv_norm, c, s);
+  {
+    const double T00 = ray.A[0], T01 = ray.A[1], T10 = ray.A[2], T11 = ray.A[3];
+    const double r00 = T00 * c + T01 * s, r01 = T01 * c - T00 * s, r10 = T10 * c + T11 * s, r11 = T11 * c - T10 * s;
+    ray.Aprev[0] = c * r00 + s * r10; ray.Aprev[1] = c * r01 + s * r11;
+    ray.Aprev[2] = c * r10 - s * r00; ray.Aprev[3] = c * r11 - s * r01;
+  }
+  {
+    const double T00 = Ap[0], T01 = Ap[1], T10 = Ap[2], T11 = Ap[3];
+    const double r00 = T00 * c + T01 * s, r01 = T01 * c - T00 * s, r10 = T10 * c + T11 * s, r11 = T11 * c - T10 * s;
+    ray.A[0] = c * r00 + s * r10; ray.A[1] = c * r01 + s * r11;
+    ray.A[2] = c * r10 - s * r00; ray.A[3] = c * r11 - s * r01;
+  }
+  const double rs = wp * inv_np;
+  ray.n[0] = np[0] * rs; ray.n[1] = np[1] * rs; ray.n[2] = np[2] * rs;
+  ray.beta[0] = betap[0]; ray.beta[1] = betap[1]; ray.beta[2] = betap[2];
+}
+#endif
+
 // rayprop_sphere of a -DBORNAPPRX build (rayprop.c:40-62): the ray moves radially to the next shell and the A recursion
 // uses U alone (no U A product, no deflection, no transport)
 CLB_HD void ray_propagate_born(Ray &ray, double wp, double wpm1, double wpm2)

@@ -66,7 +66,7 @@ __device__ __forceinline__ void ray_cp_async16(void *smem, const void *gmem)
 __global__ void __launch_bounds__(kRayThreads, 4)
 ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab *__restrict__ tab, long order, double wp,
                 double wpm1, double wpm2, int mode, const unsigned char *__restrict__ need, int coarse_shift,
-                unsigned rank_bit, int *__restrict__ err, double *__restrict__ sum6)
+                unsigned rank_bit, int *__restrict__ err, double *__restrict__ sum6, PlaneCoef pc)
 {
   __shared__ __align__(16) unsigned char s_raw[2][kRayThreads * sizeof(Ray)];
   __shared__ double s_sum[6][kRayThreads / 32];   // per-warp running sums of the plane summary (sum6 != nullptr)
@@ -114,7 +114,7 @@ ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab 
       }
       if (mode & 4) {
         if (mode & 8) ray_propagate_born(ray, wp, wpm1, wpm2);
-        else ray_propagate(ray, wp, wpm1, wpm2);
+        else ray_propagate_fast(ray, wp, wpm1, pc);
       }
       s_rays[threadIdx.x] = ray;
       if (sum6) {   // same six sums as ray_summary_kernel, without a second pass over the ray array
@@ -164,8 +164,13 @@ int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long 
   const RingTab *tab = (mode & 2) ? ring_table(order, st) : nullptr;
   if (d_sum6) CLB_CUDA_CHECK(cudaMemsetAsync(d_sum6, 0, 6 * sizeof(double), st));
   if (d_need && (coarse_order > order || !d_err)) d_need = nullptr;
+  // plane constants of the A recursion with the reference's expressions (rayprop.c:134-139), host double arithmetic
+  PlaneCoef pc;
+  pc.ccur = wpm1 * (wp - wpm2) / wp / (wpm1 - wpm2);
+  pc.cprev = 1.0 - wpm1 * (wp - wpm2) / wp / (wpm1 - wpm2);
+  pc.cu = (wp - wpm1) / wp;
   ray_step_kernel<<<(unsigned)nblocks, kRayThreads, 0, st>>>(d_rays, nrays, m, tab, order, wp, wpm1, wpm2, mode, d_need,
-                                                             (int)(2 * (order - coarse_order)), 1u << rank, d_err, d_sum6);
+                                                             (int)(2 * (order - coarse_order)), 1u << rank, d_err, d_sum6, pc);
   if (d_sum6) CLB_CUDA_CHECK(cudaGetLastError());
   CLB_CUDA_CHECK(cudaGetLastError());
   return 1;
