@@ -129,6 +129,10 @@ struct RingTab {      // one entry per ring 1 .. 4*Nside-1 (entry 0 unused)
   double cz, sz;      // cos/sin(theta) of the pixel centres as nest2ang+ang2vec give them [healpix_utils.c:133-141,700-748]
   double inv_sz;
   double cd, sd;      // cos/sin of the pixel spacing pi/2/nr
+  double dphi;        // 2 pi / ringpix exactly as get_interpol forms it           [healpix_utils.c:987,1002]
+  double inv_dphi;    // 1 / dphi (weights only; the pixel index keeps the reference's division)
+  double inv_dtheta;  // 1 / (theta(ring+1) - theta(ring)) (weights only)
+  double inv_ringpix; // 1 / ringpix (azimuth of pixel centres in units of pi)
 };
 
 // transport angle from unit vector v (with phi-hat numerator p = (-vy, vx, 0)) to unit vector r;
@@ -137,7 +141,13 @@ CLB_HD void paratrans_angle_unit(const double v[3], const double r[3], double in
 {
   const double ux = v[1] * r[2] - v[2] * r[1], uy = v[2] * r[0] - v[0] * r[2], uz = v[0] * r[1] - v[1] * r[0];
   const double c = v[0] * r[0] + v[1] * r[1] + v[2] * r[2];
-  const double up = (uy * v[0] - ux * v[1]) / (1.0 + c);
+  // 1/(1 + c): the two points are neighbours (c = 1 - eps, eps ~ 1e-8 .. 1e-3), so a short series in eps/2 replaces
+  // the division (truncation error (eps/2)^5); far-apart points take the division
+  const double eps = 1.0 - c;
+  double inv1c;
+  if (eps < 1e-2) { const double h = 0.5 * eps; inv1c = 0.5 * (1.0 + h * (1.0 + h * (1.0 + h * (1.0 + h)))); }
+  else inv1c = 1.0 / (1.0 + c);
+  const double up = (uy * v[0] - ux * v[1]) * inv1c;
   const double e0 = -c * v[1] - uz * v[0] + ux * up;
   const double e1 = c * v[0] - uz * v[1] + uy * up;
   const double e2 = (ux * v[0] + uy * v[1]) + uz * up;
@@ -162,10 +172,10 @@ __device__ __forceinline__ void get_interpol_tab(double theta, double phi, long 
   if (ir1 > 0) {
     RingInfo ri = ring_info(ir1, order);
     theta1 = tab[ir1].theta;
-    dphi = 2.0 * CLB_PI / ri.ringpix;
-    tmp = (phi / dphi - .5 * ri.shifted);
+    dphi = tab[ir1].dphi;
+    tmp = (phi / dphi - .5 * ri.shifted);                          // index: the reference's division, bit for bit
     i1 = (tmp < 0) ? ((long)(tmp)) - 1 : (long)(tmp);
-    w1 = (phi - (i1 + .5 * ri.shifted) * dphi) / dphi;
+    w1 = (phi - (i1 + .5 * ri.shifted) * dphi) * tab[ir1].inv_dphi;   // weight: reciprocal (differs by <= 1 ulp)
     i2 = i1 + 1;
     if (i1 < 0) i1 += ri.ringpix;
     if (i2 >= ri.ringpix) i2 -= ri.ringpix;
@@ -175,10 +185,10 @@ __device__ __forceinline__ void get_interpol_tab(double theta, double phi, long 
   if (ir2 < (4 * nside)) {
     RingInfo ri = ring_info(ir2, order);
     theta2 = tab[ir2].theta;
-    dphi = 2.0 * CLB_PI / ri.ringpix;
+    dphi = tab[ir2].dphi;
     tmp = (phi / dphi - .5 * ri.shifted);
     i1 = (tmp < 0) ? ((long)(tmp)) - 1 : (long)(tmp);
-    w1 = (phi - (i1 + .5 * ri.shifted) * dphi) / dphi;
+    w1 = (phi - (i1 + .5 * ri.shifted) * dphi) * tab[ir2].inv_dphi;
     i2 = i1 + 1;
     if (i1 < 0) i1 += ri.ringpix;
     if (i2 >= ri.ringpix) i2 -= ri.ringpix;
@@ -203,7 +213,7 @@ __device__ __forceinline__ void get_interpol_tab(double theta, double phi, long 
     pix[3] = ((pix[1] + 2) & 3) + npix - 4;
     ringB = 4 * nside - 1;
   } else {
-    double wtheta = (theta - theta1) / (theta2 - theta1);
+    double wtheta = (theta - theta1) * tab[ir1].inv_dtheta;
     wgt[0] *= (1 - wtheta); wgt[1] *= (1 - wtheta);
     wgt[2] *= wtheta; wgt[3] *= wtheta;
   }
@@ -234,7 +244,7 @@ __device__ __forceinline__ long ray_interp_accumulate_fast(Ray &ray, long order,
   // ray-side quantities shared by the four transports
   const double inv_r = 1.0 / sqrt(ray.n[0] * ray.n[0] + ray.n[1] * ray.n[1] + ray.n[2] * ray.n[2]);
   const double rv[3] = {ray.n[0] * inv_r, ray.n[1] * inv_r, ray.n[2] * inv_r};
-  const double inv_sr = 1.0 / sqrt((1.0 - rv[2]) * (1.0 + rv[2]));
+  const double inv_sr = rsqrt((1.0 - rv[2]) * (1.0 + rv[2]));
   double pc[4], ps[4];   // transport angles of the four stencil pixels
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -244,7 +254,7 @@ __device__ __forceinline__ long ray_interp_accumulate_fast(Ray &ray, long order,
     // (modulo the ring), i.e. a rotation by the tabulated (cd, sd)
     const long j0 = pix[2 * h] - ri.startpix;
     double s0, c0;
-    sincospi((double)(2 * j0 + ri.shifted) / (double)ri.ringpix, &s0, &c0);
+    sincospi((double)(2 * j0 + ri.shifted) * rt.inv_ringpix, &s0, &c0);
     const double c1 = c0 * rt.cd - s0 * rt.sd, s1 = s0 * rt.cd + c0 * rt.sd;
     const double inv_norm = rt.inv_sz * inv_sr;
     const double va[3] = {rt.sz * c0, rt.sz * s0, rt.cz}, vb[3] = {rt.sz * c1, rt.sz * s1, rt.cz};
@@ -287,11 +297,11 @@ __device__ __forceinline__ void ray_propagate_fast(Ray &ray, double wp, double w
   const double nx = ray.n[0], ny = ray.n[1], nz = ray.n[2];
   const double nxy2 = nx * nx + ny * ny;
   const double n2 = nxy2 + nz * nz;
-  const double inv_n = 1.0 / sqrt(n2);
+  const double inv_n = rsqrt(n2);
   const double alpha2 = ray.alpha[0] * ray.alpha[0] + ray.alpha[1] * ray.alpha[1];
   if (alpha2 > 0.0) {
     const double alpha = sqrt(alpha2);
-    const double inv_nxy = 1.0 / sqrt(nxy2);
+    const double inv_nxy = rsqrt(nxy2);
     // a = alpha_theta theta-hat + alpha_phi phi-hat (unit vectors at n)
     const double ct = ray.alpha[0] * inv_nxy * inv_n, cp = ray.alpha[1] * inv_nxy;
     const double a0 = ct * (nz * nx) - cp * ny;
@@ -326,9 +336,9 @@ __device__ __forceinline__ void ray_propagate_fast(Ray &ray, double wp, double w
       Ap[m + 2 * n] = pc.cprev * ray.Aprev[m + 2 * n] + pc.ccur * ray.A[m + 2 * n]
                       - pc.cu * (ray.U[0 + 2 * n] * ray.A[m + 2 * 0] + ray.U[1 + 2 * n] * ray.A[m + 2 * 1]);
   // transport A, Aprev from n to np; renormalise np to the shell radius
-  const double inv_np = 1.0 / sqrt(np[0] * np[0] + np[1] * np[1] + np[2] * np[2]);
+  const double inv_np = rsqrt(np[0] * np[0] + np[1] * np[1] + np[2] * np[2]);
   const double v0[3] = {nx * inv_n, ny * inv_n, nz * inv_n}, v1[3] = {np[0] * inv_np, np[1] * inv_np, np[2] * inv_np};
-  const double inv_norm = 1.0 / sqrt((1.0 - v1[2]) * (1.0 + v1[2]) * (1.0 - v0[2]) * (1.0 + v0[2]));
+  const double inv_norm = rsqrt((1.0 - v1[2]) * (1.0 + v1[2]) * (1.0 - v0[2]) * (1.0 + v0[2]));
   double c, s;
   paratrans_angle_unit(v0, v1, inv_norm, c, s);
   {

@@ -32,6 +32,14 @@ __global__ void ring_table_kernel(RingTab *__restrict__ tab, long order)
   t.inv_sz = 1.0 / t.sz;
   const double dphi = CLB_PI_2 / (double)(ri.ringpix / 4);
   t.cd = cos(dphi); t.sd = sin(dphi);
+  t.dphi = 2.0 * CLB_PI / ri.ringpix;
+  t.inv_dphi = 1.0 / t.dphi;
+  t.inv_ringpix = 1.0 / (double)ri.ringpix;
+  t.inv_dtheta = 0.0;
+  if (ring < 4 * nside - 1) {
+    const RingInfo rn = ring_info(ring + 1, order);
+    t.inv_dtheta = 1.0 / (atan2(rn.sintheta, rn.costheta) - t.theta);
+  }
   tab[ring] = t;
 }
 
