@@ -139,8 +139,10 @@ struct RingTab {      // one entry per ring 1 .. 4*Nside-1 (entry 0 unused)
 // inv_norm = 1 / (sin(theta_v) sin(theta_r))
 CLB_HD void paratrans_angle_unit(const double v[3], const double r[3], double inv_norm, double &cospsi, double &sinpsi)
 {
-  const double ux = v[1] * r[2] - v[2] * r[1], uy = v[2] * r[0] - v[0] * r[2], uz = v[0] * r[1] - v[1] * r[0];
-  const double c = v[0] * r[0] + v[1] * r[1] + v[2] * r[2];
+  // (this translation unit is built with -fmad=false for the bit-exact index arithmetic; the transport math, which has
+  // no such requirement, asks for its fused multiply-adds explicitly)
+  const double ux = fma(v[1], r[2], -(v[2] * r[1])), uy = fma(v[2], r[0], -(v[0] * r[2])), uz = fma(v[0], r[1], -(v[1] * r[0]));
+  const double c = fma(v[0], r[0], fma(v[1], r[1], v[2] * r[2]));
   // 1/(1 + c): the two points are neighbours (c = 1 - eps, eps ~ 1e-8 .. 1e-3), so a short series in eps/2 replaces
   // the division (truncation error (eps/2)^5); far-apart points take the division
   const double eps = 1.0 - c;
@@ -148,12 +150,12 @@ CLB_HD void paratrans_angle_unit(const double v[3], const double r[3], double in
   if (eps < 1e-2) { const double h = 0.5 * eps; inv1c = 0.5 * (1.0 + h * (1.0 + h * (1.0 + h * (1.0 + h)))); }
   else inv1c = 1.0 / (1.0 + c);
   const double up = (uy * v[0] - ux * v[1]) * inv1c;
-  const double e0 = -c * v[1] - uz * v[0] + ux * up;
-  const double e1 = c * v[0] - uz * v[1] + uy * up;
-  const double e2 = (ux * v[0] + uy * v[1]) + uz * up;
-  const double rxy2 = r[0] * r[0] + r[1] * r[1];
-  sinpsi = (r[2] * (e0 * r[0] + e1 * r[1]) - e2 * rxy2) * inv_norm;
-  cospsi = (e1 * r[0] - e0 * r[1]) * inv_norm;
+  const double e0 = fma(ux, up, -fma(c, v[1], uz * v[0]));
+  const double e1 = fma(uy, up, fma(c, v[0], -(uz * v[1])));
+  const double e2 = fma(uz, up, fma(ux, v[0], uy * v[1]));
+  const double rxy2 = fma(r[0], r[0], r[1] * r[1]);
+  sinpsi = fma(r[2], fma(e0, r[0], e1 * r[1]), -(e2 * rxy2)) * inv_norm;
+  cospsi = fma(e1, r[0], -(e0 * r[1])) * inv_norm;
 }
 
 #if defined(__CUDACC__)
@@ -265,16 +267,16 @@ __device__ __forceinline__ long ray_interp_accumulate_fast(Ray &ray, long order,
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const double w = wgt[k], c = pc[k], s = ps[k];
-    pot += f_phi[k] * w;
+    pot = fma((double)f_phi[k], w, pot);
     const double tv0 = f_gt[k], tv1 = f_gp[k];
-    gtheta += (tv0 * c + tv1 * s) * w;
-    gphi += (tv1 * c - tv0 * s) * w;
+    gtheta = fma(fma(tv0, c, tv1 * s), w, gtheta);
+    gphi = fma(fma(tv1, c, -(tv0 * s)), w, gphi);
     const double T00 = f_gtt[k], T01 = f_gtp[k], T11 = f_gpp[k];
     // R^T T R with R = [[c, -s], [s, c]], T symmetric                       [rot_paratrans.c:251-270]
-    const double a0 = T00 * c + T01 * s, a1 = T01 * c - T00 * s;   // row 0 of T R
-    const double b0 = T01 * c + T11 * s, b1 = T11 * c - T01 * s;   // row 1 of T R
-    t00 += (c * a0 + s * b0) * w; t01 += (c * a1 + s * b1) * w;
-    t10 += (c * b0 - s * a0) * w; t11 += (c * b1 - s * a1) * w;
+    const double a0 = fma(T00, c, T01 * s), a1 = fma(T01, c, -(T00 * s));   // row 0 of T R
+    const double b0 = fma(T01, c, T11 * s), b1 = fma(T11, c, -(T01 * s));   // row 1 of T R
+    t00 = fma(fma(c, a0, s * b0), w, t00); t01 = fma(fma(c, a1, s * b1), w, t01);
+    t10 = fma(fma(c, b0, -(s * a0)), w, t10); t11 = fma(fma(c, b1, -(s * a1)), w, t11);
   }
   ray.phi = pot;
   ray.alpha[0] += -1.0 * gtheta;
@@ -304,26 +306,26 @@ __device__ __forceinline__ void ray_propagate_fast(Ray &ray, double wp, double w
     const double inv_nxy = rsqrt(nxy2);
     // a = alpha_theta theta-hat + alpha_phi phi-hat (unit vectors at n)
     const double ct = ray.alpha[0] * inv_nxy * inv_n, cp = ray.alpha[1] * inv_nxy;
-    const double a0 = ct * (nz * nx) - cp * ny;
-    const double a1 = ct * (nz * ny) + cp * nx;
+    const double a0 = fma(ct, nz * nx, -(cp * ny));
+    const double a1 = fma(ct, nz * ny, cp * nx);
     const double a2 = -ct * nxy2;
     // unit rotation axis k = (n x a) / (|n| alpha)
     const double ik = inv_n / alpha;
-    const double k0 = (ny * a2 - nz * a1) * ik, k1 = (nz * a0 - nx * a2) * ik, k2 = (nx * a1 - ny * a0) * ik;
+    const double k0 = fma(ny, a2, -(nz * a1)) * ik, k1 = fma(nz, a0, -(nx * a2)) * ik, k2 = fma(nx, a1, -(ny * a0)) * ik;
     double sn, cs;
     sincos(alpha, &sn, &cs);
     const double omc = 1.0 - cs;
     // Rodrigues: beta' = beta cos + (k x beta) sin + k (k . beta)(1 - cos)     [rot_paratrans.c:17-45]
-    const double kb = (k0 * ray.beta[0] + k1 * ray.beta[1] + k2 * ray.beta[2]) * omc;
-    betap[0] = ray.beta[0] * cs + (k1 * ray.beta[2] - k2 * ray.beta[1]) * sn + k0 * kb;
-    betap[1] = ray.beta[1] * cs + (k2 * ray.beta[0] - k0 * ray.beta[2]) * sn + k1 * kb;
-    betap[2] = ray.beta[2] * cs + (k0 * ray.beta[1] - k1 * ray.beta[0]) * sn + k2 * kb;
-    const double qb = 2.0 * (nx * betap[0] + ny * betap[1] + nz * betap[2]);
+    const double kb = fma(k0, ray.beta[0], fma(k1, ray.beta[1], k2 * ray.beta[2])) * omc;
+    betap[0] = fma(ray.beta[0], cs, fma(fma(k1, ray.beta[2], -(k2 * ray.beta[1])), sn, k0 * kb));
+    betap[1] = fma(ray.beta[1], cs, fma(fma(k2, ray.beta[0], -(k0 * ray.beta[2])), sn, k1 * kb));
+    betap[2] = fma(ray.beta[2], cs, fma(fma(k0, ray.beta[1], -(k1 * ray.beta[0])), sn, k2 * kb));
+    const double qb = 2.0 * fma(nx, betap[0], fma(ny, betap[1], nz * betap[2]));
     const double qc = wpm1 * wpm1 - wp * wp;
-    const double q = -0.5 * (qb + copysign(sqrt(qb * qb - 4.0 * qc), qb));
+    const double q = -0.5 * (qb + copysign(sqrt(fma(qb, qb, -4.0 * qc)), qb));
     double lambda = qc / q;
     if (lambda < 0.0) lambda = q;
-    np[0] = nx + betap[0] * lambda; np[1] = ny + betap[1] * lambda; np[2] = nz + betap[2] * lambda;
+    np[0] = fma(betap[0], lambda, nx); np[1] = fma(betap[1], lambda, ny); np[2] = fma(betap[2], lambda, nz);
   } else {
     betap[0] = ray.beta[0]; betap[1] = ray.beta[1]; betap[2] = ray.beta[2];
     const double f = wp / wpm1;
@@ -333,8 +335,8 @@ __device__ __forceinline__ void ray_propagate_fast(Ray &ray, double wp, double w
   for (int n = 0; n < 2; ++n)
 #pragma unroll
     for (int m = 0; m < 2; ++m)
-      Ap[m + 2 * n] = pc.cprev * ray.Aprev[m + 2 * n] + pc.ccur * ray.A[m + 2 * n]
-                      - pc.cu * (ray.U[0 + 2 * n] * ray.A[m + 2 * 0] + ray.U[1 + 2 * n] * ray.A[m + 2 * 1]);
+      Ap[m + 2 * n] = fma(pc.cprev, ray.Aprev[m + 2 * n], fma(pc.ccur, ray.A[m + 2 * n],
+                          -(pc.cu * fma(ray.U[0 + 2 * n], ray.A[m + 2 * 0], ray.U[1 + 2 * n] * ray.A[m + 2 * 1]))));
   // transport A, Aprev from n to np; renormalise np to the shell radius
   const double inv_np = rsqrt(np[0] * np[0] + np[1] * np[1] + np[2] * np[2]);
   const double v0[3] = {nx * inv_n, ny * inv_n, nz * inv_n}, v1[3] = {np[0] * inv_np, np[1] * inv_np, np[2] * inv_np};
@@ -343,15 +345,15 @@ __device__ __forceinline__ void ray_propagate_fast(Ray &ray, double wp, double w
   paratrans_angle_unit(v0, v1, inv_norm, c, s);
   {
     const double T00 = ray.A[0], T01 = ray.A[1], T10 = ray.A[2], T11 = ray.A[3];
-    const double r00 = T00 * c + T01 * s, r01 = T01 * c - T00 * s, r10 = T10 * c + T11 * s, r11 = T11 * c - T10 * s;
-    ray.Aprev[0] = c * r00 + s * r10; ray.Aprev[1] = c * r01 + s * r11;
-    ray.Aprev[2] = c * r10 - s * r00; ray.Aprev[3] = c * r11 - s * r01;
+    const double r00 = fma(T00, c, T01 * s), r01 = fma(T01, c, -(T00 * s)), r10 = fma(T10, c, T11 * s), r11 = fma(T11, c, -(T10 * s));
+    ray.Aprev[0] = fma(c, r00, s * r10); ray.Aprev[1] = fma(c, r01, s * r11);
+    ray.Aprev[2] = fma(c, r10, -(s * r00)); ray.Aprev[3] = fma(c, r11, -(s * r01));
   }
   {
     const double T00 = Ap[0], T01 = Ap[1], T10 = Ap[2], T11 = Ap[3];
-    const double r00 = T00 * c + T01 * s, r01 = T01 * c - T00 * s, r10 = T10 * c + T11 * s, r11 = T11 * c - T10 * s;
-    ray.A[0] = c * r00 + s * r10; ray.A[1] = c * r01 + s * r11;
-    ray.A[2] = c * r10 - s * r00; ray.A[3] = c * r11 - s * r01;
+    const double r00 = fma(T00, c, T01 * s), r01 = fma(T01, c, -(T00 * s)), r10 = fma(T10, c, T11 * s), r11 = fma(T11, c, -(T10 * s));
+    ray.A[0] = fma(c, r00, s * r10); ray.A[1] = fma(c, r01, s * r11);
+    ray.A[2] = fma(c, r10, -(s * r00)); ray.A[3] = fma(c, r11, -(s * r01));
   }
   const double rs = wp * inv_np;
   ray.n[0] = np[0] * rs; ray.n[1] = np[1] * rs; ray.n[2] = np[2] * rs;
