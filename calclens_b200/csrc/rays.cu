@@ -109,7 +109,7 @@ ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab 
     Ray *s_rays = reinterpret_cast<Ray *>(s_raw[buf]);
     double ps[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (threadIdx.x < nblk) {
-      Ray ray = s_rays[threadIdx.x];
+      Ray &ray = s_rays[threadIdx.x];   // operate on the staged record in place: fields are read where they are used
       if (mode & 1) {
         ray.phi = 0.0; ray.alpha[0] = 0.0; ray.alpha[1] = 0.0;
         ray.U[0] = 0.0; ray.U[1] = 0.0; ray.U[2] = 0.0; ray.U[3] = 0.0;
@@ -124,7 +124,6 @@ ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab 
         if (mode & 8) ray_propagate_born(ray, wp, wpm1, wpm2);
         else ray_propagate_fast(ray, wp, wpm1, pc);
       }
-      s_rays[threadIdx.x] = ray;
       if (sum6) {   // same six sums as ray_summary_kernel, without a second pass over the ray array
         ps[0] = 1.0 - 0.5 * (ray.A[0] + ray.A[3]);
         ps[1] = 0.5 * (ray.A[3] - ray.A[0]);
