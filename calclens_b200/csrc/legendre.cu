@@ -332,6 +332,7 @@ legendre_synthesis_kernel(const double *__restrict__ coef, const long *__restric
     // destination: this rank's send buffer, or (fused exchange) the ring owner's receive buffer over NVLink
     double2 *o = (rp_bptr ? rp_bptr[rp] : b_send + b_off[rp]) + (long)mi * 6 * b_stride[rp];
     const long fs = b_stride[rp];
+    double2 q[6][2];   // [field][hemisphere]
 #pragma unroll
     for (int hemi = 0; hemi < 2; ++hemi) {
       const double sg = hemi ? -1.0 : 1.0;
@@ -340,13 +341,19 @@ legendre_synthesis_kernel(const double *__restrict__ coef, const long *__restric
       const double Kr = acc[j][4] + sg * acc[j][10], Ki = acc[j][5] + sg * acc[j][11];
       const double q1r = Dr * isth, q1i = Di * isth;
       const double q3r = -sg * cot * q1r - Kr + m2s2 * Pr, q3i = -sg * cot * q1i - Ki + m2s2 * Pi;
-      o[0 * fs + hemi] = make_double2(Pr, Pi);                       // phi
-      o[1 * fs + hemi] = make_double2(q1r, q1i);                     // d_theta
-      o[2 * fs + hemi] = make_double2(-dm * Pi, dm * Pr);            // i m P          (still to be divided by sin)
-      o[3 * fs + hemi] = make_double2(q3r, q3i);                     // d_theta^2
-      o[4 * fs + hemi] = make_double2(-dm * q1i, dm * q1r);          // i m d_theta    (.. / sin)
-      o[5 * fs + hemi] = make_double2(-m2 * Pr, -m2 * Pi);           // -m^2 P         (.. / sin^2)
+      q[0][hemi] = make_double2(Pr, Pi);                       // phi
+      q[1][hemi] = make_double2(q1r, q1i);                     // d_theta
+      q[2][hemi] = make_double2(-dm * Pi, dm * Pr);            // i m P          (still to be divided by sin)
+      q[3][hemi] = make_double2(q3r, q3i);                     // d_theta^2
+      q[4][hemi] = make_double2(-dm * q1i, dm * q1r);          // i m d_theta    (.. / sin)
+      q[5][hemi] = make_double2(-m2 * Pr, -m2 * Pi);           // -m^2 P         (.. / sin^2)
     }
+    // the (north, south) pair of a field is 32 contiguous, 32-byte aligned bytes: one 256-bit store each (full sectors
+    // on the local path, full packets over NVLink)
+#pragma unroll
+    for (int f = 0; f < 6; ++f)
+      asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(o + f * fs), "d"(q[f][0].x), "d"(q[f][0].y),
+                   "d"(q[f][1].x), "d"(q[f][1].y) : "memory");
   }
 }
 
