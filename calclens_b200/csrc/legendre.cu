@@ -5,10 +5,13 @@
 //   synthesis : the six ring-space fields phi, d_theta, d_phi, d_theta^2, d_theta d_phi, d_phi^2 per (m, ring)
 //               [alm2allmaps_transpose_mpi.c:272-595]
 //
-// Both kernels put one ring pair (north ring + its southern mirror, combined through the parity of l+m) on a
-// thread and walk l with the two-instruction scaled recurrence mu_{l+1} = (x A_l) mu_l - mu_{l-1} (sht_plan.cu),
-// started from the precomputed per-(m, ring) seeds, so no work is spent below the degree where lambda reaches
-// 1e-30.  All threads of a CTA share m, so recurrence coefficients and alm-derived coefficients are block-uniform.
+// Both kernels put R ring pairs (north ring + its southern mirror, combined through the parity of l+m) on a thread,
+// keep their whole state in registers and walk l with the two-instruction scaled recurrence
+// mu_{l+1} = (x A_l) mu_l - mu_{l-1} (sht_plan.cu), started from the precomputed per-(m, ring) seeds, so no work is
+// spent below the degree where lambda reaches 1e-30.  A warp owns 32*R adjacent ring pairs of one m and runs on its
+// own (no block barrier in the l loop); recurrence coefficients and alm-derived coefficients are warp-uniform and reach
+// the threads as broadcast reads of a private cp.async tile.  What this instruction mix can reach on the FP64 pipe is
+// measured by tools/fp64_probe.cu.
 //
 // Synthesis uses three complex sums instead of the reference's per-l derivative formulas:
 //   P = sum a_l lambda_l,  K = sum l(l+1) a_l lambda_l,
@@ -28,7 +31,7 @@ static_assert(kLB == kSeedAlign, "l-blocks must line up with the seed alignment"
 
 // Ring pairs are dealt in contiguous runs: warp W of the grid row owns the 32*R adjacent ring pairs starting at
 // W*32*R, thread `lane` of it the pairs W*32*R + j*32 + lane (j < R).  Adjacent rings reach |lambda| > 1e-30 at almost
-// the same degree, so one start degree per warp (analysis: per CTA) wastes ~1 % of the work and the whole warp runs
+// the same degree, so one start degree per warp wastes ~1 % of the work and the whole warp runs
 // branch-free: rings that start later carry mu = 0 until their seed is injected at their own (16-aligned) start.
 
 constexpr int kAnaTile = 32;      // degrees of recurrence coefficients per shared-memory tile of the analysis kernel

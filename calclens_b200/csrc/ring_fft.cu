@@ -1,6 +1,6 @@
 // calclens_b200/csrc/ring_fft.cu
-// Batched HEALPix ring FFTs for sm_100a: one CTA per ring, everything between the HBM read and the HBM write stays
-// in shared memory.  Replaces the per-ring FFTW calls and the pack/unpack loops of the reference:
+// Batched HEALPix ring FFTs for sm_100a: one CTA per ring (and field), everything between the HBM read and the HBM
+// write stays in shared memory.  Replaces the per-ring FFTW calls and the pack/unpack loops of the reference:
 //   analysis : ring weights, r2c, alias pick + conjugate, half-pixel phase, write g_m
 //              [map2alm_transpose_mpi.c:151-191 (weights + ring_analysis), :219-315 (pack); healpix_shtrans.c:549-571]
 //   synthesis: alias fold of b_m into float half-complex bins, half-pixel phase, c2r, 1/sin(theta) scalings,
@@ -15,9 +15,12 @@
 // arithmetic (__dmul_rn/__dadd_rn) so that results agree to the last float bit except for FP64-level noise.
 //
 // Algorithm: a real ring has n = 4r pixels.  Radix-4 split into four real length-r sequences, packed pairwise
-// into two complex length-r DFTs.  DFT_r: r a power of two -> in-place radix-4 DIF (bit-reversed read-out);
-// otherwise Bluestein with M = pow2 >= 2r-1: DIF forward, product with a precomputed bit-reversed chirp spectrum,
-// DIT inverse (no bit reversal anywhere).  (Index math prototyped in tools/fft_proto.py.)
+// into two complex length-r DFTs.  DFT_r: r a power of two -> in-place DIF (bit-reversed read-out), both transforms
+// of a ring batched in the same passes; otherwise Bluestein with M = pow2 >= 2r-1: DIF forward, product with a
+// precomputed bit-reversed chirp spectrum, DIT inverse (no bit reversal anywhere).  Passes are radix 16 in registers
+// over XOR-swizzled shared memory; half-pixel phase factors come from plan-time tables.  Rings too long for shared
+// memory (r > 4095) run the same code from an L2-resident global scratch slice.  (Index math prototyped in
+// tools/fft_proto.py.)
 #include "sht_internal.cuh"
 #include "healpix.cuh"
 #include <algorithm>
