@@ -209,6 +209,34 @@ __global__ void __launch_bounds__(128, NB) ana_pipe_k(double *out, int iters, do
   out[blockIdx.x * blockDim.x + threadIdx.x] = tot + mc[0] + mc[R - 1];
 }
 
+// FP64 tensor-core probe: mma.sync m8n8k4 f64 (DMMA) alone, and interleaved with independent DFMA chains in the same
+// warps, to see whether the two share the SM's FP64 datapath (BASELINE north_star: "DMMA only if it pays").
+template <int NMMA, int NFMA>
+__global__ void dmma_k(double *out, int iters, double a0)
+{
+  double c0[NMMA > 0 ? NMMA : 1][2];
+  double v[NFMA > 0 ? NFMA : 1];
+  const double a = 1.0 + 1e-9 * threadIdx.x + a0, b = 1.0 - 1e-9 * threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < (NMMA > 0 ? NMMA : 1); ++i) { c0[i][0] = i; c0[i][1] = -i; }
+#pragma unroll
+  for (int i = 0; i < (NFMA > 0 ? NFMA : 1); ++i) v[i] = threadIdx.x * 1e-3 + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < NMMA; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c0[i][0]), "+d"(c0[i][1]) : "d"(a), "d"(b));
+#pragma unroll
+    for (int i = 0; i < NFMA; ++i) v[i] = fma(v[i], 1.0000001, 1e-9);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < (NMMA > 0 ? NMMA : 1); ++i) s += c0[i][0] + c0[i][1];
+#pragma unroll
+  for (int i = 0; i < (NFMA > 0 ? NFMA : 1); ++i) s += v[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 static float timeit(F f)
 {
@@ -305,6 +333,21 @@ int main()
       ms = timeit([&] { ana_k<8, 8, 1, 4><<<ctas4, 128>>>(out, it3, 1e-9); }); printf(" %6.2f", 8.0 * 8 * 8 * it3 * ctas4 * 128 / ms * 1e-9);
       ms = timeit([&] { ana_k<8, 8, 2, 4><<<ctas4, 128>>>(out, it3, 1e-9); }); printf(" %6.2f\n", 8.0 * 8 * 8 * it3 * ctas4 * 128 / ms * 1e-9);
     }
+  }
+  {
+    printf("FP64 tensor (mma.m8n8k4.f64) vs FMA pipe, 16 warps/SM; TFLOP/s counted as 2*8*8*4 per warp MMA and 2*32 per warp FMA\n");
+    const int itd = 1 << 14; float ms;
+    const double wm = (double)sms * 4 * 4;   // warps in flight: 4 CTAs/SM x 4 warps
+    ms = timeit([&] { dmma_k<8, 0><<<sms * 4, 128>>>(out, itd, 1e-9); });
+    printf("DMMA only (8 independent accumulators): %6.2f\n", 8.0 * 512 * itd * wm / ms * 1e-9);
+    ms = timeit([&] { dmma_k<0, 8><<<sms * 4, 128>>>(out, itd, 1e-9); });
+    printf("DFMA only (8 chains):                   %6.2f\n", 8.0 * 64 * itd * wm / ms * 1e-9);
+    ms = timeit([&] { dmma_k<8, 8><<<sms * 4, 128>>>(out, itd, 1e-9); });
+    printf("DMMA + DFMA interleaved (8 + 8):        %6.2f total (%6.2f DMMA + %6.2f DFMA)\n",
+           (8.0 * 512 + 8.0 * 64) * itd * wm / ms * 1e-9, 8.0 * 512 * itd * wm / ms * 1e-9, 8.0 * 64 * itd * wm / ms * 1e-9);
+    ms = timeit([&] { dmma_k<2, 16><<<sms * 4, 128>>>(out, itd, 1e-9); });
+    printf("DMMA + DFMA interleaved (2 + 16):       %6.2f total (%6.2f DMMA + %6.2f DFMA)\n",
+           (2.0 * 512 + 16.0 * 64) * itd * wm / ms * 1e-9, 2.0 * 512 * itd * wm / ms * 1e-9, 16.0 * 64 * itd * wm / ms * 1e-9);
   }
   cudaError_t e = cudaDeviceSynchronize();
   printf("status %s\n", cudaGetErrorString(e));
