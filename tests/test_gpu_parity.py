@@ -658,3 +658,40 @@ def test_point_mass_plane_baseline_config0(clb, oracle):
     ratio = amp[sel] / (S / (4 * np.pi) / np.tan(d[sel] / 2))
     assert 0.97 < np.median(ratio) < 1.03, np.median(ratio)
     assert np.allclose(rg["alpha"], alpha_before_prop, rtol=0, atol=1e-8 * np.abs(alpha_before_prop).max())
+
+
+@pytest.mark.parametrize("order,lmax", [(5, 77), (6, 191), (3, 9)])
+def test_stage_outputs_stay_inside_their_buffers(clb, order, lmax):
+    """Every stage writes exactly its output buffer: canaries on both sides of g, alm, b and the maps must survive, and
+    no output element may be left unwritten (ragged lmax: partial degree blocks and coefficient tiles)."""
+    import torch
+    from calclens_b200 import _lib
+    L = _lib.load()
+    npix = 12 << (2 * order)
+    plan = clb.HEALPixSHTPlan(order, lmax)
+    pad = 4096
+    rng = np.random.default_rng(7)
+
+    def guarded(n, dtype, fill=float("nan")):
+        t = torch.full((n + 2 * pad,), -12345.0, dtype=dtype, device="cuda")
+        t[pad:pad + n] = fill
+        return t, t[pad:pad + n]
+
+    def check(t, n, what):
+        assert bool((t[:pad] == -12345.0).all()) and bool((t[pad + n:] == -12345.0).all()), "%s: write outside the buffer" % what
+        assert not bool(torch.isnan(t[pad:pad + n]).any()), "%s: element left unwritten" % what
+
+    dm = torch.from_numpy(rng.normal(size=npix).astype(np.float32)).cuda()
+    g_all, g = guarded(2 * plan.g_send_total, torch.float64)
+    are_all, are = guarded(plan.Nlm, torch.float64)
+    aim_all, aim = guarded(plan.Nlm, torch.float64)
+    b_all, b = guarded(2 * plan.b_send_total, torch.float64)
+    maps_all, maps = guarded(6 * npix, torch.float32)
+    plan.ring_analysis(dm, g)
+    plan.legendre_analysis(g, are, aim, poisson_filter=True)
+    plan.legendre_synthesis(are, aim, b)
+    plan.ring_synthesis(b, maps.view(6, npix))
+    torch.cuda.synchronize()
+    check(g_all, 2 * plan.g_send_total, "g"); check(are_all, plan.Nlm, "alm_re"); check(aim_all, plan.Nlm, "alm_im")
+    check(b_all, 2 * plan.b_send_total, "b"); check(maps_all, 6 * npix, "maps")
+    plan.destroy()
