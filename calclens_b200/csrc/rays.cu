@@ -12,7 +12,7 @@
 namespace clb {
 
 constexpr int kRayThreads = 128;
-constexpr int kRayWords = sizeof(Ray) / 16;   // 11 x 16 bytes per ray
+
 static_assert(sizeof(Ray) % 16 == 0, "ray struct must be a multiple of 16 bytes");
 
 struct RayMaps { const float *p[6]; };
@@ -60,23 +60,52 @@ static const RingTab *ring_table(long order, cudaStream_t st)
   return cache[dev][order];
 }
 
-__device__ __forceinline__ void ray_cp_async16(void *smem, const void *gmem)
+// ---- TMA (bulk async copy) helpers: one thread moves a whole tile of ray records between HBM and shared memory ----
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
 {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_src, unsigned bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_addr(smem_src)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
 // mode bit 0: zero phi/alpha/U first (the driver's pre-solve reset, raytrace.c:213-230)
 // mode bit 1: interpolate + accumulate;  mode bit 2: propagate;  mode bit 3 (with bit 2): Born-approximation propagate
-// Persistent CTAs walk the ray array in tiles of kRayThreads records; the next tile streams into the second
-// shared-memory buffer (cp.async) while the current one is being computed, and results leave through coalesced
-// 16-byte stores.
+// Persistent CTAs walk the ray array in tiles of kRayThreads records (22.5 KB, contiguous).  Tiles move by TMA bulk
+// copies issued by one thread: the next tile streams into the second shared-memory buffer (completion on an mbarrier)
+// while the current one is being computed in place, and a finished tile leaves as one bulk store.
 __global__ void __launch_bounds__(kRayThreads, 4)
 ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab *__restrict__ tab, long order, double wp,
                 double wpm1, double wpm2, int mode, const unsigned char *__restrict__ need, int coarse_shift,
                 unsigned rank_bit, int *__restrict__ err, double *__restrict__ sum6, PlaneCoef pc)
 {
-  __shared__ __align__(16) unsigned char s_raw[2][kRayThreads * sizeof(Ray)];
+  __shared__ __align__(128) unsigned char s_raw[2][kRayThreads * sizeof(Ray)];
+  __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ double s_sum[6][kRayThreads / 32];   // per-warp running sums of the plane summary (sum6 != nullptr)
   if (sum6 && (threadIdx.x & 31) == 0) {
 #pragma unroll
@@ -85,25 +114,28 @@ ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab 
   const long ntiles = (nrays + kRayThreads - 1) / kRayThreads;
   long tile = blockIdx.x;
   if (tile >= ntiles) return;
-  auto prefetch = [&](long t, int b) {
-    const long first = t * kRayThreads;
-    const int nblk = (int)min((long)kRayThreads, nrays - first);
-    const int4 *src = reinterpret_cast<const int4 *>(rays + first);
-    int4 *dst = reinterpret_cast<int4 *>(s_raw[b]);
-    for (int i = threadIdx.x; i < nblk * kRayWords; i += kRayThreads) ray_cp_async16(dst + i, src + i);
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-  };
-  prefetch(tile, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto tile_bytes = [&](long t) { return (unsigned)(min((long)kRayThreads, nrays - t * kRayThreads) * (long)sizeof(Ray)); };
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&s_bar[0], tile_bytes(tile));
+    tma_load_1d(s_raw[0], rays + tile * kRayThreads, tile_bytes(tile), &s_bar[0]);
+  }
   int buf = 0;
+  unsigned phase[2] = {0u, 0u};
   for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
     const long next = tile + gridDim.x;
-    if (next < ntiles) {
-      prefetch(next, buf ^ 1);
-      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    if (threadIdx.x == 0 && next < ntiles) {
+      // the other buffer was handed to a bulk store one iteration ago: its shared-memory reads must be over
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      mbar_expect_tx(&s_bar[buf ^ 1], tile_bytes(next));
+      tma_load_1d(s_raw[buf ^ 1], rays + next * kRayThreads, tile_bytes(next), &s_bar[buf ^ 1]);
     }
-    __syncthreads();
+    mbar_wait(&s_bar[buf], phase[buf]);
+    phase[buf] ^= 1u;
     const long first = tile * kRayThreads;
     const int nblk = (int)min((long)kRayThreads, nrays - first);
     Ray *s_rays = reinterpret_cast<Ray *>(s_raw[buf]);
@@ -141,12 +173,13 @@ ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab 
         if ((threadIdx.x & 31) == 0) s_sum[k][threadIdx.x >> 5] += v;
       }
     }
+    // the records were written through the generic proxy: make them visible to the async (TMA) proxy, then one
+    // thread hands the tile to a bulk store
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    const int4 *ssrc = reinterpret_cast<const int4 *>(s_raw[buf]);
-    int4 *gdst = reinterpret_cast<int4 *>(rays + first);
-    for (int i = threadIdx.x; i < nblk * kRayWords; i += kRayThreads) gdst[i] = ssrc[i];
-    __syncthreads();   // the next iteration streams the tile after next into this buffer
+    if (threadIdx.x == 0) tma_store_1d(rays + first, s_raw[buf], (unsigned)(nblk * (int)sizeof(Ray)));
   }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
   if (sum6 && (threadIdx.x & 31) == 0) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) atomicAdd(&sum6[k], s_sum[k][threadIdx.x >> 5]);
