@@ -277,10 +277,12 @@ __device__ void cta_dft_r(double2 *a, int r, int logM, int bluestein, const doub
   const int M = 1 << logM;
   // (fusing this product into the first inverse pass costs more than it saves: the pass reads 16 consecutive
   // elements per thread, which turns the coalesced table read into 32 wavefronts per load)
+#pragma unroll 4
   for (int k = threadIdx.x; k < M; k += blockDim.x) a[swz(k, logM)] = cmul(a[swz(k, logM)], __ldg(&bhat[k]));
   __syncthreads();
   cta_fft_dit_inv(a, logM, tw, logTW);
   if (!final_chirp) return;
+#pragma unroll 4
   for (int k = threadIdx.x; k < r; k += blockDim.x) a[swz(k, logM)] = cmul(a[swz(k, logM)], __ldg(&chirp[k]));
   __syncthreads();
 }
@@ -632,16 +634,35 @@ __device__ __forceinline__ void ring_synthesis_body(const SynArgs &A, double2 *s
   const double2 *bhat = bluestein ? bhat_all + bhat_off[r] : nullptr;
 
   // S1: folded, phased float bins
-  for (int k = threadIdx.x; k <= 2 * r; k += blockDim.x) {
-    float2 y = fold_bin(b_recv, m_boff, fslot, k, n, lmax, shifted);
-    if (shifted) {                                                  // [healpix_shtrans.c:186-197]
-      const double2 ph = __ldg(&PT[k]);                             // (cos, sin)(k pi / n), tabulated at plan time
-      double c = ph.x, s = ph.y;
-      double t0 = (double)y.x, t1 = (double)y.y;
-      y.x = __double2float_rn(__dsub_rn(__dmul_rn(t0, c), __dmul_rn(t1, s)));
-      y.y = __double2float_rn(__dadd_rn(__dmul_rn(t1, c), __dmul_rn(t0, s)));
+  // four bins per thread and trip, with the global loads of the common single-term bins (and of the phase table) issued
+  // together: this loop is otherwise bound by one exposed L2 round trip per bin
+  for (int kb = threadIdx.x; kb <= 2 * r; kb += 4 * blockDim.x) {
+    double2 bv[4], ph[4];
+    bool valid[4], single[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = kb + u * blockDim.x;
+      valid[u] = k <= 2 * r;
+      single[u] = valid[u] && (n - k > lmax) && (k > 0 || n > lmax);   // only m = k lands in this bin (see fold_bin)
+      bv[u] = make_double2(0.0, 0.0); ph[u] = make_double2(1.0, 0.0);
+      if (single[u] && k <= lmax) bv[u] = __ldg(&b_recv[m_boff[k] + fslot]);
+      if (valid[u] && shifted) ph[u] = __ldg(&PT[k]);               // (cos, sin)(k pi / n), tabulated at plan time
     }
-    Y[k] = y;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!valid[u]) continue;
+      const int k = kb + u * blockDim.x;
+      float2 y;
+      if (single[u]) y = make_float2(__double2float_rn(__dadd_rn(0.0, bv[u].x)), __double2float_rn(__dadd_rn(0.0, bv[u].y)));
+      else y = fold_bin(b_recv, m_boff, fslot, k, n, lmax, shifted);
+      if (shifted) {                                                  // [healpix_shtrans.c:186-197]
+        const double c = ph[u].x, s = ph[u].y;
+        const double t0 = (double)y.x, t1 = (double)y.y;
+        y.x = __double2float_rn(__dsub_rn(__dmul_rn(t0, c), __dmul_rn(t1, s)));
+        y.y = __double2float_rn(__dadd_rn(__dmul_rn(t1, c), __dmul_rn(t0, s)));
+      }
+      Y[k] = y;
+    }
   }
   __syncthreads();
   // c2r samples 0, n/4, n/2, 3n/4 have rational twiddles: exact sums of the float bins (same reason and same
