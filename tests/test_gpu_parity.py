@@ -695,3 +695,25 @@ def test_stage_outputs_stay_inside_their_buffers(clb, order, lmax):
     check(g_all, 2 * plan.g_send_total, "g"); check(are_all, plan.Nlm, "alm_re"); check(aim_all, plan.Nlm, "alm_im")
     check(b_all, 2 * plan.b_send_total, "b"); check(maps_all, 6 * npix, "maps")
     plan.destroy()
+
+
+def test_next_rows_golden(clb):
+    """the three 'next' rows against the committed golden vectors (no oracle library needed)"""
+    import torch
+    from calclens_b200 import _lib
+    L = _lib.load()
+    g = np.load(os.path.join(GOLD, "next_rows.npz"))
+    order = int(g["dep_order"])
+    dm = torch.zeros(12 << (2 * order), dtype=torch.float32, device="cuda")
+    dp = torch.from_numpy(g["dep_pos"]).cuda(); dmass = torch.from_numpy(g["dep_mass"]).cuda()
+    L.clb_deposit_ngp_dev(dp.data_ptr(), dmass.data_ptr(), int(dmass.numel()), order, dm.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert np.array_equal(dm.cpu().numpy(), g["dep_map"])
+    rays = g["rays_in"].copy().view(clb.RAY_DTYPE)
+    d_in = torch.from_numpy(rays.view(np.uint8).copy()).cuda(); d_out = torch.zeros_like(d_in)
+    L.clb_ray_output_dev(d_in.data_ptr(), d_out.data_ptr(), rays.size, 3, None)
+    torch.cuda.synchronize()
+    assert_rays_match(d_out.cpu().numpy().view(clb.RAY_DTYPE), g["rays_output"].view(clb.RAY_DTYPE))
+    rb = rays.copy()
+    clb.rayprop_sphere(45.0, 15.0, 0.0, rb, born=True); clb.rayprop_sphere(75.0, 45.0, 15.0, rb, born=True)
+    assert_rays_match(rb, g["rays_born"].view(clb.RAY_DTYPE))

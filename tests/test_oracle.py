@@ -161,3 +161,16 @@ def test_port_matches_reference_on_next_rows():
     ref.rayprop_born(r1, 45.0, 15.0, 0.0); port.rayprop_born(r2, 45.0, 15.0, 0.0)
     ref.rayprop_born(r1, 75.0, 45.0, 15.0); port.rayprop_born(r2, 75.0, 45.0, 15.0)
     assert r1.tobytes() == r2.tobytes()
+
+
+@pytest.mark.parametrize("orc", ORACLES, ids=IDS)
+def test_next_rows_golden(orc):
+    """NGP deposit, write_rays' output transform and the Born step against vectors produced by the unmodified reference
+    functions (tools/make_golden.py)."""
+    g = np.load(os.path.join(GOLD, "next_rows.npz"))
+    assert np.array_equal(orc.deposit_ngp(g["dep_pos"], g["dep_mass"], int(g["dep_order"])), g["dep_map"])
+    rays = g["rays_in"].copy().view(orc.RAY_DTYPE)
+    r = rays.copy(); orc.ray_output(r, 3)
+    assert r.tobytes() == g["rays_output"].tobytes()
+    r = rays.copy(); orc.rayprop_born(r, 45.0, 15.0, 0.0); orc.rayprop_born(r, 75.0, 45.0, 15.0)
+    assert r.tobytes() == g["rays_born"].tobytes()

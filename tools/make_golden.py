@@ -92,4 +92,21 @@ rz = ref.init_rays(2, 15.0); rz["U"] = rng.normal(size=rz["U"].shape) * 1e-2
 rz0 = rz.copy(); ref.rayprop(rz, 45.0, 15.0, 0.0)
 np.savez_compressed(os.path.join(OUT, "rays.npz"), order=order, maps=maps, rays0=r0.view(np.uint8), rays_interp=r1.view(np.uint8),
                     rays_prop1=r2.view(np.uint8), rays_prop2=r3.view(np.uint8), rz0=rz0.view(np.uint8), rz1=rz.view(np.uint8))
+
+# ---- the callers either side of the path ("next" rows): NGP deposit, write_rays' output transform, Born step
+nx = {}
+order = 3
+pos = (rng.normal(size=(5000, 3)) * 200.0).astype(np.float32)
+pos[:6] = [[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, 1, 0], [-1, 0, 0], [1e-3, -1e-3, 1]]
+mass = np.full(5000, 3.7e9, dtype=np.float32)
+nx["dep_order"] = order; nx["dep_pos"] = pos; nx["dep_mass"] = mass; nx["dep_map"] = ref.deposit_ngp(pos, mass, order)
+ro = ref.init_rays(3, 15.0)
+ro["n"] += rng.normal(size=ro["n"].shape) * 0.02
+for f, n in (("A", 4), ("Aprev", 4), ("U", 4), ("alpha", 2)):
+    ro[f] += rng.normal(size=(ro.size, n)) * 0.05
+nx["rays_in"] = ro.copy().view(np.uint8)
+r_out = ro.copy(); ref.ray_output(r_out, 3); nx["rays_output"] = r_out.view(np.uint8)
+r_born = ro.copy(); ref.rayprop_born(r_born, 45.0, 15.0, 0.0); ref.rayprop_born(r_born, 75.0, 45.0, 15.0)
+nx["rays_born"] = r_born.view(np.uint8)
+np.savez_compressed(os.path.join(OUT, "next_rows.npz"), **nx)
 print("golden vectors written to", OUT, {f: os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT)})
