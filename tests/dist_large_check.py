@@ -40,10 +40,7 @@ def main():
     are[ls == 0] = 0.0
     maps = s.alm2allmaps(are, aim).clone()
     lap = s.alm2allmaps(-ls * (ls + 1) * are, -ls * (ls + 1) * aim)[0].clone()
-    # this rank's rings only: analysing phi needs just those, and the identity is checked there
-    own = torch.zeros(s.npix, dtype=torch.bool, device=dev)
-    g = s.plan.ring_analysis  # noqa: F841  (keeps the name close to the stage it tests)
-    dens = maps[0].contiguous()
+    dens = maps[0].contiguous()   # analysing phi only reads this rank's own rings
     # Laplacian identity on every pixel this rank holds (halo_deg=0 -> full broadcast, so all of them)
     num = (maps[3].double() + maps[5].double() - lap.double()).pow(2).sum()
     den = lap.double().pow(2).sum()
