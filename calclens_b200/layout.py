@@ -60,6 +60,24 @@ class ExchangeLayout:
         return int(self.b_rbase[q] + (self.m_local[m] * 6 + field) * self.nslot_mine + 2 * self.rp_local[rp] + hemi)
 
 
+    # fused exchange over peer memory (csrc/sht_plan.cu:sht_plan_set_peers) -------------------------------------
+    def g_pull_index(self, m_idx, rp, hemi):
+        """where THIS rank (owner of its m_idx-th m) reads g of (rp, hemi) inside the SEND buffer of rp's owner q:
+        q's block for this rank starts after its blocks for the lower ranks (nm_of[r] * nslot_q elements each)."""
+        q = self.rp_owner[rp]
+        nslot_q = 2 * int(self.nrp_of[q])
+        sbase = sum(int(self.nm_of[r]) * nslot_q for r in range(self.rank))
+        return int(q), int(sbase + m_idx * nslot_q + 2 * self.rp_local[rp] + hemi)
+
+    def b_push_index(self, m_idx, field, rp, hemi):
+        """where THIS rank (owner of its m_idx-th m) stores b of (field, rp, hemi) inside the RECEIVE buffer of rp's
+        owner q: q's block from this rank starts after the blocks from the lower ranks (nm_of[r] * 6 * nslot_q each)."""
+        q = self.rp_owner[rp]
+        nslot_q = 2 * int(self.nrp_of[q])
+        rbase = sum(int(self.nm_of[r]) * 6 * nslot_q for r in range(self.rank))
+        return int(q), int(rbase + (m_idx * 6 + field) * nslot_q + 2 * self.rp_local[rp] + hemi)
+
+
 def ray_ranges(ray_order, nranks):
     """Contiguous NEST ranges of rays per rank = compact sky domains (cf. loadbalance.c:151-181 equal-area split)."""
     n = 12 << (2 * ray_order)

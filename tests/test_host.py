@@ -152,3 +152,25 @@ def test_domain_masks_cover_domains_and_halo():
         assert np.all((wide & own) == own) and np.any(wide != own)
         frac = np.unpackbits(wide[:, None], axis=1).sum() / (nc * nranks)
         assert 1.0 / nranks < frac < 1.0 / nranks + 0.45
+
+
+def test_fused_exchange_addresses_match_the_all_to_all_layout():
+    """The peer-memory exchange reads/writes exactly the elements the all-to-all-v would have delivered: the pull address
+    of g inside the ring owner's send buffer equals that owner's own g_send_index, and the push address of b inside the
+    ring owner's receive buffer equals that owner's own b_recv_index (CUDA-free mirror of sht_plan_set_peers)."""
+    from calclens_b200 import layout, sht
+    order, lmax = 4, 37
+    nside = 1 << order
+    for nranks in (2, 3, 5):
+        rp_owner, m_owner = sht.default_owners(order, lmax, nranks)
+        lays = [layout.ExchangeLayout(nside, lmax, nranks, r, rp_owner, m_owner) for r in range(nranks)]
+        rng = np.random.default_rng(nranks)
+        for _ in range(400):
+            m = int(rng.integers(0, lmax + 1)); rp = int(rng.integers(0, 2 * nside)); hemi = int(rng.integers(0, 2))
+            f = int(rng.integers(0, 6))
+            me = lays[int(m_owner[m])]                       # the rank whose Legendre stage handles m
+            m_idx = int(me.m_local[m])
+            q, off = me.g_pull_index(m_idx, rp, hemi)
+            assert q == rp_owner[rp] and off == lays[q].g_send_index(m, rp, hemi)
+            q, off = me.b_push_index(m_idx, f, rp, hemi)
+            assert q == rp_owner[rp] and off == lays[q].b_recv_index(m, f, rp, hemi)
