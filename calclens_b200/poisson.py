@@ -93,7 +93,7 @@ class LensPlaneSolver:
     torch.distributed process group (NCCL) with one rank per GPU."""
 
     def __init__(self, sht_order, lmax=None, ray_order=None, ring_weights=None, dist_group=None, device=None, fused=True,
-                 halo_deg=1.0):
+                 halo_deg=1.0, overlap_rays=False):
         import torch.distributed as dist
         self.dist = dist if dist_group is not None else None
         self.group = dist_group
@@ -122,6 +122,13 @@ class LensPlaneSolver:
         self._copy_stream = torch.cuda.Stream(device=self.device, priority=-1)   # runs behind the compute kernels, gets SM slots first
         self._staged = None        # (host map, scalings, buffer index, ready event) of a prefetched plane
         self._dens_free = [None, None]   # event after the last kernel that read each density buffer
+        # overlap_rays: the ray kernel of plane p runs on its own stream while the next plane's density load, ring FFT and
+        # Legendre analysis proceed (the SHT of plane p+1 does not depend on the rays); the next plane's ring synthesis,
+        # which overwrites the maps, waits for it.  The ray kernel (128 registers) fits beside two Legendre CTAs on an SM.
+        self.overlap_rays = bool(overlap_rays)
+        self._ray_stream = torch.cuda.Stream(device=self.device)
+        self._rays_done = None
+        self.ray_events = []
         self.fused = False
         self.halo_deg = float(halo_deg)
         self.coarse_order = 5
@@ -202,6 +209,7 @@ class LensPlaneSolver:
 
     def close(self):
         """Release the peer mappings and the library-owned buffers (after every rank has stopped using them)."""
+        self._wait_rays()
         if self._peer_bufs:
             torch.cuda.synchronize()
             if self.nranks > 1:
@@ -227,6 +235,7 @@ class LensPlaneSolver:
     # ---- rays ----
     def init_rays(self, binL_2):
         """alloc_rays + init_rays (raytrace_utils.c:265-347) for this rank's contiguous NEST range."""
+        self._wait_rays()
         nray_tot = 12 << (2 * self.ray_order)
         lo = (nray_tot * self.rank) // self.nranks
         hi = (nray_tot * (self.rank + 1)) // self.nranks
@@ -272,6 +281,7 @@ class LensPlaneSolver:
             mark("legendre_analysis")
             self.lib.clb_legendre_synthesis_dev(p._h, self.alm_re.data_ptr(), self.alm_im.data_ptr(), None, self._stream())
             mark("legendre_synthesis")
+            self._wait_rays()        # the previous plane's ray kernel still reads the maps (every rank, before the barrier)
             self._stream_barrier(); mark("a2a_b")
             p.ring_synthesis(self.b_recv, self.maps); mark("fft_synthesis")
             ptrs = (C.c_void_p * 6)(*[self.maps[k].data_ptr() for k in range(6)])
@@ -284,6 +294,7 @@ class LensPlaneSolver:
         p.legendre_analysis(g, self.alm_re, self.alm_im, poisson_filter=True); mark("legendre_analysis")
         p.legendre_synthesis(self.alm_re, self.alm_im, self.b_send); mark("legendre_synthesis")
         b = self._all_to_all(self.b_send, self.b_recv, p.counts[2], p.counts[3]); mark("a2a_b")
+        self._wait_rays()
         if self.nranks > 1:
             self.maps.zero_()
         p.ring_synthesis(b, self.maps); mark("fft_synthesis")
@@ -292,9 +303,16 @@ class LensPlaneSolver:
         mark("map_allreduce")
         return self.maps
 
+    def _wait_rays(self):
+        """The current stream waits for a ray kernel still running on the ray stream (overlap_rays)."""
+        if self._rays_done is not None:
+            torch.cuda.current_stream().wait_event(self._rays_done)
+            self._rays_done = None
+
     def alm2allmaps(self, alm_re, alm_im):
         """alm2allmaps_mpi over the ranks of the group: local alm (this rank's m) -> the six full maps on every rank."""
         p = self.plan
+        self._wait_rays()
         if self.fused:
             self._stream_barrier()
             self.lib.clb_legendre_synthesis_dev(p._h, alm_re.data_ptr(), alm_im.data_ptr(), None, self._stream())
@@ -320,10 +338,27 @@ class LensPlaneSolver:
         with_summary: also accumulate the six plane sums into self.summary (same kernel, no second pass)."""
         ptrs = (C.c_void_p * 6)(*[self.maps[k].data_ptr() for k in range(6)])
         need = None if self._need is None else self._need.data_ptr()
-        self.lib.clb_ray_step_ex_dev(self.rays.data_ptr(), self.nrays, ptrs, self.order, float(wpp1), float(wp), float(wpm1),
-                                     MODE_ZERO | MODE_INTERP | MODE_PROP, need, self.coarse_order if need else 0, self.rank,
-                                     self._err.data_ptr() if need else None,
-                                     self.summary.data_ptr() if with_summary else None, self._stream())
+
+        def launch(stream):
+            self.lib.clb_ray_step_ex_dev(self.rays.data_ptr(), self.nrays, ptrs, self.order, float(wpp1), float(wp), float(wpm1),
+                                         MODE_ZERO | MODE_INTERP | MODE_PROP, need, self.coarse_order if need else 0, self.rank,
+                                         self._err.data_ptr() if need else None,
+                                         self.summary.data_ptr() if with_summary else None, stream)
+        if not self.overlap_rays:
+            launch(self._stream())
+            return
+        self._wait_rays()                      # planes are sequential for the rays
+        maps_ready = torch.cuda.Event(); maps_ready.record()
+        self._ray_stream.wait_event(maps_ready)
+        t0 = torch.cuda.Event(enable_timing=True); t0.record(self._ray_stream)
+        launch(self._ray_stream.cuda_stream)
+        done = torch.cuda.Event(enable_timing=True); done.record(self._ray_stream)
+        self._rays_done = done
+        self.ray_events = (self.ray_events + [(t0, done)])[-64:]     # duration of the overlapped kernel, for bench.py
+
+    def sync_rays(self):
+        """Join the ray stream (before reading rays, summaries, or timing)."""
+        self._wait_rays()
 
     def check_halo(self):
         """Raise if a ray left the part of the sky this rank receives (the reference aborts on a missing map cell,
@@ -366,6 +401,7 @@ class LensPlaneSolver:
             self._staged = self._next_staged
         if not read_summary:
             return None
+        self._wait_rays()
         if self.nranks > 1:
             self.dist.all_reduce(self.summary, group=self.group)
         out = self.summary.cpu().numpy()
@@ -374,4 +410,5 @@ class LensPlaneSolver:
 
     def rays_host(self):
         from .rays import rays_from_device
+        self._wait_rays()
         return rays_from_device(self.rays[:self.nrays * 176])

@@ -507,7 +507,9 @@ def test_solver_step_prefetch_and_fused_summary(clb):
     planes = [(45.0, 15.0, 0.0), (75.0, 45.0, 15.0), (105.0, 75.0, 45.0)]
     a = poisson.LensPlaneSolver(order, lmax, order); a.init_rays(15.0)
     b = poisson.LensPlaneSolver(order, lmax, order); b.init_rays(15.0)
+    c = poisson.LensPlaneSolver(order, lmax, order, overlap_rays=True); c.init_rays(15.0)
     for k, pl in enumerate(planes):
+        c.step(maps[k], *sc, *pl, read_summary=False)     # rays of plane k run beside the SHT of plane k+1
         sa = a.step(maps[k], *sc, *pl)
         nxt = (maps[k + 1],) + sc if k + 1 < len(planes) else None
         sb = b.step(maps[k], *sc, *pl, prefetch=nxt)
@@ -517,6 +519,7 @@ def test_solver_step_prefetch_and_fused_summary(clb):
         a.lib.clb_ray_summary_dev(a.rays.data_ptr(), a.nrays, ref.data_ptr(), None)
         assert np.allclose(sa, ref.cpu().numpy(), rtol=1e-9, atol=1e-13)
     assert np.array_equal(a.rays_host().view(np.uint8), b.rays_host().view(np.uint8))
+    assert np.array_equal(a.rays_host().view(np.uint8), c.rays_host().view(np.uint8))
 
 
 def test_global_scratch_ring_fft_matches_shared_memory_path(clb):
