@@ -168,6 +168,19 @@ def cpu_reference_sample(sample_order, cores, target_nside, target_lmax, target_
     return planes_per_s, sample, wall
 
 
+def host_cores(sample_order):
+    """Processes for the CPU legs: every host core, bounded by memory (one reference process holds ~0.2 GB at sample
+    order 8, ~0.8 GB at order 9: six maps plus 176-byte rays) so a many-core box is not driven out of RAM."""
+    cores = os.cpu_count() or 1
+    try:
+        import psutil
+        per_proc = 0.25e9 * 4 ** max(sample_order - 8, 0)
+        cores = max(1, min(cores, int(0.5 * psutil.virtual_memory().available / per_proc)))
+    except Exception:
+        cores = min(cores, 32)
+    return cores
+
+
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -177,7 +190,7 @@ def run_reference_arm(a):
     if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libcalclens_ref.so not built (needs /root/reference at build time)"}))
         return 0
-    cores = os.cpu_count() or 1
+    cores = host_cores(a.ref_sample_order)
     vals, wall = [], 0.0
     sample_txt = ""
     for i in range(a.warmup + a.steps):
@@ -448,7 +461,7 @@ def main():
             try:
                 from oracle import ref
                 if ref.available():
-                    cores = os.cpu_count() or 1
+                    cores = host_cores(a.cpu_baseline_order)
                     v, txt, _ = cpu_reference_sample(a.cpu_baseline_order, cores, a.nside, a.lmax, nrays_total)
                     cpu_baseline = {"value": v, "unit": "planes/s", "cores": cores, "kind": "reference", "sample": txt}
                 else:
