@@ -62,6 +62,30 @@ def load():
         "clb_lens_plane": (None, [vp, vp, C.c_float, C.c_float, C.c_float, vp, C.c_long, C.c_double, C.c_double, C.c_double]),
         "clb_healpix_index_dev": (None, [C.c_int, C.c_long, C.c_long, vp, vp, vp, vp, vp]),
         "clb_healpix_interpol_dev": (None, [C.c_long, C.c_long, vp, vp, vp, vp]),
+        "clb_ray_stencil_dev": (None, [C.c_long, C.c_long, vp, vp, vp, vp]),
+        "clb_host_register": (C.c_int, [vp, C.c_long]),
+        "clb_host_unregister": (None, [vp]),
+        "clb_pool_release": (None, []),
+        # persistent solver (csrc/solver.cu); the allgather callback is a CFUNCTYPE(None, void*, void*, long, void*)
+        "clb_solver_create": (vp, [C.c_long, C.c_long, C.c_long, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_double]),
+        "clb_solver_destroy": (None, [vp]),
+        "clb_solver_query": (C.c_long, [vp, C.c_int]),
+        "clb_solver_ptr": (vp, [vp, C.c_int]),
+        "clb_solver_init_rays": (C.c_long, [vp, C.c_double, vp]),
+        "clb_solver_set_rays": (None, [vp, vp, C.c_long, vp]),
+        "clb_solver_get_rays": (None, [vp, vp, vp]),
+        "clb_solver_ray_output": (None, [vp, vp, vp]),
+        "clb_solver_step": (C.c_int, [vp, vp, C.c_float, C.c_float, C.c_float, C.c_double, C.c_double, C.c_double, vp, vp]),
+        "clb_solver_set_next": (None, [vp, vp, C.c_float, C.c_float, C.c_float]),
+        "clb_solver_check": (C.c_int, [vp, vp]),
+        "clb_solver_load_density": (None, [vp, vp, C.c_float, C.c_float, C.c_float, vp]),
+        "clb_solver_solve": (None, [vp, vp, vp]),
+        "clb_solver_alm2allmaps": (None, [vp, vp, vp, vp]),
+        "clb_solver_ray_update": (None, [vp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, vp]),
+        "clb_solver_map2alm_mapvec": (None, [vp, vp, vp, vp, vp, vp, vp]),
+        "clb_solver_alm2allmaps_mapvec": (None, [vp, vp, vp, vp, vp, vp, vp]),
+        "clb_solver_set_timing": (None, [vp, C.c_int]),
+        "clb_solver_stage_ms": (None, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)   # AttributeError here = header and library out of sync
@@ -78,4 +102,4 @@ def exported_symbols():
     hdr = os.path.join(_HERE, "..", "include", "calclens_b200.h")
     txt = open(hdr).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(clb_[a-z0-9_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(clb_[a-z0-9_]+)\s*\(", txt)) - {"clb_allgather_fn"})

@@ -18,6 +18,7 @@ UNITS = {  # source -> extra flags
     "legendre.cu": [],
     "ring_fft.cu": [],
     "rays.cu": ["-fmad=false"],
+    "solver.cu": [],
 }
 
 

@@ -1,35 +1,13 @@
 // calclens_b200/csrc/api.cu -- extern "C" boundary of libcalclens_b200.so (see include/calclens_b200.h).
-#include "sht_internal.cuh"
-#include "raymath.cuh"
+#include "launch.cuh"
 #include "../../include/calclens_b200.h"
 #include <string.h>
 
 namespace clb {
-ShtPlan *sht_plan_create(long order, long lmax, const double *ring_weights, int nranks, int rank, const int *rp_owner,
-                         const int *m_owner);
-void sht_plan_destroy(ShtPlan *p);
-int launch_ring_analysis(const ShtPlan *p, const float *d_map, double2 *d_g_send, cudaStream_t st);
-int launch_ring_synthesis(const ShtPlan *p, const double2 *d_b_recv, float *const d_maps[6], cudaStream_t st);
-int launch_legendre_analysis(ShtPlan *p, const double2 *d_g_recv, double *d_alm_re, double *d_alm_im, int apply_filter,
-                             cudaStream_t st);
-int launch_legendre_synthesis(ShtPlan *p, const double *d_alm_re, const double *d_alm_im, double2 *d_b_send, cudaStream_t st);
-int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long order, double wp, double wpm1, double wpm2,
-                    int mode, cudaStream_t st, const unsigned char *d_need = nullptr, long coarse_order = 0, int rank = 0,
-                    int *d_err = nullptr, double *d_sum6 = nullptr);
-int launch_ray_init(Ray *d_rays, long nrays, long first_nest, long ray_order, double binL_2, cudaStream_t st);
-int launch_ray_summary(const Ray *d_rays, long nrays, double *d_out6, cudaStream_t st);
-int launch_ray_output(const Ray *d_rays, Ray *d_out, long nrays, long ray_order, cudaStream_t st);
-int launch_deposit_ngp(const float *d_pos, const float *d_mass, long nparts, long order, float *d_ringmap, cudaStream_t st);
-void launch_healpix_index(int what, long order, long n, const long *in, const double *th, const double *ph, long *out, cudaStream_t st);
-void launch_healpix_interpol(long order, long n, const double *vec, long *pix, double *wgt, cudaStream_t st);
-void sht_plan_set_peers(ShtPlan *p, void *const *g_send_ptrs, void *const *b_recv_ptrs);
-int launch_maps_broadcast(const ShtPlan *p, float *const local_maps[6], float *const *peer_maps,
-                          const unsigned char *d_need, long coarse_order, cudaStream_t st);
-int launch_load_density(const ShtPlan *p, const float *src, float *dst, float premul, float densmul, float backdens,
-                        cudaStream_t st);
 extern int g_syn_rings_per_thread, g_ana_rings_per_thread, g_fft_threads_big, g_leg_warps_per_cta, g_fft_force_scratch;
 
 static long g_launches = 0;
+void count_launches(int n) { g_launches += n; }
 
 __global__ void scale_density_kernel(float *__restrict__ map, long npix, float premul, float densmul, float backdens)
 {
@@ -43,11 +21,44 @@ __global__ void scale_density_kernel(float *__restrict__ map, long npix, float p
     map[i] = v;
   }
 }
+// Host helper: which ranks need the map pixels of every coarse NEST cell.  Rank q traces the rays whose NEST index at
+// ray_order lies in [Nray q / nranks, Nray (q+1) / nranks) (cf. loadbalance.c:151-181); its rays stay within the halo
+// of that domain (the reference's MAPBUFF cells, raytrace_utils.c:116-161), so it needs every cell whose centre is
+// within margin_rad of the centre of a cell of its domain (margin_rad must include two coarse cell radii).
+void domain_masks(long ray_order, int nranks, long coarse_order, double margin_rad, unsigned char *mask)
+{
+  if (nranks > 8 || coarse_order < 0 || coarse_order > 8) { fprintf(stderr, "calclens_b200: clb_domain_masks arguments\n"); abort(); }
+  const long nc = 12L << (2 * coarse_order);
+  const long nray = 12L << (2 * ray_order);
+  std::vector<double> cen(3 * nc);
+  std::vector<unsigned char> own(nc, 0);
+  for (long c = 0; c < nc; ++c) {
+    nest2vec(c, coarse_order, &cen[3 * c]);
+    long lo, hi;   // ray NEST range covered by (or covering) the cell
+    if (ray_order >= coarse_order) { lo = c << (2 * (ray_order - coarse_order)); hi = (c + 1) << (2 * (ray_order - coarse_order)); }
+    else { lo = c >> (2 * (coarse_order - ray_order)); hi = lo + 1; }
+    for (int q = 0; q < nranks; ++q) {
+      const long qlo = (nray * q) / nranks, qhi = (nray * (q + 1)) / nranks;
+      if (lo < qhi && qlo < hi) own[c] |= (unsigned char)(1u << q);
+    }
+  }
+  const double cosm = cos(margin_rad);
+  for (long c = 0; c < nc; ++c) {
+    unsigned m = own[c];
+    const double *a = &cen[3 * c];
+    for (long d = 0; d < nc && m != ((1u << nranks) - 1u); ++d) {
+      if ((own[d] | m) == m) continue;
+      const double *b = &cen[3 * d];
+      if (a[0] * b[0] + a[1] * b[1] + a[2] * b[2] >= cosm) m |= own[d];
+    }
+    mask[c] = (unsigned char)m;
+  }
+}
+
 }  // namespace clb
 
 using namespace clb;
 
-struct clb_sht_plan { ShtPlan *p; };
 
 static ShtPlan *P(const clb_sht_plan *plan)
 {
@@ -57,7 +68,7 @@ static ShtPlan *P(const clb_sht_plan *plan)
 
 extern "C" {
 
-int clb_abi_version(void) { return 1; }
+int clb_abi_version(void) { return 2; }
 
 int clb_device_count(void)
 {
@@ -71,6 +82,14 @@ int clb_device_count(void)
   return n;
 }
 void clb_set_device(int device) { CLB_CUDA_CHECK(cudaSetDevice(device)); }
+int clb_host_register(void *p, long bytes)
+{
+  cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) { cudaGetLastError(); return 1; }   // not fatal: transfers fall back to pageable copies
+  return 0;
+}
+void clb_host_unregister(void *p) { cudaHostUnregister(p); cudaGetLastError(); }
+void clb_pool_release(void);
 long clb_launch_count(void) { return g_launches; }
 void clb_set_tuning(int what, int value)
 {
@@ -175,38 +194,9 @@ int clb_maps_broadcast_dev(const clb_sht_plan *plan, float *const local_maps[6],
   int n = launch_maps_broadcast(P(plan), local_maps, peer_maps, need, coarse_order, (cudaStream_t)stream);
   g_launches += n; return n;
 }
-// Host helper: which ranks need the map pixels of every coarse NEST cell.  Rank q traces the rays whose NEST index at
-// ray_order lies in [Nray q / nranks, Nray (q+1) / nranks) (cf. loadbalance.c:151-181); its rays stay within the halo
-// of that domain (the reference's MAPBUFF cells, raytrace_utils.c:116-161), so it needs every cell whose centre is
-// within margin_rad of the centre of a cell of its domain (margin_rad must include two coarse cell radii).
 void clb_domain_masks(long ray_order, int nranks, long coarse_order, double margin_rad, unsigned char *mask)
 {
-  if (nranks > 8 || coarse_order < 0 || coarse_order > 8) { fprintf(stderr, "calclens_b200: clb_domain_masks arguments\n"); abort(); }
-  const long nc = 12L << (2 * coarse_order);
-  const long nray = 12L << (2 * ray_order);
-  std::vector<double> cen(3 * nc);
-  std::vector<unsigned char> own(nc, 0);
-  for (long c = 0; c < nc; ++c) {
-    nest2vec(c, coarse_order, &cen[3 * c]);
-    long lo, hi;   // ray NEST range covered by (or covering) the cell
-    if (ray_order >= coarse_order) { lo = c << (2 * (ray_order - coarse_order)); hi = (c + 1) << (2 * (ray_order - coarse_order)); }
-    else { lo = c >> (2 * (coarse_order - ray_order)); hi = lo + 1; }
-    for (int q = 0; q < nranks; ++q) {
-      const long qlo = (nray * q) / nranks, qhi = (nray * (q + 1)) / nranks;
-      if (lo < qhi && qlo < hi) own[c] |= (unsigned char)(1u << q);
-    }
-  }
-  const double cosm = cos(margin_rad);
-  for (long c = 0; c < nc; ++c) {
-    unsigned m = own[c];
-    const double *a = &cen[3 * c];
-    for (long d = 0; d < nc && m != ((1u << nranks) - 1u); ++d) {
-      if ((own[d] | m) == m) continue;
-      const double *b = &cen[3 * d];
-      if (a[0] * b[0] + a[1] * b[1] + a[2] * b[2] >= cosm) m |= own[d];
-    }
-    mask[c] = (unsigned char)m;
-  }
+  domain_masks(ray_order, nranks, coarse_order, margin_rad, mask);
 }
 
 int clb_ring_analysis_dev(const clb_sht_plan *plan, const float *map, double *g_send, void *stream)
@@ -234,7 +224,7 @@ int clb_ring_synthesis_dev(const clb_sht_plan *plan, const double *b_recv, float
 int clb_scale_density_dev(float *map, long npix, float premul, float densmul, float backdens, void *stream)
 {
   if (npix <= 0) return 0;
-  scale_density_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(map, npix, premul, densmul, backdens);
+  scale_density_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(map, npix, premul, densmul, backdens);
   CLB_CUDA_CHECK(cudaGetLastError());
   g_launches += 1; return 1;
 }
@@ -289,7 +279,12 @@ void clb_healpix_index_dev(int what, long order, long n, const long *in, const d
 }
 void clb_healpix_interpol_dev(long order, long n, const double *vec, long *pix, double *wgt, void *stream)
 {
-  launch_healpix_interpol(order, n, vec, pix, wgt, (cudaStream_t)stream);
+  launch_healpix_interpol(order, n, vec, pix, wgt, 0, (cudaStream_t)stream);
+  g_launches += 1;
+}
+void clb_ray_stencil_dev(long order, long n, const double *vec, long *pix, double *wgt, void *stream)
+{
+  launch_healpix_interpol(order, n, vec, pix, wgt, 1, (cudaStream_t)stream);
   g_launches += 1;
 }
 
@@ -303,10 +298,36 @@ static void require_single(const ShtPlan *p, const char *who)
   if (p->nranks != 1) { fprintf(stderr, "calclens_b200: %s needs a single-rank plan (use the _dev stages)\n", who); abort(); }
 }
 
-struct DevBuf {
+// Device buffers of the host-pointer entry points: grow-only, kept per (device, slot) between calls so that a host that
+// calls map2alm_mpi / alm2allmaps_mpi / rayprop_sphere once per plane (or per bundle cell) does not pay cudaMalloc/cudaFree
+// every time.  clb_pool_release() frees them.
+struct DevPool {
+  static constexpr int kSlots = 8;
+  void *p[64][kSlots] = {};
+  size_t cap[64][kSlots] = {};
+  void *get(int slot, size_t bytes)
+  {
+    int dev = 0;
+    CLB_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || slot < 0 || slot >= kSlots) { fprintf(stderr, "calclens_b200: DevPool(%d, %d)\n", dev, slot); abort(); }
+    if (bytes > cap[dev][slot]) {
+      if (p[dev][slot]) CLB_CUDA_CHECK(cudaFree(p[dev][slot]));
+      CLB_CUDA_CHECK(cudaMalloc(&p[dev][slot], bytes));
+      cap[dev][slot] = bytes;
+    }
+    return p[dev][slot];
+  }
+  void release()
+  {
+    for (int d = 0; d < 64; ++d)
+      for (int k = 0; k < kSlots; ++k)
+        if (p[d][k]) { cudaSetDevice(d); cudaFree(p[d][k]); p[d][k] = nullptr; cap[d][k] = 0; }
+  }
+};
+static DevPool g_pool;
+struct DevBuf {   // a view of one pool slot
   void *p = nullptr;
-  explicit DevBuf(size_t bytes) { CLB_CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 16)); }
-  ~DevBuf() { cudaFree(p); }
+  DevBuf(int slot, size_t bytes) { p = g_pool.get(slot, bytes ? bytes : 16); }
   template <typename T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
@@ -316,8 +337,8 @@ void clb_map2alm(clb_sht_plan *plan, const float *ringmap, double *alm_re, doubl
 {
   ShtPlan *p = P(plan);
   require_single(p, "clb_map2alm");
-  DevBuf map(sizeof(float) * p->npix), g(sizeof(double2) * p->g_send_total), are(sizeof(double) * p->alm_total),
-      aim(sizeof(double) * p->alm_total);
+  DevBuf map(0, sizeof(float) * p->npix), g(1, sizeof(double2) * p->g_send_total), are(2, sizeof(double) * p->alm_total),
+      aim(3, sizeof(double) * p->alm_total);
   CLB_CUDA_CHECK(cudaMemcpy(map.p, ringmap, sizeof(float) * p->npix, cudaMemcpyHostToDevice));
   clb_ring_analysis_dev(plan, map.as<float>(), g.as<double>(), nullptr);
   clb_legendre_analysis_dev(plan, g.as<double>(), are.as<double>(), aim.as<double>(), apply_poisson_filter, nullptr);
@@ -329,8 +350,8 @@ void clb_alm2allmaps(clb_sht_plan *plan, const double *alm_re, const double *alm
 {
   ShtPlan *p = P(plan);
   require_single(p, "clb_alm2allmaps");
-  DevBuf dm(sizeof(float) * 6 * p->npix), b(sizeof(double2) * p->b_send_total), are(sizeof(double) * p->alm_total),
-      aim(sizeof(double) * p->alm_total);
+  DevBuf dm(0, sizeof(float) * 6 * p->npix), b(4, sizeof(double2) * p->b_send_total), are(2, sizeof(double) * p->alm_total),
+      aim(3, sizeof(double) * p->alm_total);
   CLB_CUDA_CHECK(cudaMemcpy(are.p, alm_re, sizeof(double) * p->alm_total, cudaMemcpyHostToDevice));
   CLB_CUDA_CHECK(cudaMemcpy(aim.p, alm_im, sizeof(double) * p->alm_total, cudaMemcpyHostToDevice));
   float *mp[6];
@@ -385,7 +406,7 @@ void clb_ray_step(void *rays, long nrays, const float *maps, long map_order, dou
 {
   clb_device_count();
   const long npix = 12L << (2 * map_order);
-  DevBuf dr(sizeof(Ray) * nrays), dm((mode & 2) ? sizeof(float) * 6 * npix : 16);
+  DevBuf dr(5, sizeof(Ray) * nrays), dm(0, (mode & 2) ? sizeof(float) * 6 * npix : 16);
   CLB_CUDA_CHECK(cudaMemcpy(dr.p, rays, sizeof(Ray) * nrays, cudaMemcpyHostToDevice));
   const float *mp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   if (mode & 2) {
@@ -402,8 +423,8 @@ void clb_lens_plane(clb_sht_plan *plan, const float *ringmap, float premul, floa
 {
   ShtPlan *p = P(plan);
   require_single(p, "clb_lens_plane");
-  DevBuf dm(sizeof(float) * 6 * p->npix), g(sizeof(double2) * p->g_send_total), b(sizeof(double2) * p->b_send_total),
-      are(sizeof(double) * p->alm_total), aim(sizeof(double) * p->alm_total), dr(sizeof(Ray) * nrays);
+  DevBuf dm(0, sizeof(float) * 6 * p->npix), g(1, sizeof(double2) * p->g_send_total), b(4, sizeof(double2) * p->b_send_total),
+      are(2, sizeof(double) * p->alm_total), aim(3, sizeof(double) * p->alm_total), dr(5, sizeof(Ray) * nrays);
   float *mp[6];
   for (int k = 0; k < 6; ++k) mp[k] = dm.as<float>() + (size_t)k * p->npix;
   CLB_CUDA_CHECK(cudaMemcpyAsync(mp[0], ringmap, sizeof(float) * p->npix, cudaMemcpyHostToDevice, nullptr));
@@ -416,5 +437,7 @@ void clb_lens_plane(clb_sht_plan *plan, const float *ringmap, float premul, floa
   clb_ray_step_dev(dr.p, nrays, mp, p->order, wp, wpm1, wpm2, 1 | 2 | 4, nullptr);
   CLB_CUDA_CHECK(cudaMemcpy(rays, dr.p, sizeof(Ray) * nrays, cudaMemcpyDeviceToHost));
 }
+
+void clb_pool_release(void) { g_pool.release(); }
 
 }  // extern "C"

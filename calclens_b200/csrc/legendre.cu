@@ -368,12 +368,12 @@ int g_syn_rings_per_thread = 4;   // tunable through clb_set_tuning(0, .)
 int g_ana_rings_per_thread = 8;   // tunable through clb_set_tuning(1, .): 8 (blocks of 8 degrees) or 4, 2, 1 (16 degrees)
 
 template <int R, int KB, int NB>
-static void launch_ana_t(const ShtPlan *p, const double2 *g_recv, int nchunk, cudaStream_t st)
+static void launch_ana_t(const ShtPlan *p, const double2 *g_recv, const double2 *const *gsrc, int nchunk, cudaStream_t st)
 {
   const int warps = g_leg_warps_per_cta;
   dim3 grid((nchunk + warps - 1) / warps, p->nm_loc);
   legendre_analysis_kernel<R, KB, NB><<<grid, 32 * warps, 0, st>>>(
-      g_recv, p->d_rp_gsrc, p->d_g_off, p->d_g_stride, p->d_A, p->d_row_off, p->d_ls_ana, p->d_seed, p->d_cth, p->d_m_loc,
+      g_recv, gsrc, p->d_g_off, p->d_g_stride, p->d_A, p->d_row_off, p->d_ls_ana, p->d_seed, p->d_cth, p->d_m_loc,
       p->d_alm_off, reinterpret_cast<double2 *>(p->d_part), p->alm_total, p->nrp, (int)p->lmax);
 }
 
@@ -381,22 +381,34 @@ int launch_legendre_analysis(ShtPlan *p, const double2 *d_g_recv, double *d_alm_
                              cudaStream_t st)
 {
   if (p->nm_loc == 0) return 0;
-  int R = g_ana_rings_per_thread;
-  while (R > 1 && p->nrp < 32 * R) R = (R > 8) ? 8 : R >> 1;   // small maps: do not leave most of a warp without rings
+  // rings per thread: the tuned value, stepped down through the instantiated set while most of a warp would be left
+  // without rings (small maps); nchunk is derived from the final R only
+  static const int kAnaR[] = {12, 10, 8, 6, 4, 2, 1};
+  int ri = 0;
+  while (kAnaR[ri] != g_ana_rings_per_thread) {
+    if (++ri >= 7) { fprintf(stderr, "calclens_b200: analysis rings per thread %d has no instantiation\n", g_ana_rings_per_thread); abort(); }
+  }
+  while (kAnaR[ri] > 1 && p->nrp < 32 * kAnaR[ri]) ++ri;
+  const int R = kAnaR[ri];
   const int nchunk = (p->nrp + 32 * R - 1) / (32 * R);        // one partial-sum row per warp
   if (!p->d_part || p->ana_nchunk != nchunk) {
     if (p->d_part) cudaFree(p->d_part);
     CLB_CUDA_CHECK(cudaMalloc(&p->d_part, sizeof(double2) * (size_t)nchunk * p->alm_total));
     p->ana_nchunk = nchunk;
   }
+  // fused exchange (clb_sht_plan_set_peers): g is pulled from the ring owners' send buffers only when the caller passes
+  // no receive buffer; a caller that hands in g_recv gets the plain local path
+  const double2 *const *gsrc = d_g_recv ? nullptr : p->d_rp_gsrc;
+  if (!d_g_recv && !gsrc) { fprintf(stderr, "calclens_b200: legendre analysis needs g_recv (no peer buffers are set)\n"); abort(); }
   switch (R) {
-    case 12: launch_ana_t<12, 8, 2>(p, d_g_recv, nchunk, st); break;
-    case 10: launch_ana_t<10, 16, 2>(p, d_g_recv, nchunk, st); break;
-    case 8: launch_ana_t<8, 8, 3>(p, d_g_recv, nchunk, st); break;
-    case 6: launch_ana_t<6, 16, 3>(p, d_g_recv, nchunk, st); break;
-    case 4: launch_ana_t<4, 16, 3>(p, d_g_recv, nchunk, st); break;
-    case 2: launch_ana_t<2, 16, 4>(p, d_g_recv, nchunk, st); break;
-    default: launch_ana_t<1, 16, 4>(p, d_g_recv, nchunk, st); break;
+    case 12: launch_ana_t<12, 8, 2>(p, d_g_recv, gsrc, nchunk, st); break;
+    case 10: launch_ana_t<10, 16, 2>(p, d_g_recv, gsrc, nchunk, st); break;
+    case 8: launch_ana_t<8, 8, 3>(p, d_g_recv, gsrc, nchunk, st); break;
+    case 6: launch_ana_t<6, 16, 3>(p, d_g_recv, gsrc, nchunk, st); break;
+    case 4: launch_ana_t<4, 16, 3>(p, d_g_recv, gsrc, nchunk, st); break;
+    case 2: launch_ana_t<2, 16, 4>(p, d_g_recv, gsrc, nchunk, st); break;
+    case 1: launch_ana_t<1, 16, 4>(p, d_g_recv, gsrc, nchunk, st); break;
+    default: fprintf(stderr, "calclens_b200: analysis rings per thread %d has no instantiation\n", R); abort();
   }
   CLB_CUDA_CHECK(cudaGetLastError());
   dim3 grid((unsigned)((p->lmax + 256) / 256), p->nm_loc);
@@ -416,14 +428,17 @@ int launch_legendre_synthesis(ShtPlan *p, const double *d_alm_re, const double *
                                                (int)p->lmax, p->d_coef);
   CLB_CUDA_CHECK(cudaGetLastError());
   int R = g_syn_rings_per_thread;
-  while (R > 1 && p->nrp < 32 * R) R >>= 1;
+  while (R > 1 && p->nrp < 32 * R) --R;   // 4, 3, 2, 1 are all instantiated
+  // fused exchange: b is pushed into the ring owners' receive buffers only when the caller passes no send buffer
+  double2 *const *bptr = d_b_send ? nullptr : p->d_rp_bptr;
+  if (!d_b_send && !bptr) { fprintf(stderr, "calclens_b200: legendre synthesis needs b_send (no peer buffers are set)\n"); abort(); }
   const int warps = g_leg_warps_per_cta;
   const int nchunk = (p->nrp + R * 32 * warps - 1) / (R * 32 * warps);
   dim3 grid(nchunk, p->nm_loc);
 #define CLB_SYN_LAUNCH(RR)                                                                                           \
   legendre_synthesis_kernel<RR><<<grid, 32 * warps, 0, st>>>(p->d_coef, p->d_row_off, p->d_ls_syn, p->d_seed, p->d_cth, \
                                                               p->d_sth, p->d_m_loc, p->d_b_off, p->d_b_stride, d_b_send, \
-                                                              p->d_rp_bptr, p->nrp, (int)p->lmax)
+                                                              bptr, p->nrp, (int)p->lmax)
   switch (R) {
     case 4: CLB_SYN_LAUNCH(4); break;
     case 3: CLB_SYN_LAUNCH(3); break;

@@ -60,11 +60,6 @@ CLB_HD void paratrans_angle(const double _vec[3], const double _rvec[3], double 
   cospsi = (rephi[0] * ephi[0] + rephi[1] * ephi[1] + rephi[2] * ephi[2]) / norm;
 }
 
-CLB_HD void transport_vec(const double t[2], double cospsi, double sinpsi, double rt[2])   // [rot_paratrans.c:168-169]
-{
-  rt[0] = t[0] * cospsi + t[1] * sinpsi;
-  rt[1] = -1.0 * t[0] * sinpsi + t[1] * cospsi;
-}
 // T' = R^T T R with R = [[c, -s], [s, c]]                              [rot_paratrans.c:251-270]
 CLB_HD void transport_tensor(const double T[2][2], double c, double s, double RT[2][2])
 {
@@ -77,52 +72,13 @@ CLB_HD void transport_tensor(const double T[2][2], double c, double s, double RT
     for (int j = 0; j < 2; ++j) RT[i][j] = rt[i][0] * t1[0][j] + rt[i][1] * t1[1][j];
 }
 
-// Interpolate phi, grad phi, grad grad phi at the ray position from six RING-ordered float maps and accumulate
-// into the ray exactly as the reference's caller does: phi = ., alpha -= grad, U += hessian.
-//                                        [shtpoissonsolve.c:1122-1204 shearinterp_comp, :666-702 caller]
-// maps: m_phi, m_gt, m_gp, m_gtt, m_gtp, m_gpp (same argument order as alm2allmaps_mpi, healpix_shtrans.h:70-72)
-CLB_HD void ray_interp_accumulate(Ray &ray, long order, const float *m_phi, const float *m_gt, const float *m_gp,
-                                  const float *m_gtt, const float *m_gtp, const float *m_gpp)
-{
-  double theta, phi, wgt[4];
-  long pix[4];
-  vec2ang(ray.n, theta, phi);
-  get_interpol(theta, phi, pix, wgt, order);
-  double pot = 0.0, gtheta = 0.0, gphi = 0.0;
-  double ti[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-  const long npix_map = 12L << (2 * order);
-  for (int k = 0; k < 4; ++k) {
-    long p = pix[k];
-    // a ray with a non-finite position would index outside the maps; the reference aborts on a missing cell
-    // (shtpoissonsolve.c:683-689) -- here the gather is kept in bounds and the NaNs stay visible in the ray
-    if (!(p >= 0 && p < npix_map)) p = 0;
-    double vec[3], z, ph, c, s, tvec[2], rtvec[2], T[2][2], RT[2][2];
-    pot += m_phi[p] * wgt[k];
-    ringpix2zphi(p, order, z, ph);
-    zphi2vec(z, ph, vec);
-    paratrans_angle(vec, ray.n, c, s);   // the reference evaluates the same angle twice (vector, then tensor)
-    tvec[0] = m_gt[p]; tvec[1] = m_gp[p];
-    transport_vec(tvec, c, s, rtvec);
-    gtheta += rtvec[0] * wgt[k];
-    gphi += rtvec[1] * wgt[k];
-    T[0][0] = m_gtt[p]; T[0][1] = m_gtp[p]; T[1][0] = m_gtp[p]; T[1][1] = m_gpp[p];
-    transport_tensor(T, c, s, RT);
-    ti[0][0] += RT[0][0] * wgt[k]; ti[0][1] += RT[0][1] * wgt[k];
-    ti[1][0] += RT[1][0] * wgt[k]; ti[1][1] += RT[1][1] * wgt[k];
-  }
-  ray.phi = pot;
-  ray.alpha[0] += -1.0 * gtheta;
-  ray.alpha[1] += -1.0 * gphi;
-  ray.U[0] += ti[0][0]; ray.U[1] += ti[0][1]; ray.U[2] += ti[1][0]; ray.U[3] += ti[1][1];
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// Fast device path.  Same mathematics as the functions above with the per-ring quantities tabulated once per map
-// resolution and the transport angle evaluated without normalising the rotation axis:
+// Device path of the interpolation (shtpoissonsolve.c:1122-1204 shearinterp_comp, :666-702 caller) with the per-ring
+// quantities tabulated once per map resolution and the transport angle evaluated without normalising the rotation axis:
 //   R e = e cos(a) + (u x e) + u (u.e) / (1 + cos(a)),   u = v x v'  (|u| = sin(a)),
 // which is Rodrigues' formula with axis u/|u| (rot_paratrans.c:78-92) after cancelling |u|.  Pixel indices and
 // interpolation weights are formed by exactly the reference's expressions (they must be bit-exact); the transported
-// quantities agree with the line-by-line mirror above to ~1e-15.
+// quantities agree with the reference (oracle) to ~1e-15.
 // ---------------------------------------------------------------------------------------------------------------
 struct RingTab {      // one entry per ring 1 .. 4*Nside-1 (entry 0 unused)
   double theta;       // atan2(sin, cos) of the ring as get_interpol takes it           [healpix_utils.c:986,1001]
@@ -221,13 +177,14 @@ __device__ __forceinline__ void get_interpol_tab(double theta, double phi, long 
   }
 }
 
-__device__ __forceinline__ long ray_interp_accumulate_fast(Ray &ray, long order, const RingTab *__restrict__ tab,
+__device__ __forceinline__ void ray_interp_accumulate_fast(Ray &ray, long order, const RingTab *__restrict__ tab,
                                                            const float *__restrict__ m_phi, const float *__restrict__ m_gt,
                                                            const float *__restrict__ m_gp, const float *__restrict__ m_gtt,
-                                                           const float *__restrict__ m_gtp, const float *__restrict__ m_gpp)
+                                                           const float *__restrict__ m_gtp, const float *__restrict__ m_gpp,
+                                                           long pix[4])
 {
   double theta, phi, wgt[4];
-  long pix[4], ring[2];
+  long ring[2];
   vec2ang(ray.n, theta, phi);
   get_interpol_tab(theta, phi, pix, wgt, order, tab, ring[0], ring[1]);
   const long npix_map = 12L << (2 * order);
@@ -282,7 +239,6 @@ __device__ __forceinline__ long ray_interp_accumulate_fast(Ray &ray, long order,
   ray.alpha[0] += -1.0 * gtheta;
   ray.alpha[1] += -1.0 * gphi;
   ray.U[0] += t00; ray.U[1] += t01; ray.U[2] += t10; ray.U[3] += t11;
-  return pix[0];
 }
 #endif
 
@@ -290,9 +246,10 @@ __device__ __forceinline__ long ray_interp_accumulate_fast(Ray &ray, long order,
 // Plane constants of the A recursion, formed on the host with the reference's expressions (rayprop.c:134-139)
 struct PlaneCoef { double cprev, ccur, cu; };   // (1 - c), c, (wp - wpm1)/wp with c = wpm1 (wp - wpm2) / wp / (wpm1 - wpm2)
 
-// Fast device form of ray_propagate: the same mathematics with the normalisations shared -- |n x a| = |n| |alpha|
+// rayprop_sphere for one ray (rayprop.c:18-189, rot_paratrans.c:17-45): wp = w_{p+1}, wpm1 = w_p (the reference's
+// argument names).  Same mathematics as the reference with the normalisations shared -- |n x a| = |n| |alpha|
 // because a is tangent at n, |theta-hat numerator| = |n| |n_xy| -- and reciprocals multiplied instead of repeated
-// divisions.  Agrees with the line-by-line mirror above to ~1e-15 relative.
+// divisions.  Agrees with the reference (oracle) to ~1e-15 relative.
 __device__ __forceinline__ void ray_propagate_fast(Ray &ray, double wp, double wpm1, const PlaneCoef &pc)
 {
   double np[3], betap[3], Ap[4];
@@ -374,91 +331,6 @@ CLB_HD void ray_propagate_born(Ray &ray, double wp, double wpm1, double wpm2)
             - ((wp - wpm1) / wp) * (ray.U[k]);
   for (int k = 0; k < 4; ++k) { ray.Aprev[k] = ray.A[k]; ray.A[k] = Ap[k]; }
   double r = sqrt(ray.n[0] * ray.n[0] + ray.n[1] * ray.n[1] + ray.n[2] * ray.n[2]);   // rayprop.c:183-187 (both builds)
-  r = wp / r;
-  ray.n[0] *= r; ray.n[1] *= r; ray.n[2] *= r;
-}
-
-// One lens-plane step of one ray: wp = w_{p+1}, wpm1 = w_p, wpm2 = w_{p-1} (the reference's argument names).
-//                                        [rayprop.c:18-189 rayprop_sphere (non-BORNAPPRX branch),
-//                                         rot_paratrans.c:17-45 generate_rotmat_axis_angle_countercw]
-CLB_HD void ray_propagate(Ray &ray, double wp, double wpm1, double wpm2)
-{
-  double np[3], betap[3], Ap[4];
-  double alpha = sqrt(ray.alpha[0] * ray.alpha[0] + ray.alpha[1] * ray.alpha[1]);
-  if (alpha > 0.0) {
-    double phihat[3], thetahat[3], a[3], nxa[3], R[3][3], norm;
-    phihat[0] = -1.0 * ray.n[1]; phihat[1] = ray.n[0]; phihat[2] = 0.0;
-    norm = sqrt(phihat[0] * phihat[0] + phihat[1] * phihat[1]);
-    phihat[0] /= norm; phihat[1] /= norm;
-    thetahat[0] = ray.n[2] * ray.n[0];
-    thetahat[1] = ray.n[2] * ray.n[1];
-    thetahat[2] = -1.0 * (ray.n[0] * ray.n[0] + ray.n[1] * ray.n[1]);
-    norm = sqrt(thetahat[0] * thetahat[0] + thetahat[1] * thetahat[1] + thetahat[2] * thetahat[2]);
-    thetahat[0] /= norm; thetahat[1] /= norm; thetahat[2] /= norm;
-    a[0] = ray.alpha[0] * thetahat[0] + ray.alpha[1] * phihat[0];
-    a[1] = ray.alpha[0] * thetahat[1] + ray.alpha[1] * phihat[1];
-    a[2] = ray.alpha[0] * thetahat[2] + ray.alpha[1] * phihat[2];
-    nxa[0] = ray.n[1] * a[2] - ray.n[2] * a[1];
-    nxa[1] = ray.n[2] * a[0] - ray.n[0] * a[2];
-    nxa[2] = ray.n[0] * a[1] - ray.n[1] * a[0];
-    norm = sqrt(nxa[0] * nxa[0] + nxa[1] * nxa[1] + nxa[2] * nxa[2]);
-    nxa[0] /= norm; nxa[1] /= norm; nxa[2] /= norm;
-    // rotation matrix about nxa by alpha, counter-clockwise
-    double sinangle = sin(alpha), cosangle = cos(alpha);
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) R[i][j] = 0.0;
-    R[0][0] = cosangle; R[1][1] = cosangle; R[2][2] = cosangle;
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) R[i][j] += nxa[i] * nxa[j] * (1.0 - cosangle);
-    R[0][1] -= nxa[2] * sinangle; R[0][2] += nxa[1] * sinangle; R[1][2] -= nxa[0] * sinangle;
-    R[1][0] += nxa[2] * sinangle; R[2][0] -= nxa[1] * sinangle; R[2][1] += nxa[0] * sinangle;
-    for (int i = 0; i < 3; ++i) {
-      betap[i] = R[i][0] * ray.beta[0];
-      betap[i] += R[i][1] * ray.beta[1];
-      betap[i] += R[i][2] * ray.beta[2];
-    }
-    double qa = 1.0;
-    double qb = 2.0 * (ray.n[0] * betap[0] + ray.n[1] * betap[1] + ray.n[2] * betap[2]);
-    double qc = wpm1 * wpm1 - wp * wp;
-    double q = -0.5 * (qb + qb / fabs(qb) * sqrt(qb * qb - 4.0 * qa * qc));
-    double lambda = qc / q;
-    if (lambda < 0.0) lambda = q / qa;
-    np[0] = ray.n[0] + betap[0] * lambda;
-    np[1] = ray.n[1] + betap[1] * lambda;
-    np[2] = ray.n[2] + betap[2] * lambda;
-  } else {
-    betap[0] = ray.beta[0]; betap[1] = ray.beta[1]; betap[2] = ray.beta[2];
-    np[0] = ray.n[0] / wpm1 * wp;
-    np[1] = ray.n[1] / wpm1 * wp;
-    np[2] = ray.n[2] / wpm1 * wp;
-  }
-  for (int n = 0; n < 2; ++n)
-    for (int m = 0; m < 2; ++m)
-      Ap[m + 2 * n] = (1.0 - wpm1 * (wp - wpm2) / wp / (wpm1 - wpm2)) * ray.Aprev[m + 2 * n]
-                      + (wpm1 * (wp - wpm2) / wp / (wpm1 - wpm2)) * ray.A[m + 2 * n]
-                      - ((wp - wpm1) / wp) * (ray.U[0 + 2 * n] * ray.A[m + 2 * 0] + ray.U[1 + 2 * n] * ray.A[m + 2 * 1]);
-  double c, s, T[2][2], RT[2][2];
-#if defined(__CUDA_ARCH__)
-  {
-    const double i0 = 1.0 / sqrt(ray.n[0] * ray.n[0] + ray.n[1] * ray.n[1] + ray.n[2] * ray.n[2]);
-    const double i1 = 1.0 / sqrt(np[0] * np[0] + np[1] * np[1] + np[2] * np[2]);
-    const double v0[3] = {ray.n[0] * i0, ray.n[1] * i0, ray.n[2] * i0}, v1[3] = {np[0] * i1, np[1] * i1, np[2] * i1};
-    const double inv_norm = 1.0 / sqrt((1.0 - v1[2]) * (1.0 + v1[2]) * (1.0 - v0[2]) * (1.0 + v0[2]));
-    paratrans_angle_unit(v0, v1, inv_norm, c, s);
-  }
-#else
-  paratrans_angle(ray.n, np, c, s);
-#endif
-  // Aprev <- transport(A), A <- transport(Ap)
-  T[0][0] = ray.A[0]; T[0][1] = ray.A[1]; T[1][0] = ray.A[2]; T[1][1] = ray.A[3];
-  transport_tensor(T, c, s, RT);
-  ray.Aprev[0] = RT[0][0]; ray.Aprev[1] = RT[0][1]; ray.Aprev[2] = RT[1][0]; ray.Aprev[3] = RT[1][1];
-  T[0][0] = Ap[0]; T[0][1] = Ap[1]; T[1][0] = Ap[2]; T[1][1] = Ap[3];
-  transport_tensor(T, c, s, RT);
-  ray.A[0] = RT[0][0]; ray.A[1] = RT[0][1]; ray.A[2] = RT[1][0]; ray.A[3] = RT[1][1];
-  ray.n[0] = np[0]; ray.n[1] = np[1]; ray.n[2] = np[2];
-  ray.beta[0] = betap[0]; ray.beta[1] = betap[1]; ray.beta[2] = betap[2];
-  double r = sqrt(ray.n[0] * ray.n[0] + ray.n[1] * ray.n[1] + ray.n[2] * ray.n[2]);
   r = wp / r;
   ray.n[0] *= r; ray.n[1] *= r; ray.n[2] *= r;
 }

@@ -8,6 +8,7 @@
 #include "sht_internal.cuh"
 #include "raymath.cuh"
 #include <algorithm>
+#include <mutex>
 
 namespace clb {
 
@@ -43,18 +44,23 @@ __global__ void ring_table_kernel(RingTab *__restrict__ tab, long order)
   tab[ring] = t;
 }
 
+// (built once per (device, order) and kept for the life of the process; the build is synchronised, so any stream may
+// use the table afterwards)
 static const RingTab *ring_table(long order, cudaStream_t st)
 {
   static RingTab *cache[16][32] = {};
+  static std::mutex mu;
   int dev = 0;
   CLB_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 16 || order < 0 || order >= 32) { fprintf(stderr, "calclens_b200: ring_table(%d, %ld)\n", dev, order); abort(); }
+  std::lock_guard<std::mutex> lock(mu);
   if (!cache[dev][order]) {
     const long n = 4L << order;
     RingTab *t = nullptr;
     CLB_CUDA_CHECK(cudaMalloc(&t, sizeof(RingTab) * n));
     ring_table_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(t, order);
     CLB_CUDA_CHECK(cudaGetLastError());
+    CLB_CUDA_CHECK(cudaStreamSynchronize(st));
     cache[dev][order] = t;
   }
   return cache[dev][order];
@@ -147,10 +153,16 @@ ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab 
         ray.U[0] = 0.0; ray.U[1] = 0.0; ray.U[2] = 0.0; ray.U[3] = 0.0;
       }
       if (mode & 2) {
-        const long p0 = ray_interp_accumulate_fast(ray, order, tab, maps.p[0], maps.p[1], maps.p[2], maps.p[3], maps.p[4], maps.p[5]);
-        // sharded runs: the stencil must lie inside the part of the sky this rank received (the reference aborts on a
-        // missing map cell, shtpoissonsolve.c:683-689; here the flag is raised and the host aborts)
-        if (need && !(need[ring2nest(p0, order) >> coarse_shift] & rank_bit)) atomicOr(err, 1);
+        long px[4];
+        ray_interp_accumulate_fast(ray, order, tab, maps.p[0], maps.p[1], maps.p[2], maps.p[3], maps.p[4], maps.p[5], px);
+        // sharded runs: every pixel of the stencil must lie inside the part of the sky this rank received (the reference
+        // aborts on a missing map cell, shtpoissonsolve.c:683-689; here the flag is raised and the host aborts)
+        if (need) {
+          unsigned ok = rank_bit;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ok &= need[ring2nest(px[k], order) >> coarse_shift];
+          if (!ok) atomicOr(err, 1);
+        }
       }
       if (mode & 4) {
         if (mode & 8) ray_propagate_born(ray, wp, wpm1, wpm2);
@@ -194,13 +206,7 @@ int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long 
   RayMaps m;
   for (int k = 0; k < 6; ++k) m.p[k] = d_maps ? d_maps[k] : nullptr;
   const long ntiles = (nrays + kRayThreads - 1) / kRayThreads;
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    CLB_CUDA_CHECK(cudaGetDevice(&dev));
-    CLB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  const long nblocks = std::min<long>(ntiles, (long)sms * 4);
+  const long nblocks = std::min<long>(ntiles, (long)sm_count() * 4);
   const RingTab *tab = (mode & 2) ? ring_table(order, st) : nullptr;
   if (d_sum6) CLB_CUDA_CHECK(cudaMemsetAsync(d_sum6, 0, 6 * sizeof(double), st));
   if (d_need && (coarse_order > order || !d_err)) d_need = nullptr;
@@ -264,7 +270,7 @@ int launch_ray_summary(const Ray *d_rays, long nrays, double *d_out6, cudaStream
 {
   CLB_CUDA_CHECK(cudaMemsetAsync(d_out6, 0, 6 * sizeof(double), st));
   if (nrays <= 0) return 0;
-  ray_summary_kernel<<<148 * 4, 256, 0, st>>>(d_rays, nrays, d_out6);
+  ray_summary_kernel<<<sm_count() * 4, 256, 0, st>>>(d_rays, nrays, d_out6);
   CLB_CUDA_CHECK(cudaGetLastError());
   return 1;
 }
@@ -323,7 +329,7 @@ __global__ void deposit_ngp_kernel(const float *__restrict__ pos, const float *_
 int launch_deposit_ngp(const float *d_pos, const float *d_mass, long nparts, long order, float *d_ringmap, cudaStream_t st)
 {
   if (nparts <= 0) return 0;
-  const long blocks = std::min<long>((nparts + 255) / 256, 148L * 16);
+  const long blocks = std::min<long>((nparts + 255) / 256, (long)sm_count() * 16);
   deposit_ngp_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_pos, d_mass, nparts, order, d_ringmap);
   CLB_CUDA_CHECK(cudaGetLastError());
   return 1;
@@ -360,10 +366,25 @@ void launch_healpix_index(int what, long order, long n, const long *in, const do
   healpix_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(what, order, n, in, th, ph, out);
   CLB_CUDA_CHECK(cudaGetLastError());
 }
-void launch_healpix_interpol(long order, long n, const double *vec, long *pix, double *wgt, cudaStream_t st)
+// the stencil exactly as ray_step_kernel forms it: vec2ang + get_interpol_tab (tabulated ring colatitudes, reciprocal
+// weights) -- exposed so the bit-exactness tests exercise the hot kernel's own index path
+__global__ void ray_stencil_kernel(long order, long n, const double *__restrict__ vec, const RingTab *__restrict__ tab,
+                                   long *__restrict__ pix, double *__restrict__ wgt)
+{
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v[3] = {vec[3 * i], vec[3 * i + 1], vec[3 * i + 2]}, theta, phi, w[4];
+  long p[4], ra, rb;
+  vec2ang(v, theta, phi);
+  get_interpol_tab(theta, phi, p, w, order, tab, ra, rb);
+  for (int k = 0; k < 4; ++k) { pix[4 * i + k] = p[k]; wgt[4 * i + k] = w[k]; }
+}
+
+void launch_healpix_interpol(long order, long n, const double *vec, long *pix, double *wgt, int use_table, cudaStream_t st)
 {
   if (n <= 0) return;
-  healpix_interpol_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(order, n, vec, pix, wgt);
+  if (use_table) ray_stencil_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(order, n, vec, ring_table(order, st), pix, wgt);
+  else healpix_interpol_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(order, n, vec, pix, wgt);
   CLB_CUDA_CHECK(cudaGetLastError());
 }
 

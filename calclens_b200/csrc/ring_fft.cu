@@ -838,16 +838,7 @@ static double2 *fft_scratch(FftTables *t, size_t bytes)
   }
   return t->d_scratch;
 }
-static int scratch_ctas()
-{
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    CLB_CUDA_CHECK(cudaGetDevice(&dev));
-    CLB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  return sms * 2;
-}
+static int scratch_ctas() { return sm_count() * 2; }
 
 void fft_tables_destroy(ShtPlan *p)
 {
@@ -1080,7 +1071,7 @@ int launch_load_density(const ShtPlan *p, const float *src, float *dst, float pr
   const bool on_device = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
   cudaGetLastError();
   const int nslots = 2 * p->nrp_loc;
-  const int grid = on_device ? std::min(nslots, 148 * 8) : std::min(nslots, 96);   // PCIe needs few CTAs, HBM many
+  const int grid = on_device ? std::min(nslots, sm_count() * 8) : std::min(nslots, 96);   // PCIe needs few CTAs, HBM many
   load_density_kernel<<<grid, 512, 0, st>>>(src, dst, geom_of(p), p->d_rp_loc, nslots, premul, densmul, backdens);
   CLB_CUDA_CHECK(cudaGetLastError());
   return 1;
@@ -1104,7 +1095,9 @@ __global__ void ring_broadcast_kernel(MapPtrs local, PeerMaps peers, int nranks,
     unsigned m = 0xffu;
     if (need) {
       const long pix = start + 4L * i;
-      m = need[ring2nest(pix, order) >> coarse_shift] | need[ring2nest(pix + 3, order) >> coarse_shift];
+      // four consecutive ring pixels can touch up to four coarse cells (corner cuts): OR over all of them
+      m = need[ring2nest(pix, order) >> coarse_shift] | need[ring2nest(pix + 1, order) >> coarse_shift] |
+          need[ring2nest(pix + 2, order) >> coarse_shift] | need[ring2nest(pix + 3, order) >> coarse_shift];
     }
     m &= ~(1u << rank);
     if (!m) continue;

@@ -18,6 +18,17 @@
 
 namespace clb {
 
+// SM count of the current device (cached per device)
+inline int sm_count()
+{
+  static int cache[64] = {};
+  int dev = 0;
+  CLB_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return 148;
+  if (!cache[dev]) CLB_CUDA_CHECK(cudaDeviceGetAttribute(&cache[dev], cudaDevAttrMultiProcessorCount, dev));
+  return cache[dev];
+}
+
 constexpr int kSeedAlign = 16;    // Legendre l-blocks start at m + k*kSeedAlign
 constexpr int kRowPad = 64;       // zero padding at the end of every (m, l) table row
 constexpr int kNoStart = 0x7fffffff;

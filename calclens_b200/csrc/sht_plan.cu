@@ -162,6 +162,10 @@ ShtPlan *sht_plan_create(long order, long lmax, const double *ring_weights, int 
   p->rp_owner.assign(nrp, 0); p->m_owner.assign(lmax + 1, 0);
   for (int rp = 0; rp < nrp; ++rp) p->rp_owner[rp] = rp_owner ? rp_owner[rp] : 0;
   for (long m = 0; m <= lmax; ++m) p->m_owner[m] = m_owner ? m_owner[m] : 0;
+  for (int rp = 0; rp < nrp; ++rp)
+    if (p->rp_owner[rp] < 0 || p->rp_owner[rp] >= nranks) { fprintf(stderr, "calclens_b200: rp_owner[%d] = %d outside [0, %d)\n", rp, p->rp_owner[rp], nranks); abort(); }
+  for (long m = 0; m <= lmax; ++m)
+    if (p->m_owner[m] < 0 || p->m_owner[m] >= nranks) { fprintf(stderr, "calclens_b200: m_owner[%ld] = %d outside [0, %d)\n", m, p->m_owner[m], nranks); abort(); }
   p->nrp_of_rank.assign(nranks, 0); p->nm_of_rank.assign(nranks, 0);
   std::vector<int> rp_local_idx(nrp), m_local_idx(lmax + 1);
   for (int rp = 0; rp < nrp; ++rp) rp_local_idx[rp] = p->nrp_of_rank[p->rp_owner[rp]]++;

@@ -8,12 +8,14 @@ rays are split into contiguous NEST ranges, i.e. compact sky domains (cf. loadba
 reference's ring->domain shuffle with halo cells (map_shuffle.c) every rank receives the six full derivative maps, so
 rays never miss a map cell however far they have been deflected.
 
-Two exchange back ends:
-* fused (default on one NVLink/NVSwitch node): the receive buffers of all ranks are mapped into every process (CUDA
-  IPC) and the producing kernels -- ring-FFT epilogue, Legendre-synthesis epilogue, map broadcast -- store straight
-  into the consumer's buffers; the only collectives left are stream-ordered barriers between producer and consumer.
-* NCCL: one all-to-all-v per transpose and an all-reduce of the maps (disjoint ring sets); used when peer mapping is
-  unavailable, and by the CPU (gloo) tests of the exchange layout.
+The driver itself lives below the C ABI (``clb_solver_*``, csrc/solver.cu): this class is a thin caller of it, so a C
+host (CALCLENS through shim/calclens_b200_shim.c) reaches exactly the same code.  Two exchange back ends:
+* fused (default on one NVLink/NVSwitch node, the C solver): the buffers of all ranks are mapped into every process
+  (CUDA IPC) and the producing kernels -- Legendre-synthesis epilogue, map broadcast -- store straight into the
+  consumer's buffers (the Legendre analysis pulls g from the ring owners); stages are ordered by a device-side barrier
+  over peer memory, no communication library on the per-plane path.
+* NCCL (``fused=False``; Python, over the ``_dev`` stage API): one all-to-all-v per transpose and an all-reduce of the
+  maps (disjoint ring sets); the comparison arm, and the fallback when peer mapping is unavailable.
 """
 import ctypes as C
 import math
@@ -88,154 +90,137 @@ def density_scalings(order, part_mass, densfact, backdens):
     return (np.float32(part_mass / MASS_SCALE), np.float32(densfact / area * MASS_SCALE), np.float32(backdens))
 
 
+class _SolverPlan(sht.HEALPixSHTPlan):
+    """View of the plan owned by a C solver (not destroyed from Python)."""
+
+    def __init__(self, lib, handle, order, lmax, nranks, rank, device):
+        self.lib = lib
+        self.order, self.lmax = int(order), int(lmax)
+        self.nside = sht.order2nside(order)
+        self.npix = sht.order2npix(order)
+        self.nranks, self.rank = int(nranks), int(rank)
+        self.device = device
+        self.ring_weights = None
+        self._h = handle
+        self._query()
+
+    def destroy(self):
+        self._h = None
+
+
+_ALLGATHER_T = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p)
+
+
 class LensPlaneSolver:
     """One rank's share of the per-plane hot path.  ``dist_group`` = None for a single GPU, otherwise an initialised
-    torch.distributed process group (NCCL) with one rank per GPU."""
+    torch.distributed process group with one rank per GPU (used for bootstrap only on the fused path)."""
 
     def __init__(self, sht_order, lmax=None, ray_order=None, ring_weights=None, dist_group=None, device=None, fused=True,
-                 halo_deg=1.0, overlap_rays=False):
+                 halo_deg=1.0, allgather=None, nranks=None, rank=None, rp_owner=None, m_owner=None):
         import torch.distributed as dist
         self.dist = dist if dist_group is not None else None
         self.group = dist_group
-        self.nranks = dist.get_world_size(dist_group) if dist_group is not None else 1
-        self.rank = dist.get_rank(dist_group) if dist_group is not None else 0
-        self.plan = sht.HEALPixSHTPlan(sht_order, lmax, ring_weights, self.nranks, self.rank, device=device)
-        self.device = self.plan.device
-        self.lib = self.plan.lib
+        if dist_group is not None:
+            self.nranks, self.rank = dist.get_world_size(dist_group), dist.get_rank(dist_group)
+        else:
+            self.nranks, self.rank = int(nranks or 1), int(rank or 0)   # (emulated ranks: allgather= a Python callable)
+        self.lib = _lib.load()
+        if device is not None:
+            torch.cuda.set_device(device)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.lib.clb_set_device(self.device.index)
         self.order = int(sht_order)
-        self.npix = self.plan.npix
+        self.lmax = int(sht.order2lmax(self.order) if lmax is None else lmax)
+        self.npix = sht.order2npix(self.order)
         self.ray_order = self.order if ray_order is None else int(ray_order)
+        self.halo_deg = float(halo_deg)
+        self.coarse_order = 5
+        self.rays = None
+        self.nrays = 0
+        self.first_nest = 0
+        self.fused = False
+        self._need = None
+        self._cs = None
+        self._next = None
+        self._timing = False
+        w = None if ring_weights is None else np.ascontiguousarray(ring_weights, dtype=np.float64)
+        ro = None if rp_owner is None else np.ascontiguousarray(rp_owner, dtype=np.int32)
+        mo = None if m_owner is None else np.ascontiguousarray(m_owner, dtype=np.int32)
+        if self.nranks == 1 or fused:
+            gather = allgather
+            if gather is None and self.nranks > 1:
+                def gather(data):
+                    out = [None] * self.nranks
+                    self.dist.all_gather_object(out, data, group=self.group)
+                    return out
+
+            def _cb(send, recv, nbytes, _ctx):
+                parts = gather(C.string_at(send, nbytes))
+                C.memmove(recv, b"".join(parts), nbytes * self.nranks)
+            self._cb = _ALLGATHER_T(_cb)   # keep the trampoline alive as long as the solver
+            self._cs = self.lib.clb_solver_create(self.order, self.lmax, self.ray_order, None if w is None else w.ctypes.data,
+                                                  self.nranks, self.rank, None if ro is None else ro.ctypes.data,
+                                                  None if mo is None else mo.ctypes.data,
+                                                  self._cb if self.nranks > 1 else _ALLGATHER_T(), None, self.halo_deg)
+        if self._cs:
+            q = lambda k: self.lib.clb_solver_query(self._cs, k)
+            ptr = lambda k: self.lib.clb_solver_ptr(self._cs, k)
+            self.fused = bool(q(2))
+            self.plan = _SolverPlan(self.lib, ptr(4), self.order, self.lmax, self.nranks, self.rank, self.device)
+            self.maps = self._dev_view(ptr(0), (6, self.npix), torch.float32)
+            self.alm_re = self._dev_view(ptr(2), (max(self.plan.Nlm, 1),), torch.float64)
+            self.alm_im = self._dev_view(ptr(3), (max(self.plan.Nlm, 1),), torch.float64)
+            self.summary = self._dev_view(ptr(8), (6,), torch.float64)
+            if q(4):
+                self._need = self._dev_view(ptr(5), (12 << (2 * self.coarse_order),), torch.uint8)
+                self.need_fraction = q(5) * 1e-6
+            self.host_barriers = bool(q(6))
+            return
+        # ---- NCCL exchange over the _dev stage API (fused=False, or peer mapping unavailable) ----
+        self.plan = sht.HEALPixSHTPlan(sht_order, self.lmax, w, self.nranks, self.rank, rp_owner=ro, m_owner=mo, device=device)
         p = self.plan
         f64 = dict(dtype=torch.float64, device=self.device)
         self.g_send = torch.empty(2 * max(p.g_send_total, 1), **f64)
         self.b_send = torch.empty(2 * max(p.b_send_total, 1), **f64)
-        if self.nranks > 1:
-            self.g_recv = torch.empty(2 * max(p.g_recv_total, 1), **f64)
-            self.b_recv = torch.empty(2 * max(p.b_recv_total, 1), **f64)
-        else:
-            self.g_recv, self.b_recv = self.g_send, self.b_send
+        self.g_recv = torch.empty(2 * max(p.g_recv_total, 1), **f64)
+        self.b_recv = torch.empty(2 * max(p.b_recv_total, 1), **f64)
         self.alm_re = torch.empty(max(p.Nlm, 1), **f64)
         self.alm_im = torch.empty(max(p.Nlm, 1), **f64)
-        self.maps = None
         self.summary = torch.zeros(6, **f64)
-        self._dens = [torch.zeros(self.npix, dtype=torch.float32, device=self.device) for _ in range(2)]
-        self._copy_stream = torch.cuda.Stream(device=self.device, priority=-1)   # runs behind the compute kernels, gets SM slots first
-        self._staged = None        # (host map, scalings, buffer index, ready event) of a prefetched plane
-        self._dens_free = [None, None]   # event after the last kernel that read each density buffer
-        # overlap_rays: the ray kernel of plane p runs on its own stream while the next plane's density load, ring FFT and
-        # Legendre analysis proceed (the SHT of plane p+1 does not depend on the rays); the next plane's ring synthesis,
-        # which overwrites the maps, waits for it.  The ray kernel (128 registers) fits beside two Legendre CTAs on an SM.
-        self.overlap_rays = bool(overlap_rays)
-        self._ray_stream = torch.cuda.Stream(device=self.device)
-        self._rays_done = None
-        self.ray_events = []
-        self.fused = False
-        self.halo_deg = float(halo_deg)
-        self.coarse_order = 5
-        self._need = None          # device mask of the coarse cells each rank needs (fused exchange only)
-        self._err = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self._peer_bufs = []
-        if self.nranks > 1 and fused:
-            self._setup_peer_exchange()
-        if self.maps is None:
-            self.maps = torch.zeros((6, self.npix), dtype=torch.float32, device=self.device)
-        self.rays = None
-        self.nrays = 0
-        self.first_nest = 0
+        self._dens = torch.zeros(self.npix, dtype=torch.float32, device=self.device)
+        self.maps = torch.zeros((6, self.npix), dtype=torch.float32, device=self.device)
 
-    # ---- fused exchange over peer memory ----
     def _dev_view(self, ptr, shape, dtype):
         """torch tensor over device memory owned by the library (CUDA array interface, zero copy)."""
         class _Holder:
             pass
         h = _Holder()
-        h.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": {torch.float64: "<f8", torch.float32: "<f4"}[dtype],
-                                      "data": (int(ptr), False), "version": 2, "strides": None}
+        ts = {torch.float64: "<f8", torch.float32: "<f4", torch.uint8: "|u1"}[dtype]
+        h.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": ts, "data": (int(ptr), False), "version": 2,
+                                      "strides": None}
         return torch.as_tensor(h, device=self.device)
 
-    def _setup_peer_exchange(self):
-        """Allocate the receive buffers as peer-mappable memory, exchange the IPC handles through the process group
-        and hand the peer pointers to the plan (clb_sht_plan_set_peers).  Falls back to the NCCL exchange, on all
-        ranks together, if any mapping fails."""
-        p, L = self.plan, self.lib
-        sizes = [16 * max(p.g_send_total, 1), 16 * max(p.b_recv_total, 1), 4 * 6 * self.npix]   # g send, b receive, maps
-        own = [L.clb_peer_alloc(n) for n in sizes]
-        handles = []
-        for ptr in own:
-            buf = C.create_string_buffer(64)
-            L.clb_peer_export(ptr, buf)
-            handles.append(buf.raw)
-        gathered = [None] * self.nranks
-        self.dist.all_gather_object(gathered, handles, group=self.group)
-        peers = [[None] * 3 for _ in range(self.nranks)]
-        ok = 1
-        for q in range(self.nranks):
-            for k in range(3):
-                if q == self.rank:
-                    peers[q][k] = own[k]
-                else:
-                    ptr = L.clb_peer_import(C.create_string_buffer(gathered[q][k], 64))
-                    if not ptr:
-                        ok = 0
-                    peers[q][k] = ptr
-        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
-        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)
-        self._peer_bufs = (own, peers)
-        if int(flag.item()) == 0:
-            return   # stay on the NCCL path (buffers are simply not used)
-        g_arr = (C.c_void_p * self.nranks)(*[peers[q][0] for q in range(self.nranks)])
-        b_arr = (C.c_void_p * self.nranks)(*[peers[q][1] for q in range(self.nranks)])
-        L.clb_sht_plan_set_peers(p._h, g_arr, b_arr)
-        self._peer_maps = (C.c_void_p * (6 * self.nranks))(*[peers[q][2] + 4 * self.npix * k for q in range(self.nranks) for k in range(6)])
-        self.g_send = self._dev_view(own[0], (2 * max(p.g_send_total, 1),), torch.float64)
-        self.g_recv = None         # analysis reads g from the ring owners' send buffers
-        self.b_recv = self._dev_view(own[1], (2 * max(p.b_recv_total, 1),), torch.float64)
-        self.maps = self._dev_view(own[2], (6, self.npix), torch.float32)
-        self.maps.zero_()
-        self.b_send = None         # synthesis stores b into the ring owners' receive buffers
-        self._tiny = torch.zeros(1, dtype=torch.float32, device=self.device)
-        # halo-limited map broadcast: a pixel goes to the ranks whose ray domain, grown by halo_deg, can reach it.
-        # Cells of a coarse NEST grid stand in for the reference's halo bundle cells (raytrace_utils.c:116-161); the
-        # margin adds two coarse cell radii (a HEALPix pixel's radius is < 1.2 x its mean spacing).
-        if self.halo_deg > 0 and self.order >= self.coarse_order:
-            spacing = math.sqrt(4.0 * math.pi / (12 << (2 * self.coarse_order)))
-            margin = math.radians(self.halo_deg) + 2.0 * 1.2 * spacing
-            mask = np.zeros(12 << (2 * self.coarse_order), dtype=np.uint8)
-            L.clb_domain_masks(self.ray_order, self.nranks, self.coarse_order, margin, mask.ctypes.data)
-            self._need = torch.from_numpy(mask).to(self.device)
-            self.need_fraction = float(np.unpackbits(mask[:, None], axis=1)[:, -self.nranks:].sum()) / (mask.size * self.nranks)
-        self.fused = True
-        self.dist.barrier(group=self.group)
-
     def close(self):
-        """Release the peer mappings and the library-owned buffers (after every rank has stopped using them)."""
-        self._wait_rays()
-        if self._peer_bufs:
+        """Release the solver (collective on multi-rank solvers: every rank must call it)."""
+        if self._cs:
             torch.cuda.synchronize()
-            if self.nranks > 1:
-                self.dist.barrier(group=self.group)
-            own, peers = self._peer_bufs
-            self.maps = self.g_send = self.b_recv = None
-            for q in range(self.nranks):
-                if q != self.rank:
-                    for ptr in peers[q]:
-                        if ptr:
-                            self.lib.clb_peer_release(ptr)
-            if self.nranks > 1:
-                self.dist.barrier(group=self.group)
-            for ptr in own:
-                self.lib.clb_peer_free(ptr)
-            self._peer_bufs = []
+            self.maps = self.alm_re = self.alm_im = self.summary = self._need = self.rays = None
+            self.plan.destroy()
+            self.lib.clb_solver_destroy(self._cs)
+            self._cs = None
             self.fused = False
 
-    def _stream_barrier(self):
-        """All ranks' work enqueued so far has completed before anything enqueued afterwards starts (stream ordered)."""
-        self.dist.all_reduce(self._tiny, group=self.group)
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
 
     # ---- rays ----
     def init_rays(self, binL_2):
         """alloc_rays + init_rays (raytrace_utils.c:265-347) for this rank's contiguous NEST range."""
-        self._wait_rays()
+        if self._cs:
+            self.nrays = self.lib.clb_solver_init_rays(self._cs, float(binL_2), self._stream())
+            self.first_nest = self.lib.clb_solver_query(self._cs, 1)
+            self.rays = self._dev_view(self.lib.clb_solver_ptr(self._cs, 1), (max(self.nrays, 1) * 176,), torch.uint8)
+            return self.nrays
         nray_tot = 12 << (2 * self.ray_order)
         lo = (nray_tot * self.rank) // self.nranks
         hi = (nray_tot * (self.rank + 1)) // self.nranks
@@ -244,171 +229,126 @@ class LensPlaneSolver:
         self.lib.clb_ray_init_dev(self.rays.data_ptr(), self.nrays, lo, self.ray_order, float(binL_2), self._stream())
         return self.nrays
 
-    def _stream(self):
-        return torch.cuda.current_stream().cuda_stream
+    def set_timing(self, on=True):
+        """Per-stage CUDA events inside the C solver (bench.py)."""
+        self._timing = bool(on)
+        if self._cs:
+            self.lib.clb_solver_set_timing(self._cs, 1 if on else 0)
+
+    def stage_ms(self):
+        out = (C.c_double * 9)()
+        self.lib.clb_solver_stage_ms(self._cs, out)
+        return list(out)
 
     def _all_to_all(self, send, recv, send_counts, recv_counts):
-        if self.nranks == 1:
-            return send
         self.dist.all_to_all_single(recv[:2 * sum(recv_counts)], send[:2 * sum(send_counts)],
                                     output_split_sizes=[2 * c for c in recv_counts],
                                     input_split_sizes=[2 * c for c in send_counts], group=self.group)
         return recv
 
-    # ---- the SHT Poisson solve: counts map in self.maps[0] -> six derivative maps in self.maps ----
-    def load_density(self, counts_map, premul, densmul, backdens, dst=None):
+    # ---- the SHT Poisson solve: counts map -> six derivative maps in self.maps ----
+    def load_density(self, counts_map, premul, densmul, backdens):
         """Scale this rank's rings of a full-sky count map (device tensor or pinned host tensor, RING float32) into the
         density buffer: shtpoissonsolve.c:342-502 for the raw-map input path."""
         assert counts_map.dtype == torch.float32 and counts_map.numel() == self.npix and counts_map.is_contiguous()
+        if self._cs:
+            self.lib.clb_solver_load_density(self._cs, counts_map.data_ptr(), float(premul), float(densmul), float(backdens), self._stream())
+            return None
         assert counts_map.is_cuda or counts_map.is_pinned(), "host maps must be pinned (they are read by the GPU directly)"
-        dst = self._dens[0] if dst is None else dst
-        self.lib.clb_load_density_dev(self.plan._h, counts_map.data_ptr(), dst.data_ptr(), float(premul), float(densmul),
+        self.lib.clb_load_density_dev(self.plan._h, counts_map.data_ptr(), self._dens.data_ptr(), float(premul), float(densmul),
                                       float(backdens), self._stream())
-        return dst
+        return self._dens
 
-    def solve(self, density=None, mark=None):
-        """density map (this rank's rings valid; default: the buffer load_density filled) -> six derivative maps.
-        ``mark(name)`` (optional) is called after each stage has been enqueued (bench.py records CUDA events there)."""
-        mark = mark or (lambda name: None)
-        p = self.plan
-        dens = self._dens[0] if density is None else density
-        if self.fused:
-            # producers store into the consumers' buffers over NVLink; barriers order producer and consumer stages
-            self._stream_barrier()   # every rank is done with the previous plane's g, b and maps
-            p.ring_analysis(dens, self.g_send); mark("fft_analysis")
-            self._stream_barrier(); mark("a2a_g")
-            self.lib.clb_legendre_analysis_dev(p._h, None, self.alm_re.data_ptr(), self.alm_im.data_ptr(), 1, self._stream())
-            mark("legendre_analysis")
-            self.lib.clb_legendre_synthesis_dev(p._h, self.alm_re.data_ptr(), self.alm_im.data_ptr(), None, self._stream())
-            mark("legendre_synthesis")
-            self._wait_rays()        # the previous plane's ray kernel still reads the maps (every rank, before the barrier)
-            self._stream_barrier(); mark("a2a_b")
-            p.ring_synthesis(self.b_recv, self.maps); mark("fft_synthesis")
-            ptrs = (C.c_void_p * 6)(*[self.maps[k].data_ptr() for k in range(6)])
-            self.lib.clb_maps_broadcast_dev(p._h, ptrs, self._peer_maps, None if self._need is None else self._need.data_ptr(),
-                                            self.coarse_order, self._stream())
-            self._stream_barrier(); mark("map_allreduce")
+    def solve(self, density=None):
+        """density map (this rank's rings valid; default: the buffer load_density filled) -> six derivative maps."""
+        if self._cs:
+            self.lib.clb_solver_solve(self._cs, None if density is None else density.data_ptr(), self._stream())
             return self.maps
-        p.ring_analysis(dens, self.g_send); mark("fft_analysis")
-        g = self._all_to_all(self.g_send, self.g_recv, p.counts[0], p.counts[1]); mark("a2a_g")
-        p.legendre_analysis(g, self.alm_re, self.alm_im, poisson_filter=True); mark("legendre_analysis")
-        p.legendre_synthesis(self.alm_re, self.alm_im, self.b_send); mark("legendre_synthesis")
-        b = self._all_to_all(self.b_send, self.b_recv, p.counts[2], p.counts[3]); mark("a2a_b")
-        self._wait_rays()
-        if self.nranks > 1:
-            self.maps.zero_()
-        p.ring_synthesis(b, self.maps); mark("fft_synthesis")
-        if self.nranks > 1:
-            self.dist.all_reduce(self.maps, group=self.group)   # disjoint ring sets: x + 0 is exact
-        mark("map_allreduce")
+        p = self.plan
+        dens = self._dens if density is None else density
+        p.ring_analysis(dens, self.g_send)
+        g = self._all_to_all(self.g_send, self.g_recv, p.counts[0], p.counts[1])
+        p.legendre_analysis(g, self.alm_re, self.alm_im, poisson_filter=True)
+        p.legendre_synthesis(self.alm_re, self.alm_im, self.b_send)
+        b = self._all_to_all(self.b_send, self.b_recv, p.counts[2], p.counts[3])
+        self.maps.zero_()
+        p.ring_synthesis(b, self.maps)
+        self.dist.all_reduce(self.maps, group=self.group)   # disjoint ring sets: x + 0 is exact
         return self.maps
 
-    def _wait_rays(self):
-        """The current stream waits for a ray kernel still running on the ray stream (overlap_rays)."""
-        if self._rays_done is not None:
-            torch.cuda.current_stream().wait_event(self._rays_done)
-            self._rays_done = None
-
     def alm2allmaps(self, alm_re, alm_im):
-        """alm2allmaps_mpi over the ranks of the group: local alm (this rank's m) -> the six full maps on every rank."""
-        p = self.plan
-        self._wait_rays()
-        if self.fused:
-            self._stream_barrier()
-            self.lib.clb_legendre_synthesis_dev(p._h, alm_re.data_ptr(), alm_im.data_ptr(), None, self._stream())
-            self._stream_barrier()
-            p.ring_synthesis(self.b_recv, self.maps)
-            ptrs = (C.c_void_p * 6)(*[self.maps[k].data_ptr() for k in range(6)])
-            self.lib.clb_maps_broadcast_dev(p._h, ptrs, self._peer_maps, None if self._need is None else self._need.data_ptr(),
-                                            self.coarse_order, self._stream())
-            self._stream_barrier()
+        """alm2allmaps_mpi over the ranks of the group: local alm (this rank's m) -> the six maps (fused exchange with a
+        halo: every rank holds its own rings plus the part of the sky its rays can reach; otherwise full maps)."""
+        if self._cs:
+            self.lib.clb_solver_alm2allmaps(self._cs, alm_re.data_ptr(), alm_im.data_ptr(), self._stream())
             return self.maps
+        p = self.plan
         p.legendre_synthesis(alm_re, alm_im, self.b_send)
         b = self._all_to_all(self.b_send, self.b_recv, p.counts[2], p.counts[3])
-        if self.nranks > 1:
-            self.maps.zero_()
+        self.maps.zero_()
         p.ring_synthesis(b, self.maps)
-        if self.nranks > 1:
-            self.dist.all_reduce(self.maps, group=self.group)
+        self.dist.all_reduce(self.maps, group=self.group)
         return self.maps
 
     def ray_update(self, wpp1, wp, wpm1, with_summary=False):
         """zero + interpolate + propagate: rayprop_sphere(planeRadPlus1, planeRad, planeRadMinus1) as called at
         raytrace.c:262, preceded by the reset of raytrace.c:213-230 and the interpolation of shtpoissonsolve.c:666-702.
         with_summary: also accumulate the six plane sums into self.summary (same kernel, no second pass)."""
-        ptrs = (C.c_void_p * 6)(*[self.maps[k].data_ptr() for k in range(6)])
-        need = None if self._need is None else self._need.data_ptr()
-
-        def launch(stream):
-            self.lib.clb_ray_step_ex_dev(self.rays.data_ptr(), self.nrays, ptrs, self.order, float(wpp1), float(wp), float(wpm1),
-                                         MODE_ZERO | MODE_INTERP | MODE_PROP, need, self.coarse_order if need else 0, self.rank,
-                                         self._err.data_ptr() if need else None,
-                                         self.summary.data_ptr() if with_summary else None, stream)
-        if not self.overlap_rays:
-            launch(self._stream())
+        if self._cs:
+            self.lib.clb_solver_ray_update(self._cs, float(wpp1), float(wp), float(wpm1), MODE_ZERO | MODE_INTERP | MODE_PROP,
+                                           1 if with_summary else 0, self._stream())
             return
-        self._wait_rays()                      # planes are sequential for the rays
-        maps_ready = torch.cuda.Event(); maps_ready.record()
-        self._ray_stream.wait_event(maps_ready)
-        t0 = torch.cuda.Event(enable_timing=True); t0.record(self._ray_stream)
-        launch(self._ray_stream.cuda_stream)
-        done = torch.cuda.Event(enable_timing=True); done.record(self._ray_stream)
-        self._rays_done = done
-        self.ray_events = (self.ray_events + [(t0, done)])[-64:]     # duration of the overlapped kernel, for bench.py
-
-    def sync_rays(self):
-        """Join the ray stream (before reading rays, summaries, or timing)."""
-        self._wait_rays()
+        ptrs = (C.c_void_p * 6)(*[self.maps[k].data_ptr() for k in range(6)])
+        self.lib.clb_ray_step_ex_dev(self.rays.data_ptr(), self.nrays, ptrs, self.order, float(wpp1), float(wp), float(wpm1),
+                                     MODE_ZERO | MODE_INTERP | MODE_PROP, None, 0, self.rank, None,
+                                     self.summary.data_ptr() if with_summary else None, self._stream())
 
     def check_halo(self):
         """Raise if a ray left the part of the sky this rank receives (the reference aborts on a missing map cell,
         shtpoissonsolve.c:683-689); synchronises."""
-        if self._need is not None and int(self._err.item()) != 0:
+        if self._cs:
+            self._raise(self.lib.clb_solver_check(self._cs, self._stream()))
+
+    def _raise(self, err):
+        if err & 2:
+            raise RuntimeError("calclens_b200: a rank never reached a barrier of the fused exchange")
+        if err & 1:
             raise RuntimeError("calclens_b200: a ray left its domain + halo (%.2f deg); raise halo_deg" % self.halo_deg)
 
-    def prefetch(self, counts_map, premul, densmul, backdens):
-        """Start loading the NEXT plane's density on the copy stream while the current plane computes: the host map is
-        read by the GPU directly (only this rank's rings), scaled, and parked in the spare density buffer."""
-        k = 1 if (self._staged is None or self._staged[2] == 0) else 0
-        cs = self._copy_stream
-        if self._dens_free[k] is not None:
-            cs.wait_event(self._dens_free[k])
-        with torch.cuda.stream(cs):
-            self.load_density(counts_map, premul, densmul, backdens, dst=self._dens[k])
-            ev = torch.cuda.Event(); ev.record(cs)
-        self._next_staged = (counts_map, (float(premul), float(densmul), float(backdens)), k, ev)
-
     def step(self, counts_map, premul, densmul, backdens, wpp1, wp, wpm1, read_summary=True, prefetch=None):
-        """One lens plane.  ``counts_map``: RING float32 full-sky map, a device tensor or a pinned host tensor.
+        """One lens plane.  ``counts_map``: RING float32 full-sky map, a device tensor or a (pinned) host tensor.
         ``prefetch`` = (next_counts_map, premul, densmul, backdens) starts the next plane's load behind this plane's
-        kernels; a later step() given that same map picks the staged density up instead of loading again."""
-        st = self._staged
-        key = (float(premul), float(densmul), float(backdens))
-        if st is not None and st[0] is counts_map and st[1] == key:
-            torch.cuda.current_stream().wait_event(st[3])
-            k = st[2]
-        else:
-            k = 0 if st is None else 1 - st[2]
-            self.load_density(counts_map, premul, densmul, backdens, dst=self._dens[k])
-            self._staged = (None, None, k, None)
-        self.solve(self._dens[k])
-        ev = torch.cuda.Event(); ev.record()
-        self._dens_free[k] = ev
-        self._staged = (None, None, k, None)
+        kernels; a later step() given that same map picks the staged density up instead of loading again.
+        Returns the six ray sums over all ranks (read_summary) or None."""
+        assert counts_map.dtype == torch.float32 and counts_map.numel() == self.npix and counts_map.is_contiguous()
+        if self._cs:
+            if prefetch is not None:
+                nm, a, b, c = prefetch
+                self._next = nm    # keep the tensor alive until its load has run
+                self.lib.clb_solver_set_next(self._cs, nm.data_ptr(), float(a), float(b), float(c))
+            out = (C.c_double * 6)() if read_summary else None
+            err = self.lib.clb_solver_step(self._cs, counts_map.data_ptr(), float(premul), float(densmul), float(backdens),
+                                           float(wpp1), float(wp), float(wpm1), out, self._stream())
+            if not read_summary:
+                return None
+            self._raise(err)
+            res = np.array(list(out))
+            if self.nranks > 1 and self.dist is not None:
+                t = torch.from_numpy(res).to(self.device)
+                self.dist.all_reduce(t, group=self.group)
+                res = t.cpu().numpy()
+            return res
+        self.load_density(counts_map, premul, densmul, backdens)
+        self.solve()
         self.ray_update(wpp1, wp, wpm1, with_summary=read_summary)
-        if prefetch is not None:
-            self.prefetch(*prefetch)
-            self._staged = self._next_staged
         if not read_summary:
             return None
-        self._wait_rays()
-        if self.nranks > 1:
-            self.dist.all_reduce(self.summary, group=self.group)
-        out = self.summary.cpu().numpy()
-        self.check_halo()
-        return out
+        self.dist.all_reduce(self.summary, group=self.group)
+        return self.summary.cpu().numpy()
 
     def rays_host(self):
         from .rays import rays_from_device
-        self._wait_rays()
         return rays_from_device(self.rays[:self.nrays * 176])
+
+    def sync_rays(self):
+        """(kept for callers of the round-1 API: the ray kernel runs on the caller's stream, nothing to join)"""

@@ -112,6 +112,9 @@ class HEALPixSHTPlan:
         self._h = self.lib.clb_sht_plan_create(self.order, self.lmax, None if w is None else w.ctypes.data, self.nranks,
                                                self.rank, None if ro is None else ro.ctypes.data,
                                                None if mo is None else mo.ctypes.data)
+        self._query()
+
+    def _query(self):
         q = lambda k: self.lib.clb_sht_plan_query(self._h, k)
         self.Nlm = q(2)
         self.nrp_loc, self.nm_loc = q(3), q(4)

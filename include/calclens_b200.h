@@ -23,7 +23,7 @@ extern "C" {
 
 typedef struct clb_sht_plan clb_sht_plan;
 
-int clb_abi_version(void);
+int clb_abi_version(void);   /* 2 */
 /* number of CUDA devices; aborts if the CUDA runtime reports none (no CPU fallback exists) */
 int clb_device_count(void);
 void clb_set_device(int device);
@@ -130,7 +130,9 @@ int clb_ray_output_dev(const void *rays, void *out_rays, long nrays, long ray_or
  * (Part.pos, raytrace.h:246-253), ringmap RING-ordered and zeroed by the caller; feeds clb_load_density_dev */
 int clb_deposit_ngp_dev(const float *pos, const float *mass, long nparts, long order, float *ringmap, void *stream);
 
-/* ---- host-pointer entry points (single rank; transfers inside) ---- */
+/* ---- host-pointer entry points (transfers inside; device buffers are pooled between calls, clb_pool_release frees
+ * them) ---- */
+void clb_pool_release(void);
 /* map2alm_mpi on a RING-ordered map (healpix_shtrans.h:67) */
 void clb_map2alm(clb_sht_plan *plan, const float *ringmap, double *alm_re, double *alm_im, int apply_poisson_filter);
 /* alm2allmaps_mpi; maps = 6 consecutive RING-ordered maps (healpix_shtrans.h:70-72) */
@@ -157,6 +159,80 @@ void clb_healpix_index_dev(int what, long order, long n, const long *in, const d
                            long *out, void *stream);
 /* vec2ang + get_interpol (healpix_utils.c:120,971): vec[3n] -> pix[4n], wgt[4n] */
 void clb_healpix_interpol_dev(long order, long n, const double *vec, long *pix, double *wgt, void *stream);
+/* the same stencil exactly as the ray kernel forms it (tabulated ring colatitudes, reciprocal weights): the index path
+ * that runs in clb_ray_step*_dev, exposed for the bit-exactness tests */
+void clb_ray_stencil_dev(long order, long n, const double *vec, long *pix, double *wgt, void *stream);
+
+/* ---- persistent lens-plane solver: one object per rank / GPU that owns everything living across planes (plan,
+ * exchange buffers, six derivative maps, double-buffered density, device-resident rays) and runs the whole per-plane
+ * path: do_healpix_sht_poisson_solve from the raw count map on (shtpoissonsolve.c:342-708) plus the plane's
+ * rayprop_sphere calls (raytrace.c:256-269).  It replaces the body of the reference's plane loop between the ray reset
+ * (raytrace.c:213-230) and the end of the propagation loop (:256-269).
+ *   nranks > 1: one process per GPU on one NVLink/NVSwitch node.  The exchange buffers are mapped into every process
+ *   (CUDA IPC); the handles travel through `allgather` (every rank contributes `bytes` bytes, receives nranks*bytes in
+ *   rank order -- MPI_Allgather(send, bytes, MPI_BYTE, recv, bytes, MPI_BYTE, MPI_COMM_WORLD) in CALCLENS).  The two
+ *   transposes (map2alm_transpose_mpi.c:339-381, alm2allmaps_transpose_mpi.c:656-724) and the ring -> domain shuffle
+ *   (map_shuffle.c:22-631) are then stores/loads of the producing/consuming kernels over NVLink, ordered by a
+ *   device-side barrier; no host synchronisation on the per-plane path.  Returns NULL if peer mapping is unavailable.
+ *   rp_owner / m_owner as in clb_sht_plan_create (NULL: round-robin, balanced); rays are split into contiguous NEST
+ *   ranges (compact sky domains, cf. loadbalance.c:151-181); halo_deg > 0 limits the map broadcast to each rank's
+ *   domain + halo (the reference's MAPBUFF bundle cells, raytrace_utils.c:116-161), 0 sends full maps.
+ *   Entry points that take a stream enqueue on it and return without synchronising unless stated. ---- */
+typedef struct clb_solver clb_solver;
+typedef void (*clb_allgather_fn)(const void *send, void *recv, long bytes, void *ctx);
+clb_solver *clb_solver_create(long sht_order, long lmax, long ray_order, const double *ring_weights, int nranks, int rank,
+                              const int *rp_owner, const int *m_owner, clb_allgather_fn allgather, void *ctx,
+                              double halo_deg);
+void clb_solver_destroy(clb_solver *s);   /* collective on multi-rank solvers */
+/* what: 0 rays on this rank, 1 first NEST index, 2 fused exchange active, 3 kernels launched, 4 halo mask in use,
+ * 5 mean fraction of the sky a rank receives x 1e6, 6 host barriers in use (ranks time-share a GPU), 7 Npix */
+long clb_solver_query(const clb_solver *s, int what);
+/* device pointers owned by the solver: 0 six maps [6][Npix], 1 rays, 2/3 alm re/im, 4 the clb_sht_plan, 5 halo mask,
+ * 6/7 the two density buffers, 8 the six ray sums */
+void *clb_solver_ptr(clb_solver *s, int what);
+/* alloc_rays + init_rays (raytrace_utils.c:265-347) for this rank's NEST range; returns the number of rays */
+long clb_solver_init_rays(clb_solver *s, double binL_2, void *stream);
+/* rays from / to a host array of HEALPixRay (restart, write_rays); get synchronises */
+void clb_solver_set_rays(clb_solver *s, const void *host_rays, long nrays, void *stream);
+void clb_solver_get_rays(clb_solver *s, void *host_rays, void *stream);
+/* write_rays' pre-output transform (rayio.c:300-312) into a host array; the resident rays are untouched; synchronises */
+void clb_solver_ray_output(clb_solver *s, void *host_out, void *stream);
+/* One lens plane.  counts_map: full-sky RING float32 count map in device memory, pinned/registered host memory (read by
+ * the GPU directly, only this rank's rings cross PCIe) or pageable host memory (staged); scalings as
+ * clb_scale_density_dev; (wpp1, wp, wpm1) = rayprop_sphere's arguments at raytrace.c:262.  sum6 != NULL: the six ray
+ * sums of this rank are copied back and the call synchronises; returns 0, or bit 0 = a ray left this rank's domain +
+ * halo (the reference aborts: shtpoissonsolve.c:683-689), bit 1 = a peer never reached a barrier. */
+int clb_solver_step(clb_solver *s, const float *counts_map, float premul, float densmul, float backdens, double wpp1,
+                    double wp, double wpm1, double *sum6, void *stream);
+/* register the NEXT plane's map: the following clb_solver_step starts loading it on a side stream behind its own
+ * kernels, and the step after that, given the same pointer and scalings, finds its density already on the device */
+void clb_solver_set_next(clb_solver *s, const float *next_counts_map, float premul, float densmul, float backdens);
+/* synchronise and return the error bits of clb_solver_step */
+int clb_solver_check(clb_solver *s, void *stream);
+/* the pieces of a step, for callers that interleave their own work: density load into the current buffer, the SHT
+ * Poisson solve (density_dev NULL = the current buffer), alm2allmaps_mpi from device alm of this rank's m, ray update
+ * (mode bits as clb_ray_step_dev: 1 reset, 2 interpolate + accumulate, 4 propagate, 8 Born form) */
+void clb_solver_load_density(clb_solver *s, const float *counts_map, float premul, float densmul, float backdens, void *stream);
+void clb_solver_solve(clb_solver *s, const float *density_dev, void *stream);
+void clb_solver_alm2allmaps(clb_solver *s, const double *alm_re, const double *alm_im, void *stream);
+void clb_solver_ray_update(clb_solver *s, double wpp1, double wp, double wpm1, int mode, int with_summary, void *stream);
+/* map2alm_mpi / alm2allmaps_mpi with the reference's per-rank arguments (healpix_shtrans.h:67,70-72): mapvec = this
+ * rank's ring pairs in the padded layout of healpix_shtrans.c:90-118 (north_start/south_start = the plan's
+ * northStartIndMapvec/southStartIndMapvec, indexed by ring - firstRingTasks[rank]), alm = the m range this rank owns.
+ * The solver must have been created with rp_owner/m_owner describing firstRingTasks..lastRingTasks and
+ * firstMTasks..lastMTasks.  Host pointers; collective over the ranks; synchronises.  (No Poisson filter: the caller
+ * applies it, shtpoissonsolve.c:526-550.) */
+void clb_solver_map2alm_mapvec(clb_solver *s, const float *mapvec, const long *north_start, const long *south_start,
+                               double *alm_re, double *alm_im, void *stream);
+void clb_solver_alm2allmaps_mapvec(clb_solver *s, const double *alm_re, const double *alm_im, float *const mapvec[6],
+                                   const long *north_start, const long *south_start, void *stream);
+/* per-stage CUDA-event timing of the last step: scale, fft_analysis, exchange g, legendre_analysis, legendre_synthesis,
+ * exchange b, fft_synthesis, map broadcast, rays (milliseconds; synchronises) */
+void clb_solver_set_timing(clb_solver *s, int on);
+void clb_solver_stage_ms(clb_solver *s, double *ms9);
+/* pin / unpin a host array in place so transfers from it run at full PCIe rate (AllRaysGlobal, raw maps) */
+int clb_host_register(void *p, long bytes);
+void clb_host_unregister(void *p);
 
 #ifdef __cplusplus
 }

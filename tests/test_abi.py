@@ -11,7 +11,7 @@ def test_library_loads_and_exports_header_symbols():
     assert len(names) >= 25
     for n in names:
         assert hasattr(L, n), "symbol %s declared in include/calclens_b200.h is not exported" % n
-    assert L.clb_abi_version() == 1
+    assert L.clb_abi_version() == 2
 
 
 def test_binding_covers_header():
