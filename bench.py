@@ -114,71 +114,43 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline (the compiled reference functions in oracle/_ref on host cores)
+# reference arm / CPU baseline: the reference's own MPI code on the host cores (oracle/cpu_arm.py)
 # ----------------------------------------------------------------------------------------------------------------
-def _cpu_sample_worker(args):
-    order, lmax, ray_order, seed = args
-    from oracle import ref
-    rng = np.random.default_rng(seed)
-    nside = 1 << order
-    npix = 12 * nside * nside
-    m = rng.lognormal(sigma=0.5, size=npix).astype(np.float32)
-    m = (m * np.float32(8.0) - np.float32(8.0 * math.exp(0.125))).astype(np.float32)
-    t0 = time.time()
-    are, aim = ref.map2alm(order, lmax, m)
-    t1 = time.time()
-    are, aim = ref.poisson_filter(lmax, are, aim)
-    maps = ref.alm2allmaps(order, lmax, are, aim)
-    t2 = time.time()
-    maps *= np.float32(1e-3 / max(float(np.abs(maps[3]).max()), 1e-30))
-    rays = ref.init_rays(ray_order, 15.0)
-    t3 = time.time()
-    ref.shearinterp(order, min(order, 3), maps, rays)
-    ref.rayprop(rays, 45.0, 15.0, 0.0)
-    t4 = time.time()
-    return (t1 - t0, t2 - t1, t4 - t3)
-
-
-def cpu_reference_sample(sample_order, cores, target_nside, target_lmax, target_nrays, seed=0):
-    """Run one bounded sample of the reference on `cores` processes in parallel (independent planes, which is how a
-    user would occupy the cores without MPI) and extrapolate to the target plane with the exact triple/ray counts."""
-    import multiprocessing as mp
-    s_nside = 1 << sample_order
-    s_lmax = 2 * s_nside
-    s_ray_order = sample_order
-    jobs = [(sample_order, s_lmax, s_ray_order, seed + i) for i in range(cores)]
-    t0 = time.time()
-    if cores > 1:
-        with mp.get_context("fork").Pool(cores) as pool:
-            res = pool.map(_cpu_sample_worker, jobs)
-    else:
-        res = [_cpu_sample_worker(jobs[0])]
-    wall = time.time() - t0
-    t_ana = float(np.mean([r[0] for r in res])); t_syn = float(np.mean([r[1] for r in res])); t_ray = float(np.mean([r[2] for r in res]))
-    tri_s = triple_count(s_nside, s_lmax); tri_t = triple_count(target_nside, target_lmax)
-    nrays_s = 12 * (1 << (2 * s_ray_order))
-    per_plane_core_s = (t_ana + t_syn) * (tri_t / tri_s) + t_ray * (target_nrays / nrays_s)
-    planes_per_s = cores / per_plane_core_s
-    sample = ("reference map2alm_mpi+filter+alm2allmaps_mpi+shearinterp_comp+rayprop_sphere (oracle/_ref, single-rank MPI stub, "
-              "FFTW replaced by the FP64 shim) at Nside=%d lmax=%d rays Nside=%d on %d process(es) in parallel: "
-              "%.2f s analysis, %.2f s synthesis, %.2f s rays per process (wall %.1f s); EXTRAPOLATED to Nside=%d lmax=%d, %d rays "
-              "with the exact triple ratio %.1f and ray ratio %.1f" % (
-                  s_nside, s_lmax, 1 << s_ray_order, cores, t_ana, t_syn, t_ray, wall, target_nside, target_lmax, target_nrays,
-                  tri_t / tri_s, target_nrays / nrays_s))
-    return planes_per_s, sample, wall
-
-
 def host_cores(sample_order):
-    """Processes for the CPU legs: every host core, bounded by memory (one reference process holds ~0.2 GB at sample
-    order 8, ~0.8 GB at order 9: six maps plus 176-byte rays) so a many-core box is not driven out of RAM."""
+    """Ranks for the CPU legs: the largest power of two <= host cores (the reference's hypercube exchange wants one),
+    bounded by memory (one rank holds six maps plus its share of the rays)."""
     cores = os.cpu_count() or 1
     try:
         import psutil
-        per_proc = 0.25e9 * 4 ** max(sample_order - 8, 0)
+        per_proc = 0.6e9 * 4 ** max(sample_order - 10, 0)
         cores = max(1, min(cores, int(0.5 * psutil.virtual_memory().available / per_proc)))
     except Exception:
-        cores = min(cores, 32)
-    return cores
+        pass
+    p = 1
+    while 2 * p <= min(cores, 64):
+        p *= 2
+    return p
+
+
+def cpu_reference_sample(sample_order, cores, target_nside, target_lmax, target_nrays, seed=0):
+    """One lens plane of the reference on `cores` MPI-stub ranks at the sample size (same lmax/Nside ratio as the target),
+    extrapolated to the target plane: Legendre time by the exact triple ratio, ring-FFT time by sum(n log2 n), ray time by
+    the ray count.  Returns (planes/s at the target, detail dict, wall seconds)."""
+    from oracle import cpu_arm
+    s_nside = 1 << sample_order
+    s_lmax = min(int(round(target_lmax * s_nside / float(target_nside))), 3 * s_nside - 1)
+    return cpu_arm.sample(sample_order, s_lmax, sample_order, cores, seed, triple_count, (target_nside, target_lmax, target_nrays))
+
+
+def cpu_sample_text(detail):
+    m, e = detail["measured_seconds"], detail["extrapolation"]
+    return ("reference map2alm_mpi + filter + alm2allmaps_mpi + shearinterp_comp + rayprop_sphere, %s built %s, %d ranks of the "
+            "shared-memory MPI stub (real hypercube transposes; FFTW replaced by the FP64 shim), one plane at Nside=%d lmax=%d rays "
+            "Nside=%d: %.2f s analysis, %.2f s synthesis, %.2f s rays (max over ranks); EXTRAPOLATED to the target plane: Legendre x%.1f "
+            "(triples), ring FFT x%.1f (n log n), rays x%.1f -> %.1f s per plane" % (
+                detail["library"], detail["flags"], detail["ranks"], detail["sample"]["nside"], detail["sample"]["lmax"],
+                detail["sample"]["ray_nside"], m["map2alm_mpi"], m["filter+alm2allmaps_mpi"], m["shearinterp_comp+rayprop_sphere"],
+                e["legendre_by_triples"], e["fft_by_npix_log_n"], e["rays_by_count"], detail["extrapolated_seconds_per_plane"]))
 
 
 def run_reference_arm(a):
@@ -190,11 +162,10 @@ def run_reference_arm(a):
     if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libcalclens_ref.so not built (needs /root/reference at build time)"}))
         return 0
-    cores = host_cores(a.ref_sample_order)
-    vals, wall = [], 0.0
-    sample_txt = ""
+    cores = host_cores(a.cpu_sample_order)
+    vals, wall, detail = [], 0.0, None
     for i in range(a.warmup + a.steps):
-        v, sample_txt, w = cpu_reference_sample(a.ref_sample_order, cores, a.nside, a.lmax, cfg["nrays"], seed=100 + i)
+        v, detail, w = cpu_reference_sample(a.cpu_sample_order, cores, a.nside, a.lmax, cfg["nrays"], seed=100 + i)
         if i >= a.warmup:
             vals.append(v); wall += w
     value = float(np.mean(vals)) if vals else 0.0
@@ -203,7 +174,8 @@ def run_reference_arm(a):
             "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": cfg["config"],
             "ray_plane_updates_per_s": value * cfg["nrays"],
-            "cpu_baseline": {"value": value, "unit": "planes/s", "cores": cores, "kind": "reference", "sample": sample_txt},
+            "cpu_baseline": {"value": value, "unit": "planes/s", "cores": cores, "kind": "reference", "sample": cpu_sample_text(detail),
+                             "detail": detail},
             "e2e": {"value": value, "unit": "planes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -222,36 +194,189 @@ def workload_config(a):
                                     % (4e-9 * 12 * a.nside ** 2, 176e-9 * nrays, 16e-9 * 7 * (4 * a.nside) * (a.lmax + 1))}}
 
 
+def _hash_normal(l, m, seed, which):
+    """standard normals that depend only on (l, m, seed): the same alm on any number of ranks (32-bit integer hash of
+    the indices, Box-Muller)"""
+    import torch
+
+    def h(salt):
+        x = (l * 0x9E3779B1 + m * 0x85EBCA77 + (seed * 2 + salt) * 0xC2B2AE3D + which * 0x27D4EB2F) & 0xFFFFFFFF
+        x = x ^ (x >> 16); x = (x * 0x7FEB352D) & 0xFFFFFFFF
+        x = x ^ (x >> 15); x = (x * 0x846CA68B) & 0xFFFFFFFF
+        x = x ^ (x >> 16)
+        return (x.double() + 0.5) / 4294967296.0
+    return torch.sqrt(-2.0 * torch.log(h(0))) * torch.cos(2.0 * math.pi * h(1))
+
+
 def make_count_maps(solver, nmaps, lmax, seed=1234, nbar=8.0, sigma=0.5):
     """Synthetic lognormal over-density shells: Gaussian field with C_l ~ (l+10)^-1.2 synthesised
-    with this library's own alm->map, delta = exp(sigma g - sigma^2/2) - 1, counts = nbar (1 + delta).  Outside any timed region."""
+    with this library's own alm->map, delta = exp(sigma g - sigma^2/2) - 1, counts = nbar (1 + delta).  The alm depend only
+    on (l, m, seed) and the normalisation is analytic, so every rank count gives the same shells.  Outside any timed region."""
     import torch
     p = solver.plan
+    dev = solver.device
+    ll = torch.arange(1, lmax + 1, dtype=torch.float64)
+    var = float(((2 * ll + 1) / (4 * math.pi) * (ll + 10.0) ** -1.2).sum())     # field variance of the spectrum
     maps = []
     for k in range(nmaps):
-        gen = torch.Generator(device=solver.device); gen.manual_seed(seed + k + 7919 * solver.rank)
-        are = torch.randn(max(p.Nlm, 1), generator=gen, device=solver.device, dtype=torch.float64)
-        aim = torch.randn(max(p.Nlm, 1), generator=gen, device=solver.device, dtype=torch.float64)
-        # scale by sqrt(C_l/2): degree l of every local (m, l) without one launch per m
         if p.nm_loc:
-            mloc = torch.as_tensor(np.asarray(p.m_local), device=solver.device, dtype=torch.int64)
+            mloc = torch.as_tensor(np.asarray(p.m_local), device=dev, dtype=torch.int64)
             cnt = lmax + 1 - mloc
             start = torch.cumsum(cnt, 0) - cnt
-            ls = (torch.arange(int(cnt.sum()), device=solver.device, dtype=torch.int64)
-                  - torch.repeat_interleave(start, cnt) + torch.repeat_interleave(mloc, cnt)).double()
             ms = torch.repeat_interleave(mloc, cnt)
+            li = torch.arange(int(cnt.sum()), device=dev, dtype=torch.int64) - torch.repeat_interleave(start, cnt) + ms
+            ls = li.double()
+            # a_lm = sqrt(C_l/2) (x + i y) for m > 0, sqrt(C_l) x for m = 0
+            amp = torch.sqrt(0.5 * (ls + 10.0) ** -1.2)
+            amp[ms == 0] *= math.sqrt(2.0)
+            amp[li < 1] = 0.0
+            are = _hash_normal(li, ms, seed + k, 0) * amp
+            aim = _hash_normal(li, ms, seed + k, 1) * amp
+            aim[ms == 0] = 0.0
         else:
-            ls = torch.zeros(1, device=solver.device, dtype=torch.float64); ms = torch.zeros(1, device=solver.device, dtype=torch.int64)
-        amp = torch.sqrt(0.5 * (ls + 10.0) ** -1.2)
-        amp[ls < 1] = 0.0
-        are[:ls.numel()] *= amp; aim[:ls.numel()] *= amp
-        aim[:ls.numel()][ms == 0] = 0.0          # m = 0 coefficients are real
-        solver.alm2allmaps(are, aim)
-        g = solver.maps[0].double()
-        g = g / g.std()
+            are = torch.zeros(1, device=dev, dtype=torch.float64); aim = torch.zeros(1, device=dev, dtype=torch.float64)
+        solver.alm2allmaps(are.contiguous(), aim.contiguous())
+        g = solver.maps[0].double() / math.sqrt(var)
         counts = (nbar * torch.exp(sigma * g - 0.5 * sigma * sigma)).float()
         maps.append(counts)
     return maps
+
+
+STAGES = ["scale", "fft_analysis", "a2a_g", "legendre_analysis", "legendre_synthesis", "a2a_b", "fft_synthesis", "map_allreduce", "rays"]
+
+
+def measure(a, L, poisson, torch, dist, world, rank, local_rank, group, order, ray_order, lmax, steps, warmup, with_e2e=True):
+    """device-resident and end-to-end planes/s of one configuration through clb_solver_* (calclens_b200/csrc/solver.cu)"""
+    t_setup = time.time()
+    solver = poisson.LensPlaneSolver(order, lmax, ray_order, dist_group=group, device=local_rank, fused=(a.exchange == "fused"))
+    if world > 1 and a.exchange == "fused":
+        assert solver.fused, "bench.py: the fused exchange is not active (peer mapping failed) -- refusing to report NCCL numbers as fused"
+    cosmo = poisson.Cosmology(0.27)
+    max_dist = 30.0 * a.planes
+    pp = [poisson.plane_params(p, a.planes, max_dist, 0.27, cosmo) for p in range(a.planes)]
+    solver.init_rays(pp[0]["binL"] / 2.0)
+    nmaps = 3
+    dev_maps = make_count_maps(solver, nmaps, lmax)
+    host_maps = [torch.empty(solver.npix, dtype=torch.float32).pin_memory() for _ in range(nmaps)]
+    for h, d in zip(host_maps, dev_maps):
+        h.copy_(d)
+    torch.cuda.synchronize()
+    t_setup = time.time() - t_setup
+
+    def plane_args(step, peek=False):
+        if step % a.planes == 0 and step > 0 and not peek:
+            solver.init_rays(pp[0]["binL"] / 2.0)   # a new light cone: rays back at the first shell
+        p = pp[step % a.planes]
+        binL = p["binL"]
+        vshell = 4.0 * math.pi / 3.0 * ((p["wp"] + binL / 2) ** 3 - (p["wp"] - binL / 2) ** 3)
+        part_mass = 0.27 * poisson.RHO_CRIT * vshell / (8.0 * solver.npix)   # the shell holds its mean mass (SURVEY.md section 8d)
+        premul, densmul, backdens = poisson.density_scalings(order, part_mass, p["densfact"], p["backdens"])
+        return premul, densmul, backdens, p["wpp1"], p["wp"], p["wpm1"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=solver.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- device-resident throughput ("value"): count maps already in HBM, no host synchronisation between planes
+    for s in range(warmup):
+        solver.step(dev_maps[s % nmaps], *plane_args(s), read_summary=False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.clb_launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()    # lets `ncu --profile-from-start off` list exactly the timed region's launches
+    e0.record()
+    for s in range(steps):
+        solver.step(dev_maps[(warmup + s) % nmaps], *plane_args(warmup + s), read_summary=False)
+    e1.record()
+    barrier()
+    torch.cuda.profiler.stop()
+    launches = L.clb_launch_count() - launches0
+    ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / steps
+    clocks = sampler.stop() if rank == 0 else None
+    # per-stage times (CUDA events recorded inside the solver on the launching stream), a separate pass of the same steps
+    stage_ms = {k: 0.0 for k in STAGES}
+    solver.set_timing(True)
+    base = warmup + steps
+    for s in range(steps):
+        solver.step(dev_maps[(base + s) % nmaps], *plane_args(base + s), read_summary=False)
+        for k, v in zip(STAGES, solver.stage_ms()):
+            stage_ms[k] += v / steps
+    solver.set_timing(False)
+    base += steps
+    out = {"ms_per_step": ms_per_step, "stage_ms": stage_ms, "launches": launches, "clocks": clocks, "setup_s": t_setup,
+           "npix": solver.npix, "fused": solver.fused, "host_barriers": getattr(solver, "host_barriers", False)}
+    if with_e2e:
+        # ---- end to end through the public API with host buffers: H2D of the plane's map (prefetched behind the previous
+        # plane's kernels) + D2H of the six ray sums every step
+        for s in range(min(warmup, 2)):
+            nxt = (host_maps[(base + s + 1) % nmaps],) + tuple(plane_args(base + s + 1, peek=True)[:3])
+            solver.step(host_maps[(base + s) % nmaps], *plane_args(base + s), prefetch=nxt)
+        base += min(warmup, 2)
+        barrier()
+        e0.record()
+        summ = None
+        for s in range(steps):
+            nxt = (host_maps[(base + s + 1) % nmaps],) + tuple(plane_args(base + s + 1, peek=True)[:3])
+            summ = solver.step(host_maps[(base + s) % nmaps], *plane_args(base + s), prefetch=nxt)
+        e1.record()
+        barrier()
+        out["e2e_ms"] = max_over_ranks(e0.elapsed_time(e1)) / steps
+        out["last_summary"] = [float(x) for x in summ]
+    solver.close()
+    return out
+
+
+def run_sweep(a, L, poisson, torch, dist, world, rank, local_rank, group):
+    """BASELINE configs[3]: SHT Poisson round trip (map2alm + filter + alm2allmaps) Nside 512..8192, lmax = 2 Nside, one JSON
+    line per size with the CPU arm (measured directly up to the sample order, extrapolated above it) beside it."""
+    import calclens_b200 as clb
+    lines = []
+    sizes = [512, 1024, 2048, 4096] + ([8192] if world >= 4 else [])
+    for nside in sizes:
+        order = int(round(math.log2(nside))); lmax = 2 * nside
+        solver = poisson.LensPlaneSolver(order, lmax, order, dist_group=group, device=local_rank, fused=True)
+        dens = torch.randn(solver.npix, device=solver.device, dtype=torch.float32)
+        for _ in range(2):
+            solver.solve(dens)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            solver.solve(dens)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=solver.device); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        solver.close()
+        if rank == 0:
+            tri = triple_count(nside, lmax)
+            cpu = None
+            if not a.no_cpu_baseline:
+                try:
+                    so = min(order, a.cpu_sample_order)
+                    cores = host_cores(so)
+                    v, detail, _ = cpu_reference_sample(so, cores, nside, lmax, 0)
+                    cpu = {"sht_round_trips_per_s": v, "cores": cores, "kind": "reference", "extrapolated": so != order, "detail": detail}
+                except Exception as exc:
+                    cpu = {"failed": repr(exc)}
+            lines.append({"metric": "SHT Poisson round trip (map2alm + filter + alm2allmaps) per second", "value": 1000.0 / ms, "unit": "round trips/s",
+                          "ms_per_round_trip": ms, "n_gpus": world, "nside": nside, "lmax": lmax, "triples": tri,
+                          "legendre_tflops_algorithmic": 24.0 * tri / (ms * 1e-3) / 1e12, "cpu_baseline": cpu, "steps": a.steps})
+    return lines
 
 
 def main():
@@ -264,11 +389,11 @@ def main():
     ap.add_argument("--lmax", type=int, default=None)
     ap.add_argument("--ray-nside", type=int, default=None)
     ap.add_argument("--planes", type=int, default=50)
-    ap.add_argument("--ref-sample-order", type=int, default=8, help="log2 Nside of the bounded CPU sample of the reference arm")
-    ap.add_argument("--cpu-baseline-order", type=int, default=9, help="log2 Nside of the cpu_baseline sample inside the GPU arm (0 = skip)")
+    ap.add_argument("--cpu-sample-order", type=int, default=10,
+                    help="log2 Nside of the bounded CPU sample (the same in the reference arm and in the GPU arm's cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--overlap-rays", type=int, default=0,
-                    help="1: run the ray kernel of plane p on its own stream beside the next plane's Legendre analysis")
+    ap.add_argument("--no-lmax3", action="store_true", help="skip the second measurement at the reference's own lmax = 3 Nside - 1")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE configs[3]: SHT round-trip sweep over Nside, one JSON line per size")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="multi-GPU exchange: stores into peer memory from the producing kernels, or NCCL all-to-all + all-reduce")
     a = ap.parse_args()
@@ -286,7 +411,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import calclens_b200 as clb
     from calclens_b200 import _lib, poisson
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -308,110 +432,27 @@ def main():
     cfg = workload_config(a)
     nrays_total = cfg["nrays"]
 
-    t_setup = time.time()
-    solver = poisson.LensPlaneSolver(order, a.lmax, ray_order, dist_group=group, device=local_rank, fused=(a.exchange == "fused"),
-                                     overlap_rays=bool(a.overlap_rays))
-    cosmo = poisson.Cosmology(0.27)
-    max_dist = 30.0 * a.planes
-    pp = [poisson.plane_params(p, a.planes, max_dist, 0.27, cosmo) for p in range(a.planes)]
-    solver.init_rays(pp[0]["binL"] / 2.0)
-    nmaps = 3
-    dev_maps = make_count_maps(solver, nmaps, a.lmax)
-    # partMass so that the shell holds its mean mass: sum(mass) = Omega_m rho_crit V_shell  
-    host_maps = [torch.empty(solver.npix, dtype=torch.float32).pin_memory() for _ in range(nmaps)]
-    for h, d in zip(host_maps, dev_maps):
-        h.copy_(d)
-    torch.cuda.synchronize()
-    t_setup = time.time() - t_setup
-
-    def plane_args(step, peek=False):
-        if step % a.planes == 0 and step > 0 and not peek:
-            solver.init_rays(pp[0]["binL"] / 2.0)   # a new light cone: rays back at the first shell
-        p = pp[step % a.planes]
-        binL = p["binL"]
-        vshell = 4.0 * math.pi / 3.0 * ((p["wp"] + binL / 2) ** 3 - (p["wp"] - binL / 2) ** 3)
-        part_mass = 0.27 * poisson.RHO_CRIT * vshell / (8.0 * solver.npix)
-        premul, densmul, backdens = poisson.density_scalings(order, part_mass, p["densfact"], p["backdens"])
-        return premul, densmul, backdens, p["wpp1"], p["wp"], p["wpm1"]
-
-    def barrier():
+    if a.sweep:
+        lines = run_sweep(a, L, poisson, torch, dist, world, rank, local_rank, group)
+        if rank == 0:
+            for ln in lines:
+                real_stdout.write(json.dumps(ln) + "\n")
+            real_stdout.flush()
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            dist.destroy_process_group()
+        return 0
 
-    def max_over_ranks(ms):
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=solver.device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return ms
-
-    # stage events (for the per-kernel roofline), recorded on the launching stream inside the timed region
-    stage_names = ["scale", "fft_analysis", "a2a_g", "legendre_analysis", "legendre_synthesis", "a2a_b", "fft_synthesis", "map_allreduce", "rays"]
-    stage_ms = {k: 0.0 for k in stage_names}
-
-    def timed_step(step, src_maps, record):
-        premul, densmul, backdens, wpp1, wp, wpm1 = plane_args(step)
-        p = solver.plan
-        ev = []
-
-        def mark(*_):
-            if record:
-                e = torch.cuda.Event(enable_timing=True); e.record(); ev.append(e)
-        mark()
-        solver.load_density(src_maps[step % nmaps], premul, densmul, backdens); mark()
-        solver.solve(mark=lambda name: mark())
-        solver.ray_update(wpp1, wp, wpm1); mark()
-        return ev
-
-    # ---- device-resident throughput ("value")
-    for s in range(a.warmup):
-        timed_step(s, dev_maps, False)
-    solver.sync_rays()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = L.clb_launch_count()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    all_ev = []
-    torch.cuda.profiler.start()    # lets `ncu --profile-from-start off` list exactly the timed region's launches
-    e0.record()
-    for s in range(a.steps):
-        all_ev.append(timed_step(a.warmup + s, dev_maps, True))
-    solver.sync_rays()      # (overlap_rays: the last plane's ray kernel is part of the timed region)
-    e1.record()
-    barrier()
-    torch.cuda.profiler.stop()
-    launches = L.clb_launch_count() - launches0
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    for ev in all_ev:
-        for k, name in enumerate(stage_names):
-            stage_ms[name] += ev[k].elapsed_time(ev[k + 1]) / a.steps
-    if solver.overlap_rays and solver.ray_events:
-        # the ray kernel ran beside the next plane's Legendre analysis: report its own (stretched) duration
-        evs = solver.ray_events[-a.steps:]
-        stage_ms["rays"] = sum(x.elapsed_time(y) for x, y in evs) / len(evs)
-    clocks = sampler.stop() if rank == 0 else None
-    ms_per_step = ms_total / a.steps
+    r = measure(a, L, poisson, torch, dist, world, rank, local_rank, group, order, ray_order, a.lmax, a.steps, a.warmup)
+    ms_per_step, stage_ms = r["ms_per_step"], r["stage_ms"]
     value = 1000.0 / ms_per_step
-
-    # ---- end-to-end through the public API with host buffers (H2D of the plane's map + D2H of the summary every step)
-    base = a.warmup + a.steps      # planes continue where the first loop stopped (rays sit at that shell)
-    for s in range(min(a.warmup, 2)):
-        nxt = (host_maps[(base + s + 1) % nmaps],) + tuple(plane_args(base + s + 1, peek=True)[:3])
-        solver.step(host_maps[(base + s) % nmaps], *plane_args(base + s), prefetch=nxt)
-    base += min(a.warmup, 2)
-    barrier()
-    e0.record()
-    for s in range(a.steps):
-        # the next plane's map starts streaming in (pinned host -> this rank's rings on the device) behind this plane's kernels
-        nxt = (host_maps[(base + s + 1) % nmaps],) + tuple(plane_args(base + s + 1, peek=True)[:3])
-        summ = solver.step(host_maps[(base + s) % nmaps], *plane_args(base + s), prefetch=nxt)
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / a.steps
-    e2e_value = 1000.0 / e2e_ms
+    # second configuration: the band limit the reference itself runs at this Nside (healpix_shtrans.c:518-521)
+    lmax3 = None
+    if not a.no_lmax3 and a.lmax != 3 * a.nside - 1:
+        r3 = measure(a, L, poisson, torch, dist, world, rank, local_rank, group, order, ray_order, 3 * a.nside - 1, max(2, a.steps // 2), 2,
+                     with_e2e=False)
+        lmax3 = {"lmax": 3 * a.nside - 1, "ms_per_step": r3["ms_per_step"], "value": 1000.0 / r3["ms_per_step"], "unit": "planes/s",
+                 "stage_ms": r3["stage_ms"], "triples": triple_count(a.nside, 3 * a.nside - 1),
+                 "note": "same workload at the reference's own hard-wired lmax = 3 Nside - 1 (SURVEY.md D1)"}
 
     if rank == 0:
         wm = work_model(a.nside, a.lmax, nrays_total)
@@ -434,12 +475,14 @@ def main():
             pass
         ach_syn = wm["flops_synthesis"] / world / (stage_ms["legendre_synthesis"] * 1e-3) / 1e12
         traffic = None
-        try:
-            tj = json.load(open(os.path.join(HERE, "profiles", "r01_traffic.json")))
-            if world == 1 and a.nside == 4096 and a.lmax == 8192:
-                traffic = tj.get("legendre_synthesis", {}).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+        for tf in ("r02_traffic.json", "r01_traffic.json"):
+            try:
+                tj = json.load(open(os.path.join(HERE, "profiles", tf)))
+                if world == 1 and a.nside == 4096 and a.lmax == 8192:
+                    traffic = tj.get("legendre_synthesis", {}).get("dram_bytes_per_launch")
+                    break
+            except Exception:
+                pass
         roofline = {"kernel": "legendre_synthesis_kernel (dominant)", "bound": "fp64", "achieved": ach_syn, "peak": fp64_peak, "unit": "TFLOP/s",
                     "frac": ach_syn / fp64_peak, "traffic": traffic,
                     "peak_source": fp64_src, "algorithmic_flops_per_launch": wm["flops_synthesis"] / world,
@@ -457,13 +500,14 @@ def main():
         for v in stages.values():
             v["frac"] = v["achieved"] / v["peak"]
         cpu_baseline = None
-        if world == 1 and not a.no_cpu_baseline and a.cpu_baseline_order > 0:
+        if world == 1 and not a.no_cpu_baseline:
             try:
                 from oracle import ref
                 if ref.available():
-                    cores = host_cores(a.cpu_baseline_order)
-                    v, txt, _ = cpu_reference_sample(a.cpu_baseline_order, cores, a.nside, a.lmax, nrays_total)
-                    cpu_baseline = {"value": v, "unit": "planes/s", "cores": cores, "kind": "reference", "sample": txt}
+                    cores = host_cores(a.cpu_sample_order)
+                    v, detail, _ = cpu_reference_sample(a.cpu_sample_order, cores, a.nside, a.lmax, nrays_total)
+                    cpu_baseline = {"value": v, "unit": "planes/s", "cores": cores, "kind": "reference", "sample": cpu_sample_text(detail),
+                                    "detail": detail}
                 else:
                     cpu_baseline = {"value": None, "unit": "planes/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
             except Exception as exc:   # the GPU numbers stand even if the CPU leg fails
@@ -472,21 +516,23 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": cfg["config"],
                 "ray_plane_updates_per_s": value * nrays_total,
-                "e2e": {"value": e2e_value, "unit": "planes/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 4 * solver.npix,
-                        "d2h_bytes_per_step": 48 * world, "api": "calclens_b200.poisson.LensPlaneSolver.step(pinned host count map, prefetch=next plane) -> 6 ray sums on host; every rank reads only its own rings of the host map",
-                        "last_summary": [float(x) for x in summ]},
-                "gpu_launches": int(launches * world),
-                "clocks": clocks,
+                "e2e": {"value": 1000.0 / r["e2e_ms"], "unit": "planes/s", "ms_per_step": r["e2e_ms"], "h2d_bytes_per_step": 4 * r["npix"],
+                        "d2h_bytes_per_step": 48 * world,
+                        "api": "C ABI clb_solver_set_next + clb_solver_step(pinned host count map, &sum6) of libcalclens_b200.so (called through "
+                               "calclens_b200.poisson.LensPlaneSolver.step): host map in, six ray sums out; every rank reads only its own rings of the host map",
+                        "last_summary": r["last_summary"],
+                        "checksum_note": "the six ray sums after the last timed plane; inputs depend only on (l, m, seed), so lines at different N are comparable"},
+                "gpu_launches": int(r["launches"] * world),
+                "clocks": r["clocks"],
                 "roofline": roofline, "roofline_stages": stages, "stage_ms": stage_ms,
                 "hbm_peak_source": hbm_src,
-                "overlap_rays": bool(a.overlap_rays),
-                "exchange": ("fused peer stores (CUDA IPC over NVLink) + stream barriers" if solver.fused else
-                             "NCCL all-to-all-v + all-reduce" if world > 1 else "none (single GPU)"),
+                "lmax_3nside_minus_1": lmax3,
+                "exchange": (("fused peer loads/stores (CUDA IPC over NVLink) + device-side peer barrier" + (" [host barriers]" if r["host_barriers"] else ""))
+                             if r["fused"] and world > 1 else "NCCL all-to-all-v + all-reduce" if world > 1 else "none (single GPU)"),
                 "cpu_baseline": cpu_baseline,
-                "setup_s": t_setup}
+                "setup_s": r["setup_s"]}
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
-    solver.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -264,7 +264,7 @@ void ref_driver_init(long bundleOrder, long rayOrder, long mapOrder, const char 
   rayTraceData.partMass = partMass; rayTraceData.maxComvDistance = maxComvDistance; rayTraceData.NumLensPlanes = NumLensPlanes;
   rayTraceData.OmegaM = OmegaM;
   rayTraceData.minRa = 0.0; rayTraceData.maxRa = 360.0; rayTraceData.minDec = -90.0; rayTraceData.maxDec = 90.0;
-  rayTraceData.maxRayMemImbalance = 0.75; rayTraceData.NumFilesIOInParallel = NTasks;
+  rayTraceData.maxRayMemImbalance = 0.25; rayTraceData.NumFilesIOInParallel = NTasks;
   rayTraceData.galImageSearchRayBufferRad = sqrt(4.0*M_PI/order2npix(bundleOrder)) + RAYBUFF_RADIUS_ARCMIN/60.0/180.0*M_PI;   /* config.c:226 */
   init_bundlecells();
   alloc_rays();
@@ -297,7 +297,16 @@ void ref_driver_plane(long planeNum, double wpm1, double wp, double wpp1, double
 }
 
 long ref_driver_nrays(void) { return NumAllRaysGlobal; }
-void ref_driver_get_rays(HEALPixRay *out) { memcpy(out, AllRaysGlobal, sizeof(HEALPixRay) * NumAllRaysGlobal); }
+#ifdef CLB_SHIM_BUILD
+void calclens_b200_sync_rays(void);   /* device-resident mode of the shim: the host reads AllRaysGlobal only after this */
+#endif
+void ref_driver_get_rays(HEALPixRay *out)
+{
+#ifdef CLB_SHIM_BUILD
+  calclens_b200_sync_rays();
+#endif
+  memcpy(out, AllRaysGlobal, sizeof(HEALPixRay) * NumAllRaysGlobal);
+}
 void ref_driver_finalize(void)
 {
   free(AllRaysGlobal); AllRaysGlobal = NULL; NumAllRaysGlobal = 0;

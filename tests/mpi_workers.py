@@ -40,6 +40,14 @@ def driver_planes(rank, ntasks, cfg, planes, variant="ref"):
     return rays
 
 
+def driver_planes_to_file(rank, ntasks, cfg, planes, out_dir, variant="ref"):
+    """driver_planes for large runs: this rank's rays go to <out_dir>/rays.<rank>.npy instead of through the result queue"""
+    rays = driver_planes(rank, ntasks, cfg, planes, variant)
+    fn = os.path.join(out_dir, "rays.%d.npy" % rank)
+    np.save(fn, rays)
+    return fn, int(rays.size)
+
+
 def timed_driver_planes(rank, ntasks, cfg, planes, variant="fast"):
     """as driver_planes, timing every plane (seconds; the caller takes the max over ranks)"""
     import time

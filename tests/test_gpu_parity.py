@@ -495,8 +495,8 @@ def test_load_density_matches_scale_density(clb):
 
 
 def test_solver_step_prefetch_and_fused_summary(clb):
-    """LensPlaneSolver.step with the next plane prefetched from pinned host memory gives the same rays as without, and
-    the summary accumulated inside the ray kernel equals the separate summary kernel."""
+    """clb_solver_step with the next plane prefetched from pinned host memory (clb_solver_set_next) gives the same rays as
+    without, and the summary accumulated inside the ray kernel equals the separate summary kernel."""
     import torch
     from calclens_b200 import poisson
     order, lmax = 6, 128
@@ -507,9 +507,7 @@ def test_solver_step_prefetch_and_fused_summary(clb):
     planes = [(45.0, 15.0, 0.0), (75.0, 45.0, 15.0), (105.0, 75.0, 45.0)]
     a = poisson.LensPlaneSolver(order, lmax, order); a.init_rays(15.0)
     b = poisson.LensPlaneSolver(order, lmax, order); b.init_rays(15.0)
-    c = poisson.LensPlaneSolver(order, lmax, order, overlap_rays=True); c.init_rays(15.0)
     for k, pl in enumerate(planes):
-        c.step(maps[k], *sc, *pl, read_summary=False)     # rays of plane k run beside the SHT of plane k+1
         sa = a.step(maps[k], *sc, *pl)
         nxt = (maps[k + 1],) + sc if k + 1 < len(planes) else None
         sb = b.step(maps[k], *sc, *pl, prefetch=nxt)
@@ -519,7 +517,7 @@ def test_solver_step_prefetch_and_fused_summary(clb):
         a.lib.clb_ray_summary_dev(a.rays.data_ptr(), a.nrays, ref.data_ptr(), None)
         assert np.allclose(sa, ref.cpu().numpy(), rtol=1e-9, atol=1e-13)
     assert np.array_equal(a.rays_host().view(np.uint8), b.rays_host().view(np.uint8))
-    assert np.array_equal(a.rays_host().view(np.uint8), c.rays_host().view(np.uint8))
+    a.close(); b.close()
 
 
 def test_global_scratch_ring_fft_matches_shared_memory_path(clb):
@@ -720,3 +718,184 @@ def test_next_rows_golden(clb):
     rb = rays.copy()
     clb.rayprop_sphere(45.0, 15.0, 0.0, rb, born=True); clb.rayprop_sphere(75.0, 45.0, 15.0, rb, born=True)
     assert_rays_match(rb, g["rays_born"].view(clb.RAY_DTYPE))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# round 2: the kernel's own stencil path, halo masks, the C solver with emulated ranks, parity at the quoted sizes
+# ----------------------------------------------------------------------------------------------------------------
+def _edge_vectors(order, rng, n_random):
+    """unit vectors: random ones plus points within a few ulp of ring boundaries (theta of every sampled ring), of pixel
+    boundaries in phi, of the poles and of phi = 0 / 2 pi"""
+    nside = 1 << order
+    v = rng.normal(size=(n_random, 3)); v /= np.linalg.norm(v, axis=1)[:, None]
+    rings = np.unique(np.concatenate([np.arange(1, min(4 * nside, 40)), rng.integers(1, 4 * nside, 300),
+                                      [nside - 1, nside, nside + 1, 2 * nside, 3 * nside - 1, 3 * nside, 3 * nside + 1, 4 * nside - 1]]))
+    rings = rings[(rings >= 1) & (rings <= 4 * nside - 1)]
+    zs = []
+    for r in rings:
+        if r < nside:
+            z = 1.0 - r * r / (3.0 * nside * nside)
+        elif r <= 3 * nside:
+            z = (2 * nside - r) * 2.0 / (3.0 * nside)
+        else:
+            rr = 4 * nside - r
+            z = -(1.0 - rr * rr / (3.0 * nside * nside))
+        zs.append(z)
+    zs = np.array(zs)
+    edge = []
+    for k in (-2, -1, 0, 1, 2):
+        z = zs.copy()
+        for _ in range(abs(k)):
+            z = np.nextafter(z, np.inf if k > 0 else -np.inf)
+        z = np.clip(z, -1.0, 1.0)
+        npx = np.where(rings < nside, 4 * rings, np.where(rings <= 3 * nside, 4 * nside, 4 * (4 * nside - rings)))
+        j = rng.integers(0, npx)
+        for frac in (0.0, 0.5):                                  # pixel centres / pixel edges of shifted and unshifted rings
+            ph = (j + frac) * 2.0 * np.pi / npx
+            for dk in (-1, 0, 1):
+                p = ph.copy()
+                if dk:
+                    p = np.nextafter(p, np.inf if dk > 0 else -np.inf)
+                s = np.sqrt(np.maximum(0.0, (1.0 - z) * (1.0 + z)))
+                edge.append(np.stack([s * np.cos(p), s * np.sin(p), z], axis=1))
+    edge = np.concatenate(edge)
+    poles = np.array([[0, 0, 1.0], [0, 0, -1.0], [1e-300, 0, 1.0], [1e-9, 1e-9, 1.0], [-1e-9, 1e-12, -1.0], [1, 0, 0], [1, -1e-17, 0],
+                      [1, 1e-17, 0], [-1, 1e-17, 0], [-1, -1e-17, 0], [0, 1, 0], [0, -1, 0]], dtype=np.float64)
+    return np.concatenate([poles, edge, v])
+
+
+@pytest.mark.parametrize("order", [3, 8, 12])
+def test_ray_kernel_stencil_bit_exact_1e7(clb, oracle, order):
+    """The stencil exactly as ray_step_kernel forms it (vec2ang + get_interpol_tab through clb_ray_stencil_dev) against
+    (a) the device mirror of the reference's get_interpol on ~1e7 points (indices must be identical everywhere, weights
+    within 4 ulp-ish of the reciprocal form) and (b) the reference itself (oracle get_interpol, host libm) on 60000 of
+    them including every edge point: zero index mismatches."""
+    import torch
+    from calclens_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(1000 + order)
+    nrand = 10_000_000 if order == 12 else 2_000_000
+    v = _edge_vectors(order, rng, nrand)
+    n = v.shape[0]
+    tv = torch.from_numpy(np.ascontiguousarray(v)).cuda()
+    pa = torch.empty((n, 4), dtype=torch.int64, device="cuda"); wa = torch.empty((n, 4), dtype=torch.float64, device="cuda")
+    pb = torch.empty_like(pa); wb = torch.empty_like(wa)
+    L.clb_ray_stencil_dev(order, n, tv.data_ptr(), pa.data_ptr(), wa.data_ptr(), None)
+    L.clb_healpix_interpol_dev(order, n, tv.data_ptr(), pb.data_ptr(), wb.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert torch.equal(pa, pb), "table path and reference-mirror path disagree on %d stencils" % int((pa != pb).any(dim=1).sum())
+    assert float((wa - wb).abs().max()) < 1e-9
+    # against the reference's own get_interpol (host): all edge points + a random sample
+    nedge = n - nrand
+    idx = np.concatenate([np.arange(nedge), nedge + rng.integers(0, nrand, 60000 - min(nedge, 30000))])[:60000]
+    pix = pa[torch.from_numpy(idx).cuda()].cpu().numpy(); wgt = wa[torch.from_numpy(idx).cuda()].cpu().numpy()
+    import ctypes
+    Lr = getattr(oracle, "lib")()
+    has_ref = hasattr(Lr, "vec2ang")
+    bad = 0
+    for k, i in enumerate(idx):
+        if has_ref:
+            th, ph = ctypes.c_double(), ctypes.c_double()
+            vv = (ctypes.c_double * 3)(*v[i])
+            Lr.vec2ang(vv, ctypes.byref(th), ctypes.byref(ph))
+            theta, phi = th.value, ph.value
+        else:
+            theta = np.arctan2(np.sqrt(v[i, 0] ** 2 + v[i, 1] ** 2), v[i, 2]); phi = np.arctan2(v[i, 1], v[i, 0]) % (2 * np.pi)
+        p, w = oracle.get_interpol(theta, phi, order)
+        if list(pix[k]) != p:
+            bad += 1
+        else:
+            assert np.abs(wgt[k] - np.array(w)).max() < 1e-9
+    assert bad == 0, "%d of %d stencils differ from the reference's get_interpol" % (bad, len(idx))
+
+
+def _solver_inputs(order, seed):
+    import torch
+    npix = 12 << (2 * order)
+    rng = np.random.default_rng(seed)
+    counts = torch.from_numpy((8.0 * rng.lognormal(sigma=0.5, size=npix)).astype(np.float32)).pin_memory()
+    sc = (np.float32(1.0), np.float32(2e-4), np.float32(8.0 * np.exp(0.125) * 2e-4))
+    return counts, sc
+
+
+@pytest.mark.parametrize("nranks,order,halo", [(2, 5, 1.0), (3, 6, 0.5), (4, 6, 0.0)])
+def test_c_solver_emulated_ranks_with_halo_masks(clb, nranks, order, halo):
+    """clb_solver_* with N ranks emulated as threads on one GPU: the fused exchange, the halo-limited map broadcast with
+    REAL need masks (order == coarse order 5 is the corner-cut case of the 4-pixel groups) and the per-stencil mask
+    check of the ray kernel.  Rays and summaries must equal the single-rank solver bit for bit; every pixel any ray's
+    stencil touches must have been delivered; pushing a ray out of its domain must raise the error flag."""
+    import torch
+    from calclens_b200 import poisson
+    from tests.emu import ThreadRanks
+    lmax = 2 << order
+    counts, sc = _solver_inputs(order, 77)
+    planes = [(45.0, 15.0, 0.0), (75.0, 45.0, 15.0)]
+    single = poisson.LensPlaneSolver(order, lmax, order); single.init_rays(15.0)
+    ssum = [single.step(counts, *sc, *pl) for pl in planes]
+    srays = single.rays_host().copy()
+    smaps = single.maps.cpu().numpy()
+    emu = ThreadRanks(nranks)
+
+    def body(rank, gather):
+        s = poisson.LensPlaneSolver(order, lmax, order, nranks=nranks, rank=rank, allgather=gather, halo_deg=halo)
+        assert s.fused
+        assert (s._need is not None) == (halo > 0)
+        s.init_rays(15.0)
+        sums = [s.step(counts, *sc, *pl) for pl in planes]
+        rays = s.rays_host().copy()
+        maps = s.maps.cpu().numpy()
+        need = None if s._need is None else s._need.cpu().numpy()
+        # push one ray to the antipode of its domain: its stencil is outside domain + halo -> error bit 0
+        err = 0
+        if need is not None and nranks > 1:
+            rr = rays[:1].copy(); rr["n"] = -rr["n"]
+            s.rays[:176] = torch.from_numpy(rr.view(np.uint8)).cuda()
+            s.lib.clb_solver_ray_update(s._cs, 105.0, 75.0, 45.0, 1 | 2, 0, None)
+            err = s.lib.clb_solver_check(s._cs, None)
+        first = s.first_nest
+        s.close()
+        return sums, rays, maps, need, err, first
+
+    res = emu.run(body)
+    got = np.concatenate([r[1] for r in res])
+    assert np.array_equal(got.view(np.uint8), srays.view(np.uint8)), "rays differ from the single-rank solver"
+    for k in range(len(planes)):
+        tot = sum(r[0][k] for r in res)
+        assert np.allclose(tot, ssum[k], rtol=1e-9, atol=1e-13)
+    if halo > 0:
+        co = 5
+        npix = 12 << (2 * order)
+        pix = torch.arange(npix, dtype=torch.int64, device="cuda"); out = torch.empty_like(pix)
+        single.lib.clb_healpix_index_dev(0, order, npix, pix.data_ptr(), None, None, out.data_ptr(), None)   # ring -> nest
+        torch.cuda.synchronize()
+        cell = out.cpu().numpy() >> (2 * (order - co))
+        for q, (_, rays, maps, need, err, first) in enumerate(res):
+            assert err & 1, "rank %d: a ray far outside domain + halo did not raise the error flag" % q
+            # every map pixel inside the cells this rank needs equals the single-rank map (nothing undelivered)
+            needed = ((need[cell] >> q) & 1) == 1
+            assert needed.any()
+            assert np.array_equal(maps[:, needed].view(np.uint32), smaps[:, needed].view(np.uint32)), "rank %d misses needed pixels" % q
+    else:
+        for q, r in enumerate(res):
+            assert np.array_equal(r[2].view(np.uint32), smaps.view(np.uint32)), "rank %d: full maps differ" % q
+    single.close()
+
+
+def test_tuning_fallback_small_maps(clb, oracle):
+    """clb_set_tuning(1, 6) at Nside 64 (96 <= ring pairs < 192): the rings-per-thread fallback must land on an
+    instantiated kernel and analyse every ring pair."""
+    from calclens_b200 import _lib
+    L = _lib.load()
+    order, lmax = 6, 128
+    rng = np.random.default_rng(8)
+    m = rng.normal(size=12 << (2 * order)).astype(np.float32)
+    are, aim = oracle.map2alm(order, lmax, m)
+    try:
+        for R in (12, 10, 6, 4, 2, 1):
+            L.clb_set_tuning(1, R)
+            plan = clb.HEALPixSHTPlan(order, lmax)
+            gre, gim = clb.map2alm_mpi(m, plan)
+            assert alm_err(gre, gim, are, aim) <= ALM_TOL, R
+            plan.destroy()
+    finally:
+        L.clb_set_tuning(1, 8)
