@@ -767,9 +767,11 @@ def _edge_vectors(order, rng, n_random):
 @pytest.mark.parametrize("order", [3, 8, 12])
 def test_ray_kernel_stencil_bit_exact_1e7(clb, oracle, order):
     """The stencil exactly as ray_step_kernel forms it (vec2ang + get_interpol_tab through clb_ray_stencil_dev) against
-    (a) the device mirror of the reference's get_interpol on ~1e7 points (indices must be identical everywhere, weights
-    within 4 ulp-ish of the reciprocal form) and (b) the reference itself (oracle get_interpol, host libm) on 60000 of
-    them including every edge point: zero index mismatches."""
+    (a) the device mirror of the reference's get_interpol on ~1e7 points (indices identical everywhere, weights equal to
+    1e-9) and (b) the reference itself (oracle get_interpol, host libm) on 60000 of them: ZERO index mismatches on the
+    random points.  The adversarial points sit within 0-2 ulp of a ring or pixel boundary, where one ulp of cos/atan2
+    (device libm vs glibc) decides between two neighbouring stencils; there a different stencil is accepted
+    only if it is the same interpolant, i.e. the pixels the two stencils do not share carry weight < 1e-9."""
     import torch
     from calclens_b200 import _lib
     L = _lib.load()
@@ -792,7 +794,7 @@ def test_ray_kernel_stencil_bit_exact_1e7(clb, oracle, order):
     import ctypes
     Lr = getattr(oracle, "lib")()
     has_ref = hasattr(Lr, "vec2ang")
-    bad = 0
+    bad_random, edge_flips = 0, 0
     for k, i in enumerate(idx):
         if has_ref:
             th, ph = ctypes.c_double(), ctypes.c_double()
@@ -802,11 +804,22 @@ def test_ray_kernel_stencil_bit_exact_1e7(clb, oracle, order):
         else:
             theta = np.arctan2(np.sqrt(v[i, 0] ** 2 + v[i, 1] ** 2), v[i, 2]); phi = np.arctan2(v[i, 1], v[i, 0]) % (2 * np.pi)
         p, w = oracle.get_interpol(theta, phi, order)
-        if list(pix[k]) != p:
-            bad += 1
-        else:
+        if list(pix[k]) == p:
             assert np.abs(wgt[k] - np.array(w)).max() < 1e-9
-    assert bad == 0, "%d of %d stencils differ from the reference's get_interpol" % (bad, len(idx))
+            continue
+        if i >= nedge:
+            bad_random += 1
+            continue
+        d = {}
+        for q, ww in zip(pix[k], wgt[k]):
+            d[int(q)] = d.get(int(q), 0.0) + float(ww)
+        for q, ww in zip(p, w):
+            d[int(q)] = d.get(int(q), 0.0) - float(ww)
+        assert sum(abs(x) for x in d.values()) < 1e-9, "edge point %d: the two stencils are different interpolants %r" % (i, d)
+        edge_flips += 1
+    assert bad_random == 0, "%d random stencils differ from the reference's get_interpol" % bad_random
+    print("order %d: %d points on the device, %d checked against the reference; %d of %d boundary points picked the neighbouring "
+          "(equivalent) stencil" % (order, n, len(idx), edge_flips, min(nedge, len(idx))))
 
 
 def _solver_inputs(order, seed):
@@ -831,6 +844,7 @@ def test_c_solver_emulated_ranks_with_halo_masks(clb, nranks, order, halo):
     counts, sc = _solver_inputs(order, 77)
     planes = [(45.0, 15.0, 0.0), (75.0, 45.0, 15.0)]
     single = poisson.LensPlaneSolver(order, lmax, order); single.init_rays(15.0)
+    centres = single.rays_host()["n"].copy()      # pixel centres (x 15) of every NEST pixel at this order
     ssum = [single.step(counts, *sc, *pl) for pl in planes]
     srays = single.rays_host().copy()
     smaps = single.maps.cpu().numpy()
@@ -845,10 +859,13 @@ def test_c_solver_emulated_ranks_with_halo_masks(clb, nranks, order, halo):
         rays = s.rays_host().copy()
         maps = s.maps.cpu().numpy()
         need = None if s._need is None else s._need.cpu().numpy()
-        # push one ray to the antipode of its domain: its stencil is outside domain + halo -> error bit 0
+        # move one ray to the centre of a coarse cell this rank does NOT receive: its stencil is outside domain + halo
         err = 0
         if need is not None and nranks > 1:
-            rr = rays[:1].copy(); rr["n"] = -rr["n"]
+            far = np.nonzero(((need >> rank) & 1) == 0)[0]
+            assert far.size > 0, "rank %d receives the whole sky: the mask test is vacuous" % rank
+            pix_far = int(far[far.size // 2]) << (2 * (order - 5))
+            rr = rays[:1].copy(); rr["n"] = centres[pix_far]
             s.rays[:176] = torch.from_numpy(rr.view(np.uint8)).cuda()
             s.lib.clb_solver_ray_update(s._cs, 105.0, 75.0, 45.0, 1 | 2, 0, None)
             err = s.lib.clb_solver_check(s._cs, None)
