@@ -4,7 +4,27 @@
 #include <string.h>
 
 namespace clb {
-extern int g_syn_rings_per_thread, g_ana_rings_per_thread, g_fft_threads_big, g_leg_warps_per_cta, g_fft_force_scratch;
+extern int g_syn_rings_per_thread, g_ana_rings_per_thread, g_fft_threads_big, g_leg_warps_per_cta, g_fft_force_scratch, g_ana_smem_reduce, g_fft_field_groups, g_fft_prefetch, g_fft_debug;
+
+// safe[c] = AND of mask[d] over every cell d whose centre lies within neighbour_rad of c's centre (c included): a ray whose
+// stencil starts in a "safe" cell cannot touch an undelivered pixel, so the ray kernel skips the per-pixel mask check there
+void safe_masks(long coarse_order, double neighbour_rad, const unsigned char *mask, unsigned char *safe)
+{
+  const long nc = 12L << (2 * coarse_order);
+  std::vector<double> cen(3 * nc);
+  for (long c = 0; c < nc; ++c) nest2vec(c, coarse_order, &cen[3 * c]);
+  const double cosr = cos(neighbour_rad);
+  for (long c = 0; c < nc; ++c) {
+    unsigned m = mask[c];
+    const double *a = &cen[3 * c];
+    for (long d = 0; d < nc && m; ++d) {
+      if ((mask[d] & m) == m) continue;
+      const double *b = &cen[3 * d];
+      if (a[0] * b[0] + a[1] * b[1] + a[2] * b[2] >= cosr) m &= mask[d];
+    }
+    safe[c] = (unsigned char)m;
+  }
+}
 
 static long g_launches = 0;
 void count_launches(int n) { g_launches += n; }
@@ -95,6 +115,10 @@ void clb_set_tuning(int what, int value)
 {
   if (what == 0 && value >= 1 && value <= 4) g_syn_rings_per_thread = value;
   if (what == 4) g_fft_force_scratch = value ? 1 : 0;
+  if (what == 5) g_ana_smem_reduce = value ? 1 : 0;
+  if (what == 6 && (value == 0 || value == 1 || value == 3)) g_fft_field_groups = value;
+  if (what == 7) g_fft_prefetch = value ? 1 : 0;
+  if (what == 8) g_fft_debug = value;   // development aid: skip phases of the ring synthesis (wrong results)
   if (what == 3 && (value == 1 || value == 2 || value == 4)) g_leg_warps_per_cta = value;
   if (what == 2 && (value == 256 || value == 512 || value == 768 || value == 1024)) g_fft_threads_big = value;   // read at plan creation
   if (what == 1 && (value == 1 || value == 2 || value == 4 || value == 6 || value == 8 || value == 10 || value == 12)) g_ana_rings_per_thread = value;

@@ -16,7 +16,7 @@ int launch_legendre_analysis(ShtPlan *p, const double2 *d_g_recv, double *d_alm_
 int launch_legendre_synthesis(ShtPlan *p, const double *d_alm_re, const double *d_alm_im, double2 *d_b_send, cudaStream_t st);
 int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long order, double wp, double wpm1, double wpm2,
                     int mode, cudaStream_t st, const unsigned char *d_need = nullptr, long coarse_order = 0, int rank = 0,
-                    int *d_err = nullptr, double *d_sum6 = nullptr);
+                    int *d_err = nullptr, double *d_sum6 = nullptr, const unsigned char *d_safe = nullptr);
 int launch_ray_init(Ray *d_rays, long nrays, long first_nest, long ray_order, double binL_2, cudaStream_t st);
 int launch_ray_summary(const Ray *d_rays, long nrays, double *d_out6, cudaStream_t st);
 int launch_ray_output(const Ray *d_rays, Ray *d_out, long nrays, long ray_order, cudaStream_t st);
@@ -28,6 +28,7 @@ int launch_maps_broadcast(const ShtPlan *p, float *const local_maps[6], float *c
 int launch_load_density(const ShtPlan *p, const float *src, float *dst, float premul, float densmul, float backdens,
                         cudaStream_t st);
 void domain_masks(long ray_order, int nranks, long coarse_order, double margin_rad, unsigned char *mask);
+void safe_masks(long coarse_order, double neighbour_rad, const unsigned char *mask, unsigned char *safe);
 void count_launches(int n);
 
 }  // namespace clb

@@ -54,7 +54,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // block of KB degrees the 2*KB per-thread partial sums are reduced over the warp with a transpose-reduce (one
 // shuffle + add per value) and written to the warp's own partial-sum row; alm_finish_kernel adds the rows of all
 // warps of an m in a fixed order (deterministic).
-template <int R, int KB, int NB>
+template <int R, int KB, int NB, bool SR>
 __global__ void __launch_bounds__(kLegThreads, NB)
 legendre_analysis_kernel(const double2 *__restrict__ g_recv, const double2 *const *__restrict__ rp_gsrc,
                          const long *__restrict__ g_off, const int *__restrict__ g_stride, const double *__restrict__ Atab,
@@ -68,6 +68,8 @@ legendre_analysis_kernel(const double2 *__restrict__ g_recv, const double2 *cons
   constexpr int V = 2 * KB;   // v[i] = re(l0+i), v[KB+i] = im(l0+i)
   constexpr int NP = (R + 1) / 2;
   __shared__ __align__(16) double s_A[kLegWarps][2][kAnaTile];
+  constexpr bool kAnaSmemReduce = (KB == 8) && SR;
+  __shared__ double s_red[kAnaSmemReduce ? kLegWarps : 1][kAnaSmemReduce ? 16 * 33 : 1];
 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int chunk = blockIdx.x * (blockDim.x >> 5) + w, mi = blockIdx.y;
@@ -150,6 +152,26 @@ legendre_analysis_kernel(const double2 *__restrict__ g_recv, const double2 *cons
           mp[j] = mu; mc[j] = mn;
         }
       }
+      if (kAnaSmemReduce) {
+        // warp reduction through shared memory: every lane parks its V partial sums ([value][lane], rows padded to 33 so
+        // that the column reads below spread over all banks), then lane L adds 16 lanes' worth of value L % 16 and one
+        // shuffle joins the two halves -- ~3x fewer instructions than the shuffle transpose-reduce, which matters because
+        // the reduction shares the issue slots of the warps that feed the FP64 pipe
+        static_assert(!kAnaSmemReduce || V == 16, "shared-memory reduction is written for blocks of 8 degrees");
+        double *red = &s_red[w][0];
+#pragma unroll
+        for (int i = 0; i < V; ++i) red[i * 33 + lane] = v[i];
+        __syncwarp();
+        const double *col = red + (lane & 15) * 33 + (lane >> 4) * 16;
+        double t0 = col[0], t1 = col[1], t2 = col[2], t3 = col[3];
+#pragma unroll
+        for (int k = 4; k < 16; k += 4) { t0 += col[k]; t1 += col[k + 1]; t2 += col[k + 2]; t3 += col[k + 3]; }
+        double t = (t0 + t1) + (t2 + t3);
+        t += __shfl_xor_sync(0xffffffffu, t, 16);
+        const double ti = __shfl_down_sync(0xffffffffu, t, KB);   // imaginary part lives KB lanes up
+        if (lane < KB && l0 + lane <= lmax) out[l0 - m + lane] = make_double2(t, ti);
+        __syncwarp();   // the parked sums are consumed before the next block overwrites them
+      } else {
       // warp transpose-reduce: afterwards lane L holds the warp total of v[L % V]
 #pragma unroll
       for (int s = V / 2; s >= 1; s >>= 1) {
@@ -164,6 +186,7 @@ legendre_analysis_kernel(const double2 *__restrict__ g_recv, const double2 *cons
       if (V == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
       const double ti = __shfl_down_sync(0xffffffffu, v[0], KB);   // imaginary part lives KB lanes up
       if (lane < KB && l0 + lane <= lmax) out[l0 - m + lane] = make_double2(v[0], ti);
+      }
     }
     __syncwarp();   // everyone is done with this tile before the next iteration's copy overwrites it
   }
@@ -367,14 +390,21 @@ int g_leg_warps_per_cta = 4;      // warps are independent in both Legendre kern
 int g_syn_rings_per_thread = 4;   // tunable through clb_set_tuning(0, .)
 int g_ana_rings_per_thread = 8;   // tunable through clb_set_tuning(1, .): 8 (blocks of 8 degrees) or 4, 2, 1 (16 degrees)
 
+int g_ana_smem_reduce = 1;        // clb_set_tuning(5, 0|1): warp reduction of the analysis kernel through shared memory (blocks of 8 degrees)
+
 template <int R, int KB, int NB>
 static void launch_ana_t(const ShtPlan *p, const double2 *g_recv, const double2 *const *gsrc, int nchunk, cudaStream_t st)
 {
   const int warps = g_leg_warps_per_cta;
   dim3 grid((nchunk + warps - 1) / warps, p->nm_loc);
-  legendre_analysis_kernel<R, KB, NB><<<grid, 32 * warps, 0, st>>>(
-      g_recv, gsrc, p->d_g_off, p->d_g_stride, p->d_A, p->d_row_off, p->d_ls_ana, p->d_seed, p->d_cth, p->d_m_loc,
-      p->d_alm_off, reinterpret_cast<double2 *>(p->d_part), p->alm_total, p->nrp, (int)p->lmax);
+  if (KB == 8 && g_ana_smem_reduce)
+    legendre_analysis_kernel<R, KB, NB, true><<<grid, 32 * warps, 0, st>>>(
+        g_recv, gsrc, p->d_g_off, p->d_g_stride, p->d_A, p->d_row_off, p->d_ls_ana, p->d_seed, p->d_cth, p->d_m_loc,
+        p->d_alm_off, reinterpret_cast<double2 *>(p->d_part), p->alm_total, p->nrp, (int)p->lmax);
+  else
+    legendre_analysis_kernel<R, KB, NB, false><<<grid, 32 * warps, 0, st>>>(
+        g_recv, gsrc, p->d_g_off, p->d_g_stride, p->d_A, p->d_row_off, p->d_ls_ana, p->d_seed, p->d_cth, p->d_m_loc,
+        p->d_alm_off, reinterpret_cast<double2 *>(p->d_part), p->alm_total, p->nrp, (int)p->lmax);
 }
 
 int launch_legendre_analysis(ShtPlan *p, const double2 *d_g_recv, double *d_alm_re, double *d_alm_im, int apply_filter,

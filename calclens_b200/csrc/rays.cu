@@ -107,8 +107,9 @@ __device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_sr
 // while the current one is being computed in place, and a finished tile leaves as one bulk store.
 __global__ void __launch_bounds__(kRayThreads, 4)
 ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab *__restrict__ tab, long order, double wp,
-                double wpm1, double wpm2, int mode, const unsigned char *__restrict__ need, int coarse_shift,
-                unsigned rank_bit, int *__restrict__ err, double *__restrict__ sum6, PlaneCoef pc)
+                double wpm1, double wpm2, int mode, const unsigned char *__restrict__ need,
+                const unsigned char *__restrict__ safe, int coarse_shift, unsigned rank_bit, int *__restrict__ err,
+                double *__restrict__ sum6, PlaneCoef pc)
 {
   __shared__ __align__(128) unsigned char s_raw[2][kRayThreads * sizeof(Ray)];
   __shared__ __align__(8) unsigned long long s_bar[2];
@@ -157,11 +158,16 @@ ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab 
         ray_interp_accumulate_fast(ray, order, tab, maps.p[0], maps.p[1], maps.p[2], maps.p[3], maps.p[4], maps.p[5], px);
         // sharded runs: every pixel of the stencil must lie inside the part of the sky this rank received (the reference
         // aborts on a missing map cell, shtpoissonsolve.c:683-689; here the flag is raised and the host aborts)
+        // safe[c] (optional) says that cell c AND every cell around it were delivered, which covers any stencil that
+        // starts in c; only rays in the rim of the received region pay for the per-pixel check
         if (need) {
-          unsigned ok = rank_bit;
+          const long c0 = ring2nest(px[0], order) >> coarse_shift;
+          if (!safe || !(safe[c0] & rank_bit)) {
+            unsigned ok = rank_bit & need[c0];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ok &= need[ring2nest(px[k], order) >> coarse_shift];
-          if (!ok) atomicOr(err, 1);
+            for (int k = 1; k < 4; ++k) ok &= need[ring2nest(px[k], order) >> coarse_shift];
+            if (!ok) atomicOr(err, 1);
+          }
         }
       }
       if (mode & 4) {
@@ -200,7 +206,7 @@ ray_step_kernel(Ray *__restrict__ rays, long nrays, RayMaps maps, const RingTab 
 
 int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long order, double wp, double wpm1,
                     double wpm2, int mode, cudaStream_t st, const unsigned char *d_need, long coarse_order, int rank, int *d_err,
-                    double *d_sum6)
+                    double *d_sum6, const unsigned char *d_safe)
 {
   if (nrays <= 0) return 0;
   RayMaps m;
@@ -210,12 +216,13 @@ int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long 
   const RingTab *tab = (mode & 2) ? ring_table(order, st) : nullptr;
   if (d_sum6) CLB_CUDA_CHECK(cudaMemsetAsync(d_sum6, 0, 6 * sizeof(double), st));
   if (d_need && (coarse_order > order || !d_err)) d_need = nullptr;
+  if (!d_need) d_safe = nullptr;
   // plane constants of the A recursion with the reference's expressions (rayprop.c:134-139), host double arithmetic
   PlaneCoef pc;
   pc.ccur = wpm1 * (wp - wpm2) / wp / (wpm1 - wpm2);
   pc.cprev = 1.0 - wpm1 * (wp - wpm2) / wp / (wpm1 - wpm2);
   pc.cu = (wp - wpm1) / wp;
-  ray_step_kernel<<<(unsigned)nblocks, kRayThreads, 0, st>>>(d_rays, nrays, m, tab, order, wp, wpm1, wpm2, mode, d_need,
+  ray_step_kernel<<<(unsigned)nblocks, kRayThreads, 0, st>>>(d_rays, nrays, m, tab, order, wp, wpm1, wpm2, mode, d_need, d_safe,
                                                              (int)(2 * (order - coarse_order)), 1u << rank, d_err, d_sum6, pc);
   if (d_sum6) CLB_CUDA_CHECK(cudaGetLastError());
   CLB_CUDA_CHECK(cudaGetLastError());

@@ -126,15 +126,37 @@ __device__ __forceinline__ double2 root16(int n, int q)
   }
 }
 
+// Twiddles.  A pass over stages lg .. lg-K+1 needs W_L^j = exp(-2 pi i j / 2^lg) for j < 2^(lg-K), i.e. W_M^i with
+// i = j << (logM - lg) < M / 2^K.  The passes are ordered so that every pass with non-trivial twiddles is a radix-16 one
+// (i < M/16), and W_M^i is formed as hi[i >> 5] * lo[i & 31] from two 32-entry tables in shared memory (hi[a] = W_M^(32a),
+// lo[b] = W_M^b) -- no global twiddle loads inside the passes, whose L2 latency was the largest single stall of the
+// Bluestein rings (profiles/r02_ring_fft.txt).  The tables alias the block-reduction scratch (s_red), which is idle
+// while the transforms run; cta_twiddle_tables() rebuilds them after every block reduction.
+constexpr int kTwEntries = 64;   // hi[32] | lo[32]
+__device__ __forceinline__ void cta_twiddle_tables(double2 *stw, int logM, const double2 *__restrict__ tw, int logTW)
+{
+  // (the caller guarantees a barrier between the last use of the aliased scratch and this call)
+  for (int t = threadIdx.x; t < kTwEntries; t += blockDim.x) {   // (small classes run CTAs of 32 threads)
+    const long i = (t < 32) ? ((long)t << 5) : (long)(t - 32);            // exponent of W_M
+    double2 w = make_double2(1.0, 0.0);
+    if (logM >= 1 && i < (1L << (logM - 1))) w = __ldg(&tw[i << (logTW - logM)]);   // table holds exp(-2 pi i k / TW), k < TW/2
+    stw[t] = w;                                                            // (exponents >= M/2 are never requested)
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ double2 tw_get(const double2 *stw, int i)     // W_M^i, i < M/16 <= 1024
+{
+  return cmul(stw[i >> 5], stw[32 + (i & 31)]);
+}
+
 // forward (sign -1) pass over the K stages with block lengths 2^lg, 2^(lg-1), .., 2^(lg-K+1)
 template <int K>
-__device__ __forceinline__ void cta_dif_pass(double2 *a, int M, int lg, const double2 *__restrict__ tw, int logTW,
-                                             double2 *a2 = nullptr)
+__device__ __forceinline__ void cta_dif_pass(double2 *a, int M, int lg, const double2 *stw, double2 *a2 = nullptr)
 {
   constexpr int RR = 1 << K;
   const int s = 1 << (lg - K);
-  const int sh = logTW - lg;
   const int logM = 31 - __clz(M);
+  const int sh = logM - lg;
   const int nbf = M >> K;                      // butterflies per array; a2 (optional) is a second, independent array
   for (int it = threadIdx.x; it < (a2 ? 2 * nbf : nbf); it += blockDim.x) {
     double2 *arr = (it >= nbf) ? a2 : a;
@@ -144,10 +166,9 @@ __device__ __forceinline__ void cta_dif_pass(double2 *a, int M, int lg, const do
     double2 x[RR];
 #pragma unroll
     for (int q = 0; q < RR; ++q) x[q] = arr[swz(base + q * s, logM)];
-    double2 w = __ldg(&tw[(size_t)j << sh]);   // W_L^j
+    double2 w = (s > 1) ? tw_get(stw, j << sh) : make_double2(1.0, 0.0);   // W_L^j
 #pragma unroll
     for (int t = 0; t < K; ++t) {
-      constexpr int dummy = 0; (void)dummy;
       const int half = RR >> (t + 1);
 #pragma unroll
       for (int g = 0; g < RR; g += 2 * half) {
@@ -169,13 +190,13 @@ __device__ __forceinline__ void cta_dif_pass(double2 *a, int M, int lg, const do
 
 // inverse (sign +1) pass: the same K stages in reverse order, conjugate twiddles applied before the butterflies
 template <int K>
-__device__ __forceinline__ void cta_dit_pass(double2 *a, int M, int lg, const double2 *__restrict__ tw, int logTW,
+__device__ __forceinline__ void cta_dit_pass(double2 *a, int M, int lg, const double2 *stw,
                                              const double2 *__restrict__ premul = nullptr)
 {
   constexpr int RR = 1 << K;
   const int s = 1 << (lg - K);
-  const int sh = logTW - lg;
   const int logM = 31 - __clz(M);
+  const int sh = logM - lg;
   for (int idx = threadIdx.x; idx < (M >> K); idx += blockDim.x) {
     const int j = idx & (s - 1);
     const int base = ((idx >> (lg - K)) << lg) + j;
@@ -187,7 +208,7 @@ __device__ __forceinline__ void cta_dit_pass(double2 *a, int M, int lg, const do
       for (int q = 0; q < RR; ++q) x[q] = cmul(x[q], __ldg(&premul[base + q * s]));
     }
     double2 wp[K];                             // W_L^(j 2^t)
-    wp[0] = __ldg(&tw[(size_t)j << sh]);
+    wp[0] = (s > 1) ? tw_get(stw, j << sh) : make_double2(1.0, 0.0);
 #pragma unroll
     for (int t = 1; t < K; ++t) wp[t] = cmul(wp[t - 1], wp[t - 1]);
 #pragma unroll
@@ -210,35 +231,36 @@ __device__ __forceinline__ void cta_dit_pass(double2 *a, int M, int lg, const do
   __syncthreads();
 }
 
-// forward, sign -1, natural order in -> bit-reversed order out
+// forward, sign -1, natural order in -> bit-reversed order out: radix-16 passes from the top stage down, the remaining
+// logM mod 4 stages last (block lengths <= 8: unit twiddle W_L^0 only)
 // a2 (optional): a second array of the same length transformed in the same passes
-__device__ void cta_fft_dif(double2 *a, int logM, const double2 *__restrict__ tw, int logTW, double2 *a2 = nullptr)
+__device__ void cta_fft_dif(double2 *a, int logM, const double2 *stw, double2 *a2 = nullptr)
 {
   const int M = 1 << logM;
   int lg = logM;
-  switch (lg & 3) {   // the remainder stages first, then radix-16 passes
-    case 1: cta_dif_pass<1>(a, M, lg, tw, logTW, a2); lg -= 1; break;
-    case 2: cta_dif_pass<2>(a, M, lg, tw, logTW, a2); lg -= 2; break;
-    case 3: cta_dif_pass<3>(a, M, lg, tw, logTW, a2); lg -= 3; break;
+  for (; lg >= 4; lg -= 4) cta_dif_pass<4>(a, M, lg, stw, a2);
+  switch (lg) {
+    case 1: cta_dif_pass<1>(a, M, 1, stw, a2); break;
+    case 2: cta_dif_pass<2>(a, M, 2, stw, a2); break;
+    case 3: cta_dif_pass<3>(a, M, 3, stw, a2); break;
     default: break;
   }
-  for (; lg >= 4; lg -= 4) cta_dif_pass<4>(a, M, lg, tw, logTW, a2);
 }
 
-// inverse (unnormalised), sign +1, bit-reversed order in -> natural order out
-// premul (optional): the spectrum is multiplied by this table (same order) on its way into the first pass
-__device__ void cta_fft_dit_inv(double2 *a, int logM, const double2 *__restrict__ tw, int logTW,
-                                const double2 *__restrict__ premul = nullptr)
+// inverse (unnormalised), sign +1, bit-reversed order in -> natural order out (the mirror image of cta_fft_dif)
+// premul (optional): the spectrum is multiplied by this table (same order) on its way into the first pass; used when the
+// first pass is the short remainder one, whose threads read consecutive elements (coalesced table reads)
+__device__ void cta_fft_dit_inv(double2 *a, int logM, const double2 *stw, const double2 *__restrict__ premul = nullptr)
 {
   const int M = 1 << logM;
-  int lg = 4;
-  for (; lg <= logM - (logM & 3); lg += 4) { cta_dit_pass<4>(a, M, lg, tw, logTW, premul); premul = nullptr; }
-  switch (logM & 3) {
-    case 1: cta_dit_pass<1>(a, M, logM, tw, logTW, premul); break;
-    case 2: cta_dit_pass<2>(a, M, logM, tw, logTW, premul); break;
-    case 3: cta_dit_pass<3>(a, M, logM, tw, logTW, premul); break;
+  const int rem = logM & 3;
+  switch (rem) {
+    case 1: cta_dit_pass<1>(a, M, 1, stw, premul); premul = nullptr; break;
+    case 2: cta_dit_pass<2>(a, M, 2, stw, premul); premul = nullptr; break;
+    case 3: cta_dit_pass<3>(a, M, 3, stw, premul); premul = nullptr; break;
     default: break;
   }
+  for (int lg = rem + 4; lg <= logM; lg += 4) { cta_dit_pass<4>(a, M, lg, stw, premul); premul = nullptr; }
 }
 
 // block-wide sum of NV doubles per thread; result valid in every thread (red: shared scratch of NV*32 doubles)
@@ -269,18 +291,23 @@ __device__ __forceinline__ int bitrev(int v, int bits) { return bits ? (int)(__b
 // chirp and zero-filled a[r..M).  On return element k of the spectrum is dft_get(a, k, ...).
 // final_chirp = false leaves the last chirp product of the Bluestein path to the caller (dft_get_chirp).
 __device__ void cta_dft_r(double2 *a, int r, int logM, int bluestein, const double2 *__restrict__ chirp,
-                          const double2 *__restrict__ bhat, const double2 *__restrict__ tw, int logTW,
-                          bool final_chirp = true)
+                          const double2 *__restrict__ bhat, const double2 *stw, bool final_chirp = true)
 {
-  cta_fft_dif(a, logM, tw, logTW);
+  cta_fft_dif(a, logM, stw);
   if (!bluestein) return;
   const int M = 1 << logM;
-  // (fusing this product into the first inverse pass costs more than it saves: the pass reads 16 consecutive
-  // elements per thread, which turns the coalesced table read into 32 wavefronts per load)
+  if ((logM & 3) != 0) {
+    // the inverse starts with the short remainder pass (consecutive elements per thread): the product with the chirp
+    // spectrum rides on it
+    cta_fft_dit_inv(a, logM, stw, bhat);
+  } else {
+    // (a radix-16 first pass reads 16 consecutive elements per thread, which would turn the coalesced table read into 32
+    // wavefronts per load: keep the separate product pass)
 #pragma unroll 4
-  for (int k = threadIdx.x; k < M; k += blockDim.x) a[swz(k, logM)] = cmul(a[swz(k, logM)], __ldg(&bhat[k]));
-  __syncthreads();
-  cta_fft_dit_inv(a, logM, tw, logTW);
+    for (int k = threadIdx.x; k < M; k += blockDim.x) a[swz(k, logM)] = cmul(a[swz(k, logM)], __ldg(&bhat[k]));
+    __syncthreads();
+    cta_fft_dit_inv(a, logM, stw);
+  }
   if (!final_chirp) return;
 #pragma unroll 4
   for (int k = threadIdx.x; k < r; k += blockDim.x) a[swz(k, logM)] = cmul(a[swz(k, logM)], __ldg(&chirp[k]));
@@ -305,6 +332,7 @@ __global__ void __launch_bounds__(512) bluestein_table_kernel(const int *__restr
                                        double2 *scratch, long stride)
 {
   extern __shared__ double2 smem_dyn[];
+  __shared__ double2 s_tw[kTwEntries];
   double2 *smem = scratch ? scratch + (long)blockIdx.x * stride : smem_dyn;   // large rings: global scratch
   for (int item = blockIdx.x; item < nr; item += gridDim.x) {
     const int r = rlist[item];
@@ -324,7 +352,8 @@ __global__ void __launch_bounds__(512) bluestein_table_kernel(const int *__restr
       if (j) smem[swz(M - j, logM)] = c;
     }
     __syncthreads();
-    cta_fft_dif(smem, logM, tw, logTW);
+    cta_twiddle_tables(s_tw, logM, tw, logTW);
+    cta_fft_dif(smem, logM, s_tw);
     const double inv = 1.0 / (double)M;   // fold the inverse-FFT normalisation into the table (exact power of two)
     for (int k = threadIdx.x; k < M; k += blockDim.x) bhat[k] = make_double2(smem[swz(k, logM)].x * inv, smem[swz(k, logM)].y * inv);
     __syncthreads();
@@ -408,7 +437,7 @@ __device__ __forceinline__ void ring_analysis_body(const AnaArgs &A, double2 *sm
   // Bins whose twiddles are rational (k = 0, n/4, n/2; real parts of n/6, n/3) are exact sums of floats and sit on
   // float rounding ties with probability ~1/n, where FFT round-off would flip a coin.  They are formed from the
   // exact class sums T[c] = sum_{j = c mod 12} x_j instead (the oracle's exactly-rounded FFT does the same).
-  __shared__ double s_red[12 * 32];
+  __shared__ __align__(16) double s_red[12 * 32];
   double T[12];
   {
     double t3[3][4];
@@ -434,6 +463,8 @@ __device__ __forceinline__ void ring_analysis_body(const AnaArgs &A, double2 *sm
       for (int q = 0; q < 4; ++q) T[4 * a + q] = t3[a][q];
     cta_sum<12>(T, s_red);
   }
+  double2 *stw = reinterpret_cast<double2 *>(s_red);   // the reduction scratch is idle from here on: twiddle tables
+  cta_twiddle_tables(stw, logM, tw, logTW);
 
   for (int pass = 0; pass < 2; ++pass) {
     for (int j = threadIdx.x; j < M; j += blockDim.x) {
@@ -449,7 +480,7 @@ __device__ __forceinline__ void ring_analysis_body(const AnaArgs &A, double2 *sm
       bufA[swz(j, logM)] = z;
     }
     __syncthreads();
-    cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW, pass != 0);
+    cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, stw, pass != 0);
     if (pass == 0) {
       for (int k = threadIdx.x; k < r; k += blockDim.x) bufB[k] = dft_get_chirp(bufA, k, logM, bluestein, chirp);
       __syncthreads();
@@ -601,9 +632,21 @@ struct SynArgs {
   const signed char *rp_logM, *rp_blu; int Mmax, rmax;
   const long *chirp_off, *bhat_off; const double2 *chirp_all, *bhat_all, *tw; int logTW;
   const double2 *phase_all; const long *phase_off;
+  int dbg;            // development aid (clb_set_tuning(8, bits)): 1 no b loads, 2 no transforms, 4 no stores -- wrong results, phase costs
+  int nfg, prefetch;   // field groups per ring (1: all six in one CTA; 3: {0,3},{1,5},{2,4}), L2 prefetch of the next field
 };
 
-__device__ __forceinline__ void ring_synthesis_body(const SynArgs &A, double2 *smem, int work, int field)
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+
+
+// One CTA synthesises two (or all six) fields of one ring, one after the other: work = 2 * (index into the class list) +
+// hemisphere, group = which fields.  Field 1 is always done before 5 and 2 before 4 by the same threads, so the
+// cot(theta) cross terms (alm2allmaps_transpose_mpi.c:1097-1147) are applied on the way out of fields 4 and 5 -- no second
+// kernel, no second pass over the maps.  (An L2 prefetch of the next field's b_m during the transform of the current
+// one was measured and lost 15 %: prefetch.global.L2 moves more than the 16 bytes per 1.5 MB stride this gather needs;
+// it stays behind clb_set_tuning(7, 1).)
+__device__ __forceinline__ void ring_synthesis_body(const SynArgs &A, double2 *smem, int work, int group)
 {
   const double2 *__restrict__ b_recv = A.b_recv; const MapPtrs &maps = A.maps; const RingGeomDev &geo = A.geo;
   const int *__restrict__ class_rp = A.class_rp, *__restrict__ rp_to_local = A.rp_to_local;
@@ -624,7 +667,7 @@ __device__ __forceinline__ void ring_synthesis_body(const SynArgs &A, double2 *s
   const int M = 1 << logM;
   const double2 *PT = phase_all + phase_off[rp];
   const int shifted = geo.shifted[rp];
-  const long fslot = (long)field * nslot_loc + 2 * rp_to_local[rp] + hemi;
+  const long slot = 2 * rp_to_local[rp] + hemi;
   double2 *bufA = smem;
   double2 *bufB = smem + Mmax;
   float2 *tailbuf = reinterpret_cast<float2 *>(smem + Mmax + rmax + 1);
@@ -632,137 +675,190 @@ __device__ __forceinline__ void ring_synthesis_body(const SynArgs &A, double2 *s
   float2 *park = tailbuf;
   const double2 *chirp = bluestein ? chirp_all + chirp_off[r] : nullptr;
   const double2 *bhat = bluestein ? bhat_all + bhat_off[r] : nullptr;
-
-  // S1: folded, phased float bins
-  // four bins per thread and trip, with the global loads of the common single-term bins (and of the phase table) issued
-  // together: this loop is otherwise bound by one exposed L2 round trip per bin
-  for (int kb = threadIdx.x; kb <= 2 * r; kb += 4 * blockDim.x) {
-    double2 bv[4], ph[4];
-    bool valid[4], single[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int k = kb + u * blockDim.x;
-      valid[u] = k <= 2 * r;
-      single[u] = valid[u] && (n - k > lmax) && (k > 0 || n > lmax);   // only m = k lands in this bin (see fold_bin)
-      bv[u] = make_double2(0.0, 0.0); ph[u] = make_double2(1.0, 0.0);
-      if (single[u] && k <= lmax) bv[u] = __ldg(&b_recv[m_boff[k] + fslot]);
-      if (valid[u] && shifted) ph[u] = __ldg(&PT[k]);               // (cos, sin)(k pi / n), tabulated at plan time
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (!valid[u]) continue;
-      const int k = kb + u * blockDim.x;
-      float2 y;
-      if (single[u]) y = make_float2(__double2float_rn(__dadd_rn(0.0, bv[u].x)), __double2float_rn(__dadd_rn(0.0, bv[u].y)));
-      else y = fold_bin(b_recv, m_boff, fslot, k, n, lmax, shifted);
-      if (shifted) {                                                  // [healpix_shtrans.c:186-197]
-        const double c = ph[u].x, s = ph[u].y;
-        const double t0 = (double)y.x, t1 = (double)y.y;
-        y.x = __double2float_rn(__dsub_rn(__dmul_rn(t0, c), __dmul_rn(t1, s)));
-        y.y = __double2float_rn(__dadd_rn(__dmul_rn(t1, c), __dmul_rn(t0, s)));
-      }
-      Y[k] = y;
-    }
-  }
-  __syncthreads();
-  // c2r samples 0, n/4, n/2, 3n/4 have rational twiddles: exact sums of the float bins (same reason and same
-  // formulas as in the oracle's exactly-rounded FFT)
-  __shared__ double s_red[8 * 32];
-  __shared__ float s_special[4];
-  {
-    double cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // R[k&3], I[k&3] over 0 < k < n/2
-    for (int k = 1 + threadIdx.x; k < 2 * r; k += blockDim.x) {
-      const float2 f = Y[k];
-      const int c4 = k & 3;
-      if (c4 == 0) { cs[0] += (double)f.x; cs[4] += (double)f.y; }
-      else if (c4 == 1) { cs[1] += (double)f.x; cs[5] += (double)f.y; }
-      else if (c4 == 2) { cs[2] += (double)f.x; cs[6] += (double)f.y; }
-      else { cs[3] += (double)f.x; cs[7] += (double)f.y; }
-    }
-    cta_sum<8>(cs, s_red);
-    if (threadIdx.x == 0) {
-      const double y0 = (double)Y[0].x, yh = (double)Y[2 * r].x, sr = (r & 1) ? -1.0 : 1.0;
-      s_special[0] = __double2float_rn(y0 + yh + 2.0 * ((cs[0] + cs[1]) + (cs[2] + cs[3])));
-      s_special[1] = __double2float_rn(y0 + sr * yh + 2.0 * ((cs[0] - cs[2]) - (cs[5] - cs[7])));
-      s_special[2] = __double2float_rn(y0 + yh + 2.0 * ((cs[0] + cs[2]) - (cs[1] + cs[3])));
-      s_special[3] = __double2float_rn(y0 + sr * yh + 2.0 * ((cs[0] - cs[2]) + (cs[5] - cs[7])));
-    }
-    __syncthreads();
-  }
-  // S2: x_{4j+q} = IDFT_r(U^(q))_j with U^(q)_{k'} = E^q sum_p i^{qp} Yfull_{k'+p r}, E = exp(2 pi i k'/n).
-  // Two real outputs per complex transform: V1 = U0 + i U1, V2 = U2 + i U3; IDFT(V) = conj(DFT(conj V)).
-  for (int k0 = threadIdx.x; k0 < r; k0 += blockDim.x) {
-    double2 y[4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      const int k = k0 + p * r;
-      float2 f = (k <= 2 * r) ? Y[k] : Y[n - k];
-      y[p] = make_double2((double)f.x, (k <= 2 * r) ? (double)f.y : -(double)f.y);
-      if (k == 0 || k == 2 * r) y[p].y = 0.0;   // c2r ignores the imaginary parts of the DC and Nyquist bins
-    }
-    double2 s02 = cadd(y[0], y[2]), d02 = csub(y[0], y[2]), s13 = cadd(y[1], y[3]), d13 = csub(y[1], y[3]);
-    double2 T0 = cadd(s02, s13), T2 = csub(s02, s13);
-    double2 T1 = cadd(d02, mul_pi(d13)), T3 = csub(d02, mul_pi(d13));
-    double2 E1 = __ldg(&PT[2 * k0]), E2 = cmul(E1, E1), E3 = cmul(E1, E2);   // exp(2 pi i k0 / n)
-    double2 U1 = cmul(T1, E1), U2 = cmul(T2, E2), U3 = cmul(T3, E3);
-    double2 v1 = cconj(cadd(T0, mul_pi(U1)));
-    double2 v2 = cconj(cadd(U2, mul_pi(U3)));
-    if (bluestein) { bufB[k0] = v2; bufA[swz(k0, logM)] = cmul(v1, __ldg(&chirp[k0])); }
-    else { bufB[swz(k0, logM)] = v2; bufA[swz(k0, logM)] = v1; }
-  }
-  __syncthreads();
-  if (!bluestein) {
-    // power-of-two ring: both length-r transforms run in the same passes (all threads busy, half the barriers)
-    cta_fft_dif(bufA, logM, tw, logTW, bufB);
-  } else {
-    for (int k = r + threadIdx.x; k < M; k += blockDim.x) bufA[swz(k, logM)] = make_double2(0.0, 0.0);
-    __syncthreads();
-    cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW, false);
-    // S5: x^(0)_j = Re(res_j), x^(1)_j = -Im(res_j), rounded to float like the reference's c2r output
-    for (int j = threadIdx.x; j < r; j += blockDim.x) {
-      double2 res = dft_get_chirp(bufA, j, logM, bluestein, chirp);
-      park[j] = make_float2(__double2float_rn(res.x), __double2float_rn(-res.y));
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < M; j += blockDim.x) {
-      double2 z = make_double2(0.0, 0.0);
-      if (j < r) z = cmul(bufB[j], __ldg(&chirp[j]));
-      bufA[swz(j, logM)] = z;
-    }
-    __syncthreads();
-    cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, tw, logTW, false);
-  }
-  // S7: float4 of four consecutive pixels, 1/sin(theta) scalings        [alm2allmaps_transpose_mpi.c:1045-1051]
   const double sth = geo.sth[rp];
-  float4 *out = reinterpret_cast<float4 *>(maps.p[field] + start);
-  for (int j = threadIdx.x; j < r; j += blockDim.x) {
-    double2 res;
-    float2 a;
-    if (bluestein) { res = dft_get_chirp(bufA, j, logM, bluestein, chirp); a = park[j]; }
-    else {
-      const int jr = swz(bitrev(j, logM), logM);
-      const double2 r1 = bufA[jr];
-      res = bufB[jr];
-      a = make_float2(__double2float_rn(r1.x), __double2float_rn(-r1.y));
-    }
-    float v[4] = {a.x, a.y, __double2float_rn(res.x), __double2float_rn(-res.y)};
+  const double cot = __ddiv_rn(geo.cth[rp], sth);   // the north ring's cos(theta); signs flip in the south
+  // x / sin(theta) for every pixel of three fields: the reciprocal is rounded once per ring and every quotient gets one
+  // FMA correction step (q = x rs; q += (x - q s) rs), which yields the correctly rounded double quotient (Markstein),
+  // i.e. the same float as the reference's (float)((double)x / sin(theta)), at 3 instructions instead of a division
+  const double rsth = __ddiv_rn(1.0, sth);
+  auto div_sth = [&](float x) {
+    const double xd = (double)x, q = __dmul_rn(xd, rsth);
+    return __double2float_rn(__fma_rn(__fma_rn(-q, sth, xd), rsth, q));
+  };
+  __shared__ __align__(16) double s_red[8 * 32];
+  __shared__ float s_special[4];
+  double2 *stw = reinterpret_cast<double2 *>(s_red);
+  // a bin k receives m = k (term 0) and m = n - k (term 1, conjugated); further terms (n + k, 2n - k, ...) exist only
+  // when n + k <= lmax.  Bins with at most two terms -- every bin of a ring with n > lmax / 2... -- take the batched path.
+  const bool deep = (n <= lmax);                      // some bin has three or more terms: generic fold for all bins
+
+  // the fields this CTA handles, in an order that puts 1 before 5 and 2 before 4 (cot terms)
+  const int nf = (A.nfg == 1) ? 6 : 2;
+#pragma unroll 1
+  for (int fi = 0; fi < nf; ++fi) {
+    const int field = (A.nfg == 1) ? fi : (fi == 0 ? group : (group == 0 ? 3 : group == 1 ? 5 : 4));
+    const int field_next = (A.nfg == 1) ? fi + 1 : (group == 0 ? 3 : group == 1 ? 5 : 4);
+    const long fslot = (long)field * nslot_loc + slot;
+    // S1: folded, phased float bins.  U bins per thread and trip, the global loads of both terms of all U bins (and of
+    // the phase table) issued together: this loop is otherwise bound by one exposed memory round trip per bin
+    constexpr int U = 4;
+    for (int kb = threadIdx.x; kb <= 2 * r; kb += U * blockDim.x) {
+      double2 b0[U], b1[U], ph[U];
+      bool valid[U], two[U];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int pidx = 4 * j + q;   // pixel index within the ring
-      if (pidx == 0) v[q] = s_special[0];
-      else if (pidx == r) v[q] = s_special[1];
-      else if (pidx == 2 * r) v[q] = s_special[2];
-      else if (pidx == 3 * r) v[q] = s_special[3];
-    }
-    if (field == 2 || field == 4 || field == 5) {
+      for (int u = 0; u < U; ++u) {
+        const int k = kb + u * blockDim.x;
+        valid[u] = k <= 2 * r;
+        two[u] = valid[u] && !deep && k > 0 && (n - k <= lmax);     // the conjugated term m = n - k lands here too
+        b0[u] = make_double2(0.0, 0.0); b1[u] = make_double2(0.0, 0.0); ph[u] = make_double2(1.0, 0.0);
+        if (valid[u] && !deep && k <= lmax && !(A.dbg & 1)) b0[u] = __ldg(&b_recv[m_boff[k] + fslot]);
+        if (two[u] && !(A.dbg & 1)) b1[u] = __ldg(&b_recv[m_boff[n - k] + fslot]);
+        if (valid[u] && shifted) ph[u] = __ldg(&PT[k]);               // (cos, sin)(k pi / n), tabulated at plan time
+      }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) v[q] = __double2float_rn(__ddiv_rn((double)v[q], sth));
+      for (int u = 0; u < U; ++u) {
+        if (!valid[u]) continue;
+        const int k = kb + u * blockDim.x;
+        float2 y;
+        if (deep) y = (A.dbg & 1) ? make_float2(1.f, 0.f) : fold_bin(b_recv, m_boff, fslot, k, n, lmax, shifted);
+        else {
+          // exactly the reference's float accumulation (ascending m; alm2allmaps_transpose_mpi.c:836-881): term 0 has
+          // wrap count 0 (sign +1), term 1 wrap count 1 (sign -1 on shifted rings) and enters conjugated
+          y = make_float2(__double2float_rn(__dadd_rn(0.0, b0[u].x)), __double2float_rn(__dadd_rn(0.0, b0[u].y)));
+          if (two[u]) {
+            const double sk = shifted ? -1.0 : 1.0;
+            y.x = __double2float_rn(__dadd_rn((double)y.x, __dmul_rn(b1[u].x, sk)));
+            y.y = __double2float_rn(__dsub_rn((double)y.y, __dmul_rn(b1[u].y, sk)));
+          }
+        }
+        if (shifted) {                                                  // [healpix_shtrans.c:186-197]
+          const double c = ph[u].x, s = ph[u].y;
+          const double t0 = (double)y.x, t1 = (double)y.y;
+          y.x = __double2float_rn(__dsub_rn(__dmul_rn(t0, c), __dmul_rn(t1, s)));
+          y.y = __double2float_rn(__dadd_rn(__dmul_rn(t1, c), __dmul_rn(t0, s)));
+        }
+        Y[k] = y;
+      }
     }
-    if (field == 5) {
+    // the next field's b_m start their trip from HBM into L2 now and arrive while this field is transformed
+    if (A.prefetch && fi + 1 < nf && !deep) {
+      const long fnext = (long)field_next * nslot_loc + slot;
+      for (int k = threadIdx.x; k <= 2 * r; k += blockDim.x) {
+        if (k <= lmax) prefetch_l2(&b_recv[m_boff[k] + fnext]);
+        if (k > 0 && n - k <= lmax && n - k > 2 * r) prefetch_l2(&b_recv[m_boff[n - k] + fnext]);
+      }
+    }
+    __syncthreads();
+    // c2r samples 0, n/4, n/2, 3n/4 have rational twiddles: exact sums of the float bins (same reason and same
+    // formulas as in the oracle's exactly-rounded FFT)
+    {
+      double cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // R[k&3], I[k&3] over 0 < k < n/2
+      for (int k = 1 + threadIdx.x; k < 2 * r; k += blockDim.x) {
+        const float2 f = Y[k];
+        const int c4 = k & 3;
+        if (c4 == 0) { cs[0] += (double)f.x; cs[4] += (double)f.y; }
+        else if (c4 == 1) { cs[1] += (double)f.x; cs[5] += (double)f.y; }
+        else if (c4 == 2) { cs[2] += (double)f.x; cs[6] += (double)f.y; }
+        else { cs[3] += (double)f.x; cs[7] += (double)f.y; }
+      }
+      cta_sum<8>(cs, s_red);
+      if (threadIdx.x == 0) {
+        const double y0 = (double)Y[0].x, yh = (double)Y[2 * r].x, sr = (r & 1) ? -1.0 : 1.0;
+        s_special[0] = __double2float_rn(y0 + yh + 2.0 * ((cs[0] + cs[1]) + (cs[2] + cs[3])));
+        s_special[1] = __double2float_rn(y0 + sr * yh + 2.0 * ((cs[0] - cs[2]) - (cs[5] - cs[7])));
+        s_special[2] = __double2float_rn(y0 + yh + 2.0 * ((cs[0] + cs[2]) - (cs[1] + cs[3])));
+        s_special[3] = __double2float_rn(y0 + sr * yh + 2.0 * ((cs[0] - cs[2]) + (cs[5] - cs[7])));
+      }
+      cta_twiddle_tables(stw, logM, tw, logTW);   // (cta_sum ended on a barrier; this one ends on a barrier too)
+    }
+    // S2: x_{4j+q} = IDFT_r(U^(q))_j with U^(q)_{k'} = E^q sum_p i^{qp} Yfull_{k'+p r}, E = exp(2 pi i k'/n).
+    // Two real outputs per complex transform: V1 = U0 + i U1, V2 = U2 + i U3; IDFT(V) = conj(DFT(conj V)).
+    for (int k0 = threadIdx.x; k0 < r; k0 += blockDim.x) {
+      double2 y[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) v[q] = __double2float_rn(__ddiv_rn((double)v[q], sth));
+      for (int p = 0; p < 4; ++p) {
+        const int k = k0 + p * r;
+        float2 f = (k <= 2 * r) ? Y[k] : Y[n - k];
+        y[p] = make_double2((double)f.x, (k <= 2 * r) ? (double)f.y : -(double)f.y);
+        if (k == 0 || k == 2 * r) y[p].y = 0.0;   // c2r ignores the imaginary parts of the DC and Nyquist bins
+      }
+      double2 s02 = cadd(y[0], y[2]), d02 = csub(y[0], y[2]), s13 = cadd(y[1], y[3]), d13 = csub(y[1], y[3]);
+      double2 T0 = cadd(s02, s13), T2 = csub(s02, s13);
+      double2 T1 = cadd(d02, mul_pi(d13)), T3 = csub(d02, mul_pi(d13));
+      double2 E1 = __ldg(&PT[2 * k0]), E2 = cmul(E1, E1), E3 = cmul(E1, E2);   // exp(2 pi i k0 / n)
+      double2 U1 = cmul(T1, E1), U2 = cmul(T2, E2), U3 = cmul(T3, E3);
+      double2 v1 = cconj(cadd(T0, mul_pi(U1)));
+      double2 v2 = cconj(cadd(U2, mul_pi(U3)));
+      if (bluestein) { bufB[k0] = v2; bufA[swz(k0, logM)] = cmul(v1, __ldg(&chirp[k0])); }
+      else { bufB[swz(k0, logM)] = v2; bufA[swz(k0, logM)] = v1; }
     }
-    out[j] = make_float4(v[0], v[1], v[2], v[3]);
+    __syncthreads();
+    if (A.dbg & 2) {
+    } else if (!bluestein) {
+      // power-of-two ring: both length-r transforms run in the same passes (all threads busy, half the barriers)
+      cta_fft_dif(bufA, logM, stw, bufB);
+    } else {
+      for (int k = r + threadIdx.x; k < M; k += blockDim.x) bufA[swz(k, logM)] = make_double2(0.0, 0.0);
+      __syncthreads();
+      cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, stw, false);
+      // S5: x^(0)_j = Re(res_j), x^(1)_j = -Im(res_j), rounded to float like the reference's c2r output
+      for (int j = threadIdx.x; j < r; j += blockDim.x) {
+        double2 res = dft_get_chirp(bufA, j, logM, bluestein, chirp);
+        park[j] = make_float2(__double2float_rn(res.x), __double2float_rn(-res.y));
+      }
+      __syncthreads();
+      for (int j = threadIdx.x; j < M; j += blockDim.x) {
+        double2 z = make_double2(0.0, 0.0);
+        if (j < r) z = cmul(bufB[j], __ldg(&chirp[j]));
+        bufA[swz(j, logM)] = z;
+      }
+      __syncthreads();
+      cta_dft_r(bufA, r, logM, bluestein, chirp, bhat, stw, false);
+    }
+    // S7: float4 of four consecutive pixels, 1/sin(theta) scalings        [alm2allmaps_transpose_mpi.c:1045-1051]
+    float4 *out = reinterpret_cast<float4 *>(maps.p[field] + start);
+    for (int j = threadIdx.x; j < r; j += blockDim.x) {
+      double2 res;
+      float2 a;
+      if (bluestein) { res = dft_get_chirp(bufA, j, logM, bluestein, chirp); a = park[j]; }
+      else {
+        const int jr = swz(bitrev(j, logM), logM);
+        const double2 r1 = bufA[jr];
+        res = bufB[jr];
+        a = make_float2(__double2float_rn(r1.x), __double2float_rn(-r1.y));
+      }
+      float v[4] = {a.x, a.y, __double2float_rn(res.x), __double2float_rn(-res.y)};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int pidx = 4 * j + q;   // pixel index within the ring
+        if (pidx == 0) v[q] = s_special[0];
+        else if (pidx == r) v[q] = s_special[1];
+        else if (pidx == 2 * r) v[q] = s_special[2];
+        else if (pidx == 3 * r) v[q] = s_special[3];
+      }
+      if (field == 2 || field == 4 || field == 5) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = div_sth(v[q]);
+      }
+      if (field == 5) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = div_sth(v[q]);
+      }
+      // cot(theta) cross terms [alm2allmaps_transpose_mpi.c:1097-1147]: map4 -= cot * map2, map5 += cot * map1 on northern
+      // rings, opposite signs on southern ones.  Fields 1 and 2 of these pixels were stored by this very thread.
+      if (field == 4 || field == 5) {
+        const float4 o = reinterpret_cast<const float4 *>(maps.p[field == 4 ? 2 : 1] + start)[j];
+        const float ov[4] = {o.x, o.y, o.z, o.w};
+        const bool sub = (field == 4) != (hemi != 0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double c = __dmul_rn(cot, (double)ov[q]);
+          v[q] = __double2float_rn(sub ? __dsub_rn((double)v[q], c) : __dadd_rn((double)v[q], c));
+        }
+      }
+      if (!(A.dbg & 4) || v[0] == 1.2345f) out[j] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __syncthreads();   // the work buffers (Y overlays bufA on the Bluestein path) are rewritten by the next field
   }
 }
 
@@ -774,32 +870,9 @@ __global__ void __launch_bounds__(512) ring_synthesis_kernel(SynArgs A)
 __global__ void __launch_bounds__(512) ring_synthesis_scratch_kernel(SynArgs A, double2 *scratch, long stride, int nwork)
 {
   double2 *buf = scratch + (long)blockIdx.x * stride;
-  for (int item = blockIdx.x; item < 6 * nwork; item += gridDim.x) {
-    ring_synthesis_body(A, buf, item / 6, item % 6);
+  for (int item = blockIdx.x; item < nwork * A.nfg; item += gridDim.x) {
+    ring_synthesis_body(A, buf, item / A.nfg, item % A.nfg);
     __syncthreads();
-  }
-}
-
-// cot(theta) cross terms, one CTA per (local ring pair, hemisphere)    [alm2allmaps_transpose_mpi.c:1097-1147]
-__global__ void ring_cot_terms_kernel(MapPtrs maps, RingGeomDev geo, const int *__restrict__ rp_loc)
-{
-  const int rp = rp_loc[blockIdx.x >> 1];
-  const int hemi = blockIdx.x & 1;
-  const long start = hemi ? geo.startS[rp] : geo.startN[rp];
-  if (start < 0) return;
-  const int n = geo.nphi[rp];
-  const double cot = __ddiv_rn(geo.cth[rp], geo.sth[rp]);   // the north ring's cos(theta); signs flip in the south
-  const float *mvt = maps.p[1] + start, *mvp = maps.p[2] + start;
-  float *mvtp = maps.p[4] + start, *mvpp = maps.p[5] + start;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    double a = __dmul_rn(cot, (double)mvp[i]), b = __dmul_rn(cot, (double)mvt[i]);
-    if (!hemi) {
-      mvtp[i] = __double2float_rn(__dsub_rn((double)mvtp[i], a));
-      mvpp[i] = __double2float_rn(__dadd_rn((double)mvpp[i], b));
-    } else {
-      mvtp[i] = __double2float_rn(__dadd_rn((double)mvtp[i], a));
-      mvpp[i] = __double2float_rn(__dsub_rn((double)mvpp[i], b));
-    }
   }
 }
 
@@ -807,6 +880,9 @@ __global__ void ring_cot_terms_kernel(MapPtrs maps, RingGeomDev geo, const int *
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 constexpr size_t kMaxSmem = 227 * 1024;
+int g_fft_field_groups = 0;     // clb_set_tuning(6, 0|1|3): CTAs per ring and hemisphere; 0 = default (3: fields {0,3}, {1,5}, {2,4})
+int g_fft_debug = 0;
+int g_fft_prefetch = 0;         // clb_set_tuning(7, 0|1): L2 prefetch of the next field's b_m
 int g_fft_force_scratch = 0;    // clb_set_tuning(4, 1): run every ring FFT from global scratch (tests the large-ring path at small Nside)
 int g_fft_threads_big = 512;   // threads per CTA for work lengths >= 4096 (clb_set_tuning(2, .))
 
@@ -963,6 +1039,8 @@ void fft_tables_create(ShtPlan *p)
     c.smem_ana = sizeof(double2) * (M + c.rmax);
     c.smem_syn = sizeof(double2) * (M + c.rmax + 1) + sizeof(float2) * c.tail;
     max_ana = std::max(max_ana, c.smem_ana); max_syn = std::max(max_syn, c.smem_syn);
+    // longest rings first: CTAs are dispatched in order, so the short ones fill the tail of the launch
+    std::stable_sort(members[k].begin(), members[k].end(), [&](int x, int y) { return p->h_nphi[x] > p->h_nphi[y]; });
     CLB_CUDA_CHECK(cudaMalloc(&c.d_rp, sizeof(int) * c.count));
     CLB_CUDA_CHECK(cudaMemcpy(c.d_rp, members[k].data(), sizeof(int) * c.count, cudaMemcpyHostToDevice));
     t->classes.push_back(c);
@@ -1019,20 +1097,19 @@ int launch_ring_synthesis(const ShtPlan *p, const double2 *d_b_recv, float *cons
   for (const auto &c : t->classes) {
     SynArgs A{d_b_recv, mp, geom_of(p), c.d_rp, plan_rp_to_local(p), p->d_m_boff, 2 * p->nrp_loc, (int)p->lmax, t->d_rp_logM,
               t->d_rp_blu, 1 << c.logM, c.rmax, t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat, t->d_tw, t->logTW,
-              t->d_phase, t->d_phase_off};
+              t->d_phase, t->d_phase_off, g_fft_debug, 1, g_fft_prefetch};
+    A.nfg = g_fft_field_groups ? g_fft_field_groups : 3;
     if (c.smem_syn <= kMaxSmem && !g_fft_force_scratch) {
-      dim3 grid(2 * c.count, 6);
+      dim3 grid(2 * c.count, A.nfg);
       ring_synthesis_kernel<<<grid, c.threads, c.smem_syn, st>>>(A);
     } else {
-      const int nwork = 2 * c.count, ctas = std::min(6 * nwork, scratch_ctas());
+      const int nwork = 2 * c.count, ctas = std::min(nwork * A.nfg, scratch_ctas());
       const long stride = (long)((c.smem_syn + 255) / 256) * 16;
       double2 *scr = fft_scratch(t, (size_t)ctas * stride * sizeof(double2));
       ring_synthesis_scratch_kernel<<<ctas, 512, 0, st>>>(A, scr, stride, nwork);
     }
     ++launches;
   }
-  ring_cot_terms_kernel<<<2 * p->nrp_loc, 256, 0, st>>>(mp, geom_of(p), p->d_rp_loc);
-  ++launches;
   CLB_CUDA_CHECK(cudaGetLastError());
   return launches;
 }

@@ -286,7 +286,8 @@ static void ray_update(Solver *s, double wpp1, double wp, double wpm1, int mode,
   const float *mp[6];
   for (int k = 0; k < 6; ++k) mp[k] = s->maps + (size_t)k * s->npix;
   LAUNCHED(s) launch_ray_step(s->rays, s->nrays, mp, s->order, wpp1, wp, wpm1, mode, st, s->d_need, kCoarseOrder, s->rank,
-                                 s->d_need ? s->d_err : nullptr, with_summary ? s->d_sum6 : nullptr);
+                                 s->d_need ? s->d_err : nullptr, with_summary ? s->d_sum6 : nullptr,
+                                 s->d_need ? s->d_need + (12L << (2 * kCoarseOrder)) : nullptr);
   mark(s, 9, st);
 }
 
@@ -389,8 +390,12 @@ clb_solver *clb_solver_create(long sht_order, long lmax, long ray_order, const d
       const double spacing = sqrt(4.0 * CLB_PI / (double)nc);
       std::vector<unsigned char> mask(nc);
       domain_masks(s->ray_order, nranks, kCoarseOrder, halo_deg * CLB_PI / 180.0 + 2.0 * 1.2 * spacing, mask.data());
-      s->d_need = (unsigned char *)dmalloc(nc);
+      // second half of the buffer: cells whose whole neighbourhood (2.5 cell spacings: every cell a stencil can reach) is delivered
+      std::vector<unsigned char> safe(nc);
+      safe_masks(kCoarseOrder, 2.5 * spacing, mask.data(), safe.data());
+      s->d_need = (unsigned char *)dmalloc(2 * nc);
       CLB_CUDA_CHECK(cudaMemcpy(s->d_need, mask.data(), nc, cudaMemcpyHostToDevice));
+      CLB_CUDA_CHECK(cudaMemcpy(s->d_need + nc, safe.data(), nc, cudaMemcpyHostToDevice));
       long bits = 0;
       for (long c = 0; c < nc; ++c) bits += __builtin_popcount(mask[c]);
       s->need_fraction = (double)bits / ((double)nc * nranks);

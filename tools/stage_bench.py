@@ -14,6 +14,10 @@ for a in sys.argv[3:]:
     elif a.startswith("warps="): _lib.load().clb_set_tuning(3, int(a[6:]))
     elif a.startswith("fft="): _lib.load().clb_set_tuning(2, int(a[4:]))
     elif a.startswith("scratch="): _lib.load().clb_set_tuning(4, int(a[8:]))
+    elif a.startswith("sr="): _lib.load().clb_set_tuning(5, int(a[3:]))
+    elif a.startswith("fg="): _lib.load().clb_set_tuning(6, int(a[3:]))
+    elif a.startswith("pf="): _lib.load().clb_set_tuning(7, int(a[3:]))
+    elif a.startswith("dbg="): _lib.load().clb_set_tuning(8, int(a[4:]))
     else: reps = int(a)
 L = _lib.load()
 plan = clb.HEALPixSHTPlan(order, lmax)
