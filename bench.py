@@ -285,9 +285,25 @@ def measure(a, L, poisson, torch, dist, world, rank, local_rank, group, order, r
             return float(t.item())
         return ms
 
+    # Two shells per SHT pass (--shells 2, the default): inside a run of n consecutive planes, plane 0 is solved together with
+    # plane 1, plane 2 with plane 3, ...; an odd last plane is solved alone.  A run therefore does exactly n planes of work.
+    def run_planes(first, n, maps, read_summary=False, prefetch=False):
+        summ = None
+        for i in range(n):
+            s = first + i
+            pair = None
+            if a.shells == 2 and i % 2 == 0 and i + 1 < n:
+                pair = (maps[(s + 1) % nmaps],) + tuple(plane_args(s + 1, peek=True)[:3])
+            pre = None
+            if prefetch:   # host maps: the planes to come stream in behind this plane's kernels
+                ahead = [s + 1] if a.shells == 1 else ([s + 2, s + 3] if i % 2 == 0 else [])
+                pre = [(maps[q % nmaps],) + tuple(plane_args(q, peek=True)[:3]) for q in ahead] or None
+            summ = solver.step(maps[s % nmaps], *plane_args(s), read_summary=read_summary, prefetch=pre, pair=pair)
+            yield s, summ
+
     # ---- device-resident throughput ("value"): count maps already in HBM, no host synchronisation between planes
-    for s in range(warmup):
-        solver.step(dev_maps[s % nmaps], *plane_args(s), read_summary=False)
+    for _ in run_planes(0, warmup, dev_maps):
+        pass
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -296,20 +312,21 @@ def measure(a, L, poisson, torch, dist, world, rank, local_rank, group, order, r
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     torch.cuda.profiler.start()    # lets `ncu --profile-from-start off` list exactly the timed region's launches
     e0.record()
-    for s in range(steps):
-        solver.step(dev_maps[(warmup + s) % nmaps], *plane_args(warmup + s), read_summary=False)
+    for _ in run_planes(warmup, steps, dev_maps):
+        pass
     e1.record()
     barrier()
     torch.cuda.profiler.stop()
     launches = L.clb_launch_count() - launches0
     ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / steps
     clocks = sampler.stop() if rank == 0 else None
-    # per-stage times (CUDA events recorded inside the solver on the launching stream), a separate pass of the same steps
+    # per-stage times (CUDA events recorded inside the solver on the launching stream), a separate pass of the same steps;
+    # with two shells per pass a pair's SHT stages are recorded on its first plane and the second records rays only, so the
+    # sums divided by the number of planes are per-plane averages
     stage_ms = {k: 0.0 for k in STAGES}
     solver.set_timing(True)
     base = warmup + steps
-    for s in range(steps):
-        solver.step(dev_maps[(base + s) % nmaps], *plane_args(base + s), read_summary=False)
+    for _ in run_planes(base, steps, dev_maps):
         for k, v in zip(STAGES, solver.stage_ms()):
             stage_ms[k] += v / steps
     solver.set_timing(False)
@@ -317,18 +334,16 @@ def measure(a, L, poisson, torch, dist, world, rank, local_rank, group, order, r
     out = {"ms_per_step": ms_per_step, "stage_ms": stage_ms, "launches": launches, "clocks": clocks, "setup_s": t_setup,
            "npix": solver.npix, "fused": solver.fused, "host_barriers": getattr(solver, "host_barriers", False)}
     if with_e2e:
-        # ---- end to end through the public API with host buffers: H2D of the plane's map (prefetched behind the previous
-        # plane's kernels) + D2H of the six ray sums every step
-        for s in range(min(warmup, 2)):
-            nxt = (host_maps[(base + s + 1) % nmaps],) + tuple(plane_args(base + s + 1, peek=True)[:3])
-            solver.step(host_maps[(base + s) % nmaps], *plane_args(base + s), prefetch=nxt)
-        base += min(warmup, 2)
+        # ---- end to end through the public API with host buffers: H2D of every plane's map (prefetched behind the previous
+        # planes' kernels) + D2H of the six ray sums every step
+        for _ in run_planes(base, 2, host_maps, read_summary=True, prefetch=True):
+            pass
+        base += 2
         barrier()
         e0.record()
         summ = None
-        for s in range(steps):
-            nxt = (host_maps[(base + s + 1) % nmaps],) + tuple(plane_args(base + s + 1, peek=True)[:3])
-            summ = solver.step(host_maps[(base + s) % nmaps], *plane_args(base + s), prefetch=nxt)
+        for _, summ in run_planes(base, steps, host_maps, read_summary=True, prefetch=True):
+            pass
         e1.record()
         barrier()
         out["e2e_ms"] = max_over_ranks(e0.elapsed_time(e1)) / steps
@@ -393,6 +408,9 @@ def main():
                     help="log2 Nside of the bounded CPU sample (the same in the reference arm and in the GPU arm's cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lmax3", action="store_true", help="skip the second measurement at the reference's own lmax = 3 Nside - 1")
+    ap.add_argument("--shells", type=int, default=2, choices=[1, 2],
+                    help="lens planes per SHT pass: 2 = consecutive planes share one pass of each Legendre kernel (the lambda_lm "
+                         "recurrence is generated once for both), 1 = plane by plane like the reference")
     ap.add_argument("--sweep", action="store_true", help="BASELINE configs[3]: SHT round-trip sweep over Nside, one JSON line per size")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="multi-GPU exchange: stores into peer memory from the producing kernels, or NCCL all-to-all + all-reduce")
@@ -403,6 +421,8 @@ def main():
         a.ray_nside = a.nside
     if a.impl == "reference":
         return run_reference_arm(a)
+    if a.exchange == "nccl" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        a.shells = 1     # the NCCL comparison arm runs plane by plane
 
     # stdout carries exactly one JSON line: libraries that print to fd 1 (NCCL's version banner, ...) go to stderr
     sys.stdout.flush()
@@ -518,11 +538,13 @@ def main():
                 "ray_plane_updates_per_s": value * nrays_total,
                 "e2e": {"value": 1000.0 / r["e2e_ms"], "unit": "planes/s", "ms_per_step": r["e2e_ms"], "h2d_bytes_per_step": 4 * r["npix"],
                         "d2h_bytes_per_step": 48 * world,
-                        "api": "C ABI clb_solver_set_next + clb_solver_step(pinned host count map, &sum6) of libcalclens_b200.so (called through "
-                               "calclens_b200.poisson.LensPlaneSolver.step): host map in, six ray sums out; every rank reads only its own rings of the host map",
+                        "api": "C ABI clb_solver_set_pair + clb_solver_set_next + clb_solver_step(pinned host count map, &sum6) of libcalclens_b200.so "
+                               "(called through calclens_b200.poisson.LensPlaneSolver.step): host map in, six ray sums out, every plane; every rank "
+                               "reads only its own rings of the host map",
                         "last_summary": r["last_summary"],
                         "checksum_note": "the six ray sums after the last timed plane; inputs depend only on (l, m, seed), so lines at different N are comparable"},
                 "gpu_launches": int(r["launches"] * world),
+                "shells_per_pass": a.shells,
                 "clocks": r["clocks"],
                 "roofline": roofline, "roofline_stages": stages, "stage_ms": stage_ms,
                 "hbm_peak_source": hbm_src,

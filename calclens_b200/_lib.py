@@ -40,12 +40,15 @@ def load():
         "clb_peer_import": (vp, [vp]),
         "clb_peer_release": (None, [vp]),
         "clb_sht_plan_set_peers": (None, [vp, vp, vp]),
+        "clb_sht_plan_set_peers_shells": (None, [vp, vp, vp, C.c_int]),
         "clb_maps_broadcast_dev": (C.c_int, [vp, vp, vp, vp, C.c_long, vp]),
         "clb_domain_masks": (None, [C.c_long, C.c_int, C.c_long, C.c_double, vp]),
         "clb_ray_step_ex_dev": (C.c_int, [vp, C.c_long, vp, C.c_long, C.c_double, C.c_double, C.c_double, C.c_int, vp, C.c_long, C.c_int, vp, vp, vp]),
         "clb_ring_analysis_dev": (C.c_int, [vp, vp, vp, vp]),
         "clb_legendre_analysis_dev": (C.c_int, [vp, vp, vp, vp, C.c_int, vp]),
         "clb_legendre_synthesis_dev": (C.c_int, [vp, vp, vp, vp, vp]),
+        "clb_legendre_analysis_shells_dev": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, vp]),
+        "clb_legendre_synthesis_shells_dev": (C.c_int, [vp, vp, vp, vp, C.c_int, vp]),
         "clb_ring_synthesis_dev": (C.c_int, [vp, vp, vp, vp]),
         "clb_scale_density_dev": (C.c_int, [vp, C.c_long, C.c_float, C.c_float, C.c_float, vp]),
         "clb_load_density_dev": (C.c_int, [vp, vp, vp, C.c_float, C.c_float, C.c_float, vp]),
@@ -77,6 +80,7 @@ def load():
         "clb_solver_ray_output": (None, [vp, vp, vp]),
         "clb_solver_step": (C.c_int, [vp, vp, C.c_float, C.c_float, C.c_float, C.c_double, C.c_double, C.c_double, vp, vp]),
         "clb_solver_set_next": (None, [vp, vp, C.c_float, C.c_float, C.c_float]),
+        "clb_solver_set_pair": (None, [vp, vp, C.c_float, C.c_float, C.c_float]),
         "clb_solver_check": (C.c_int, [vp, vp]),
         "clb_solver_load_density": (None, [vp, vp, C.c_float, C.c_float, C.c_float, vp]),
         "clb_solver_solve": (None, [vp, vp, vp]),

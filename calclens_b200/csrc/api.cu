@@ -4,7 +4,7 @@
 #include <string.h>
 
 namespace clb {
-extern int g_syn_rings_per_thread, g_ana_rings_per_thread, g_fft_threads_big, g_leg_warps_per_cta, g_fft_force_scratch, g_ana_smem_reduce, g_fft_field_groups, g_fft_prefetch, g_fft_debug;
+extern int g_syn_rings_per_thread, g_ana_rings_per_thread, g_fft_threads_big, g_leg_warps_per_cta, g_fft_force_scratch, g_ana_rows, g_syn2_rings_per_thread, g_ana2_rings_per_thread, g_fft_field_groups, g_fft_prefetch, g_fft_debug, g_solver_shells;
 
 // safe[c] = AND of mask[d] over every cell d whose centre lies within neighbour_rad of c's centre (c included): a ray whose
 // stencil starts in a "safe" cell cannot touch an undelivered pixel, so the ray kernel skips the per-pixel mask check there
@@ -115,13 +115,16 @@ void clb_set_tuning(int what, int value)
 {
   if (what == 0 && value >= 1 && value <= 4) g_syn_rings_per_thread = value;
   if (what == 4) g_fft_force_scratch = value ? 1 : 0;
-  if (what == 5) g_ana_smem_reduce = value ? 1 : 0;
+  if (what == 5 && value >= 0) g_ana_rows = value;   // partial-sum rows per m of the Legendre analysis (0 = automatic)
+  if (what == 11 && (value == 1 || value == 2)) g_solver_shells = value;   // read by clb_solver_create
+  if (what == 9 && value >= 1 && value <= 4) g_syn2_rings_per_thread = value;
+  if (what == 10 && (value == 1 || value == 2 || value == 4 || value == 6 || value == 8)) g_ana2_rings_per_thread = value;
   if (what == 6 && (value == 0 || value == 1 || value == 3)) g_fft_field_groups = value;
   if (what == 7) g_fft_prefetch = value ? 1 : 0;
   if (what == 8) g_fft_debug = value;   // development aid: skip phases of the ring synthesis (wrong results)
   if (what == 3 && (value == 1 || value == 2 || value == 4)) g_leg_warps_per_cta = value;
   if (what == 2 && (value == 256 || value == 512 || value == 768 || value == 1024)) g_fft_threads_big = value;   // read at plan creation
-  if (what == 1 && (value == 1 || value == 2 || value == 4 || value == 6 || value == 8 || value == 10 || value == 12)) g_ana_rings_per_thread = value;
+  if (what == 1 && (value == 1 || value == 2 || value == 4 || value == 6 || value == 8)) g_ana_rings_per_thread = value;
 }
 
 clb_sht_plan *clb_sht_plan_create(long order, long lmax, const double *ring_weights, int nranks, int rank,
@@ -210,7 +213,11 @@ void *clb_peer_import(const void *handle64)
 void clb_peer_release(void *p) { if (p) CLB_CUDA_CHECK(cudaIpcCloseMemHandle(p)); }
 void clb_sht_plan_set_peers(clb_sht_plan *plan, void *const *g_send_ptrs, void *const *b_recv_ptrs)
 {
-  sht_plan_set_peers(P(plan), g_send_ptrs, b_recv_ptrs);
+  sht_plan_set_peers(P(plan), g_send_ptrs, b_recv_ptrs, 1);
+}
+void clb_sht_plan_set_peers_shells(clb_sht_plan *plan, void *const *g_send_ptrs, void *const *b_recv_ptrs, int nshell)
+{
+  sht_plan_set_peers(P(plan), g_send_ptrs, b_recv_ptrs, nshell);
 }
 int clb_maps_broadcast_dev(const clb_sht_plan *plan, float *const local_maps[6], float *const *peer_maps,
                            const unsigned char *need, long coarse_order, void *stream)
@@ -238,6 +245,19 @@ int clb_legendre_analysis_dev(clb_sht_plan *plan, const double *g_recv, double *
 int clb_legendre_synthesis_dev(clb_sht_plan *plan, const double *alm_re, const double *alm_im, double *b_send, void *stream)
 {
   int n = launch_legendre_synthesis(P(plan), alm_re, alm_im, reinterpret_cast<double2 *>(b_send), (cudaStream_t)stream);
+  g_launches += n; return n;
+}
+int clb_legendre_analysis_shells_dev(clb_sht_plan *plan, const double *g_recv, double *alm_re, double *alm_im,
+                                     int apply_poisson_filter, int nshell, void *stream)
+{
+  int n = launch_legendre_analysis(P(plan), reinterpret_cast<const double2 *>(g_recv), alm_re, alm_im,
+                                   apply_poisson_filter, (cudaStream_t)stream, nshell);
+  g_launches += n; return n;
+}
+int clb_legendre_synthesis_shells_dev(clb_sht_plan *plan, const double *alm_re, const double *alm_im, double *b_send,
+                                      int nshell, void *stream)
+{
+  int n = launch_legendre_synthesis(P(plan), alm_re, alm_im, reinterpret_cast<double2 *>(b_send), (cudaStream_t)stream, nshell);
   g_launches += n; return n;
 }
 int clb_ring_synthesis_dev(const clb_sht_plan *plan, const double *b_recv, float *const maps[6], void *stream)

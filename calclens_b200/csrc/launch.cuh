@@ -8,12 +8,13 @@ namespace clb {
 ShtPlan *sht_plan_create(long order, long lmax, const double *ring_weights, int nranks, int rank, const int *rp_owner,
                          const int *m_owner);
 void sht_plan_destroy(ShtPlan *p);
-void sht_plan_set_peers(ShtPlan *p, void *const *g_send_ptrs, void *const *b_recv_ptrs);
+void sht_plan_set_peers(ShtPlan *p, void *const *g_send_ptrs, void *const *b_recv_ptrs, int nshell = 1);
 int launch_ring_analysis(const ShtPlan *p, const float *d_map, double2 *d_g_send, cudaStream_t st);
 int launch_ring_synthesis(const ShtPlan *p, const double2 *d_b_recv, float *const d_maps[6], cudaStream_t st);
 int launch_legendre_analysis(ShtPlan *p, const double2 *d_g_recv, double *d_alm_re, double *d_alm_im, int apply_filter,
-                             cudaStream_t st);
-int launch_legendre_synthesis(ShtPlan *p, const double *d_alm_re, const double *d_alm_im, double2 *d_b_send, cudaStream_t st);
+                             cudaStream_t st, int nshell = 1);
+int launch_legendre_synthesis(ShtPlan *p, const double *d_alm_re, const double *d_alm_im, double2 *d_b_send, cudaStream_t st,
+                              int nshell = 1);
 int launch_ray_step(Ray *d_rays, long nrays, const float *const d_maps[6], long order, double wp, double wpm1, double wpm2,
                     int mode, cudaStream_t st, const unsigned char *d_need = nullptr, long coarse_order = 0, int rank = 0,
                     int *d_err = nullptr, double *d_sum6 = nullptr, const unsigned char *d_safe = nullptr);

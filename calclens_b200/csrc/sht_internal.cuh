@@ -75,16 +75,18 @@ struct ShtPlan {
   int *d_ls_ana = nullptr, *d_ls_syn = nullptr;
   double2 *d_seed = nullptr;   // (mu_{ls-1}, mu_{ls})
   // plane-dependent scratch
-  double *d_coef = nullptr;    // [rows_total][8]: A, Pre, Pim, Dre, Dim, Kre, Kim, 0
-  double *d_part = nullptr;    // analysis partial sums [nchunk][alm_total][2]
+  double *d_coef = nullptr;    // [rows_total][8 * coef_shells]: A, Pre, Pim, Dre, Dim, Kre, Kim, 0 (one shell; legendre.cu for two)
+  int coef_shells = 1;
+  double *d_part = nullptr;    // analysis partial sums [shell][row][alm_total][2] (ana_nchunk = rows * shells allocated)
   int ana_nchunk = 0, ana_chunk = 0, syn_chunk = 0;
   long alm_total = 0;          // sum over local m of (lmax-m+1)
   std::vector<long> h_alm_off;
   long *d_alm_off = nullptr;
   // fused exchange over peer memory (clb_sht_plan_set_peers): destination of every m's g block / every ring pair's b
   // block inside the owning rank's receive buffer (NVLink peer pointers, or local ones for this rank's own share)
-  const double2 **d_rp_gsrc = nullptr;   // [nrp] analysis PULLS g: where ring pair rp's block lives in its owner's send buffer
-  double2 **d_rp_bptr = nullptr;         // [nrp] synthesis PUSHES b: ring pair rp's block in its owner's receive buffer
+  const double2 **d_rp_gsrc = nullptr;   // [2][nrp] (second half: second shell of a batched pass) analysis PULLS g: where ring pair rp's block lives in its owner's send buffer
+  double2 **d_rp_bptr = nullptr;         // [2][nrp] synthesis PUSHES b: ring pair rp's block in its owner's receive buffer
+  int peer_shells = 1;                   // shells the peer buffers hold (clb_sht_plan_set_peers_shells)
   // FFT tables
   struct FftTables *fft = nullptr;
 };

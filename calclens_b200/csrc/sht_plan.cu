@@ -284,13 +284,15 @@ int *plan_rp_to_local(const ShtPlan *p) { return p->d_rp_to_local; }
 // contiguous per warp -- straight out of the ring owner's buffer over NVLink.  b (synthesis): the Legendre epilogue
 // WRITES its 128-byte runs straight into the ring owner's receive buffer.  g_send_ptrs[q] / b_recv_ptrs[q] are the
 // base addresses of rank q's buffers as seen from this process (peer mappings; this rank's own buffers for q == rank).
-void sht_plan_set_peers(ShtPlan *p, void *const *g_send_ptrs, void *const *b_recv_ptrs)
+void sht_plan_set_peers(ShtPlan *p, void *const *g_send_ptrs, void *const *b_recv_ptrs, int nshell)
 {
+  // nshell = 2: every rank's buffers hold two shells back to back (second shell at + that rank's g_send_total /
+  // b_recv_total elements); the second half of the pointer tables addresses it (batched two-plane pass)
   const int nrp = p->nrp, me = p->rank;
   std::vector<int> rp_local_idx(nrp), cnt_rp(p->nranks, 0);
   for (int rp = 0; rp < nrp; ++rp) rp_local_idx[rp] = cnt_rp[p->rp_owner[rp]]++;
-  std::vector<const double2 *> gsrc(nrp);
-  std::vector<double2 *> bptr(nrp);
+  std::vector<const double2 *> gsrc(2 * (size_t)nrp, nullptr);
+  std::vector<double2 *> bptr(2 * (size_t)nrp, nullptr);
   for (int rp = 0; rp < nrp; ++rp) {
     const int q = p->rp_owner[rp];
     const long nslot_q = 2L * p->nrp_of_rank[q];
@@ -301,11 +303,16 @@ void sht_plan_set_peers(ShtPlan *p, void *const *g_send_ptrs, void *const *b_rec
     }
     gsrc[rp] = reinterpret_cast<const double2 *>(g_send_ptrs[q]) + sbase + 2L * rp_local_idx[rp];
     bptr[rp] = reinterpret_cast<double2 *>(b_recv_ptrs[q]) + rbase + 2L * rp_local_idx[rp];
+    if (nshell >= 2) {
+      gsrc[nrp + rp] = gsrc[rp] + (p->lmax + 1) * nslot_q;          // rank q's g_send_total
+      bptr[nrp + rp] = bptr[rp] + (p->lmax + 1) * 6L * nslot_q;     // rank q's b_recv_total
+    }
   }
   if (p->d_rp_gsrc) cudaFree(p->d_rp_gsrc);
   if (p->d_rp_bptr) cudaFree(p->d_rp_bptr);
   p->d_rp_gsrc = to_device(gsrc);
   p->d_rp_bptr = to_device(bptr);
+  p->peer_shells = nshell >= 2 ? 2 : 1;
 }
 
 }  // namespace clb

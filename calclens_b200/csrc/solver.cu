@@ -20,6 +20,7 @@ namespace clb {
 constexpr int kMaxPeers = 8;          // ring_broadcast_kernel addresses up to 8 ranks (one NVSwitch node)
 constexpr int kCoarseOrder = 5;       // halo masks live on a NEST grid of 12 * 4^5 cells
 constexpr int kStages = 10;           // stage boundaries recorded per step (timing)
+int g_solver_shells = 2;              // clb_set_tuning(11, 1|2): shells per SHT pass a solver is provisioned for (read at creation)
 
 struct PeerFlags { unsigned *p[kMaxPeers]; };
 
@@ -102,12 +103,19 @@ struct Solver {
   cudaEvent_t dens_ready[2] = {nullptr, nullptr}, dens_free[2] = {nullptr, nullptr}, ev_tmp = nullptr;
   bool dens_free_valid[2] = {false, false};
   int cur = 0;                       // density buffer of the plane being solved
-  const void *staged_src = nullptr;  // prefetched plane: source pointer, scalings, buffer
-  float staged_scal[3] = {0, 0, 0};
-  int staged_buf = -1;
+  struct PlaneKey {                  // a plane as the caller names it: source pointer + the three scalings
+    const void *src = nullptr; float scal[3] = {0, 0, 0};
+    bool is(const void *p, float a, float b, float c) const { return src && src == p && scal[0] == a && scal[1] == b && scal[2] == c; }
+    void set(const void *p, float a, float b, float c) { src = p; scal[0] = a; scal[1] = b; scal[2] = c; }
+  };
+  PlaneKey staged[2];                // density buffer k holds this prefetched plane (src == nullptr: nothing staged)
   float *h_stage[2] = {nullptr, nullptr};   // pinned staging for pageable host maps
-  const void *next_src = nullptr;    // plane registered by clb_solver_set_next: prefetched behind the current step's kernels
-  float next_scal[3] = {0, 0, 0};
+  PlaneKey next[2];                  // planes registered by clb_solver_set_next: prefetched behind the current step's kernels
+  int n_next = 0;
+  // two planes per SHT pass: the partner registered by clb_solver_set_pair is solved together with
+  // the next step's plane; its six maps wait in the second map set until the step that names it
+  int shells = 2;                    // shells the exchange buffers and map sets are provisioned for (clb_set_tuning(11, .))
+  PlaneKey pair, cached;             // partner to solve with the next step / plane whose maps are in map set 1
   // timing
   int timing = 0;
   cudaEvent_t ev[kStages + 1] = {};
@@ -163,8 +171,9 @@ static void default_owners(long order, long lmax, int nranks, std::vector<int> &
 static bool setup_peers(Solver *s)
 {
   ShtPlan *p = s->plan;
-  const size_t sizes[4] = {16 * (size_t)std::max<long>(p->g_send_total, 1), 16 * (size_t)std::max<long>(p->b_recv_total, 1),
-                           4 * 6 * (size_t)s->npix, 256};
+  const size_t sh = (size_t)s->shells;
+  const size_t sizes[4] = {16 * sh * (size_t)std::max<long>(p->g_send_total, 1), 16 * sh * (size_t)std::max<long>(p->b_recv_total, 1),
+                           4 * 6 * sh * (size_t)s->npix, 256};
   PeerCard mine;
   memset(&mine, 0, sizeof(mine));
   mine.pid = (int)getpid();
@@ -215,7 +224,7 @@ static bool setup_peers(Solver *s)
   if (shared_device) s->host_barriers = 1;
   std::vector<void *> gp(s->nranks), bp(s->nranks);
   for (int q = 0; q < s->nranks; ++q) { gp[q] = s->peer[q][0]; bp[q] = s->peer[q][1]; }
-  sht_plan_set_peers(p, gp.data(), bp.data());
+  sht_plan_set_peers(p, gp.data(), bp.data(), s->shells);
   s->g_send = reinterpret_cast<double2 *>(s->own[0]);
   s->b_recv = reinterpret_cast<double2 *>(s->own[1]);
   s->maps = reinterpret_cast<float *>(s->own[2]);
@@ -256,35 +265,54 @@ static void load_density(Solver *s, const float *src, int k, float premul, float
   LAUNCHED(s) launch_load_density(s->plan, v, s->dens[k], premul, densmul, backdens, st);
 }
 
-// density buffer `dens` (this rank's rings valid) -> six derivative maps
-static void solve(Solver *s, const float *dens, cudaStream_t st)
+// density buffers (this rank's rings valid) -> six derivative maps per shell.  nshell = 2 runs the two planes through ONE
+// pass of each Legendre kernel (the lambda_lm recurrence is generated once for both); the ring FFTs run per shell.  Shell s
+// uses the second half of the exchange buffers and map set s.
+static void solve(Solver *s, const float *const dens[2], int nshell, const int dens_buf[2], cudaStream_t st)
 {
   ShtPlan *p = s->plan;
-  float *mp[6];
-  for (int k = 0; k < 6; ++k) mp[k] = s->maps + (size_t)k * s->npix;
+  if (nshell > s->shells) die("solver was provisioned for one shell per pass (clb_set_tuning(11, 2) before clb_solver_create)");
+  float *mp[2][6];
+  for (int q = 0; q < nshell; ++q)
+    for (int k = 0; k < 6; ++k) mp[q][k] = s->maps + ((size_t)q * 6 + k) * s->npix;
   if (s->fused) stream_barrier(s, st);          // every rank is done with the previous plane's g, b and maps
-  LAUNCHED(s) launch_ring_analysis(p, dens, s->g_send, st); mark(s, 2, st);
+  for (int q = 0; q < nshell; ++q) {
+    LAUNCHED(s) launch_ring_analysis(p, dens[q], s->g_send + (size_t)q * p->g_send_total, st);
+    if (dens_buf && dens_buf[q] >= 0) {         // the density buffer is free again: a prefetch may overwrite it
+      CLB_CUDA_CHECK(cudaEventRecord(s->dens_free[dens_buf[q]], st));
+      s->dens_free_valid[dens_buf[q]] = true;
+    }
+  }
+  mark(s, 2, st);
   if (s->fused) stream_barrier(s, st);
   mark(s, 3, st);
-  LAUNCHED(s) launch_legendre_analysis(p, s->fused ? nullptr : s->g_recv, s->alm_re, s->alm_im, 1, st); mark(s, 4, st);
-  LAUNCHED(s) launch_legendre_synthesis(p, s->alm_re, s->alm_im, s->fused ? nullptr : s->b_send, st); mark(s, 5, st);
+  LAUNCHED(s) launch_legendre_analysis(p, s->fused ? nullptr : s->g_recv, s->alm_re, s->alm_im, 1, st, nshell); mark(s, 4, st);
+  LAUNCHED(s) launch_legendre_synthesis(p, s->alm_re, s->alm_im, s->fused ? nullptr : s->b_send, st, nshell); mark(s, 5, st);
   if (s->fused) stream_barrier(s, st);
   mark(s, 6, st);
-  LAUNCHED(s) launch_ring_synthesis(p, s->b_recv, mp, st); mark(s, 7, st);
+  for (int q = 0; q < nshell; ++q) LAUNCHED(s) launch_ring_synthesis(p, s->b_recv + (size_t)q * p->b_recv_total, mp[q], st);
+  mark(s, 7, st);
   if (s->fused) {
-    float *pm[kMaxPeers * 6];
-    for (int q = 0; q < s->nranks; ++q)
-      for (int k = 0; k < 6; ++k) pm[q * 6 + k] = reinterpret_cast<float *>(s->peer[q][2]) + (size_t)k * s->npix;
-    LAUNCHED(s) launch_maps_broadcast(p, mp, pm, s->d_need, kCoarseOrder, st);
+    for (int q = 0; q < nshell; ++q) {
+      float *pm[kMaxPeers * 6];
+      for (int r = 0; r < s->nranks; ++r)
+        for (int k = 0; k < 6; ++k) pm[r * 6 + k] = reinterpret_cast<float *>(s->peer[r][2]) + ((size_t)q * 6 + k) * s->npix;
+      LAUNCHED(s) launch_maps_broadcast(p, mp[q], pm, s->d_need, kCoarseOrder, st);
+    }
     stream_barrier(s, st);
   }
   mark(s, 8, st);
 }
+static void solve(Solver *s, const float *dens, cudaStream_t st)
+{
+  const float *d[2] = {dens, nullptr};
+  solve(s, d, 1, nullptr, st);
+}
 
-static void ray_update(Solver *s, double wpp1, double wp, double wpm1, int mode, bool with_summary, cudaStream_t st)
+static void ray_update(Solver *s, double wpp1, double wp, double wpm1, int mode, bool with_summary, cudaStream_t st, int set = 0)
 {
   const float *mp[6];
-  for (int k = 0; k < 6; ++k) mp[k] = s->maps + (size_t)k * s->npix;
+  for (int k = 0; k < 6; ++k) mp[k] = s->maps + ((size_t)set * 6 + k) * s->npix;
   LAUNCHED(s) launch_ray_step(s->rays, s->nrays, mp, s->order, wpp1, wp, wpm1, mode, st, s->d_need, kCoarseOrder, s->rank,
                                  s->d_need ? s->d_err : nullptr, with_summary ? s->d_sum6 : nullptr,
                                  s->d_need ? s->d_need + (12L << (2 * kCoarseOrder)) : nullptr);
@@ -350,14 +378,15 @@ clb_solver *clb_solver_create(long sht_order, long lmax, long ray_order, const d
   s->nranks = nranks; s->rank = rank; s->order = sht_order; s->lmax = lmax; s->ray_order = ray_order < 0 ? sht_order : ray_order;
   s->npix = 12L << (2 * sht_order);
   s->allgather = allgather; s->ctx = ctx; s->halo_deg = halo_deg;
+  s->shells = g_solver_shells;
   std::vector<int> ro, mo;
   if (nranks > 1 && (!rp_owner || !m_owner)) { default_owners(sht_order, lmax, nranks, ro, mo); rp_owner = ro.data(); m_owner = mo.data(); }
   s->plan_h = clb_sht_plan_create(sht_order, lmax, ring_weights, nranks, rank, rp_owner, m_owner);
   s->plan = s->plan_h->p;
   ShtPlan *p = s->plan;
   auto dmalloc = [](size_t bytes) { void *q = nullptr; CLB_CUDA_CHECK(cudaMalloc(&q, bytes ? bytes : 16)); return q; };
-  s->alm_re = (double *)dmalloc(sizeof(double) * std::max<long>(p->alm_total, 1));
-  s->alm_im = (double *)dmalloc(sizeof(double) * std::max<long>(p->alm_total, 1));
+  s->alm_re = (double *)dmalloc(sizeof(double) * s->shells * std::max<long>(p->alm_total, 1));
+  s->alm_im = (double *)dmalloc(sizeof(double) * s->shells * std::max<long>(p->alm_total, 1));
   for (int k = 0; k < 2; ++k) {
     s->dens[k] = (float *)dmalloc(sizeof(float) * s->npix);
     CLB_CUDA_CHECK(cudaMemset(s->dens[k], 0, sizeof(float) * s->npix));
@@ -402,11 +431,11 @@ clb_solver *clb_solver_create(long sht_order, long lmax, long ray_order, const d
     }
     host_barrier(s);
   } else {
-    s->g_send = (double2 *)dmalloc(sizeof(double2) * std::max<long>(p->g_send_total, 1));
-    s->b_send = (double2 *)dmalloc(sizeof(double2) * std::max<long>(p->b_send_total, 1));
+    s->g_send = (double2 *)dmalloc(sizeof(double2) * s->shells * std::max<long>(p->g_send_total, 1));
+    s->b_send = (double2 *)dmalloc(sizeof(double2) * s->shells * std::max<long>(p->b_send_total, 1));
     s->g_recv = s->g_send; s->b_recv = s->b_send;
-    s->maps = (float *)dmalloc(sizeof(float) * 6 * s->npix);
-    CLB_CUDA_CHECK(cudaMemset(s->maps, 0, sizeof(float) * 6 * s->npix));
+    s->maps = (float *)dmalloc(sizeof(float) * 6 * s->shells * s->npix);
+    CLB_CUDA_CHECK(cudaMemset(s->maps, 0, sizeof(float) * 6 * s->shells * s->npix));
   }
   CLB_CUDA_CHECK(cudaDeviceSynchronize());
   return h;
@@ -442,6 +471,7 @@ long clb_solver_query(const clb_solver *h, int what)
     case 5: return (long)(s->need_fraction * 1e6);
     case 6: return s->host_barriers;
     case 7: return s->npix;
+    case 8: return s->shells;
     default: return -1;
   }
 }
@@ -459,6 +489,7 @@ void *clb_solver_ptr(clb_solver *h, int what)
     case 6: return s->dens[0];
     case 7: return s->dens[1];
     case 8: return s->d_sum6;
+    case 9: return s->shells >= 2 ? s->maps + 6 * (size_t)s->npix : nullptr;
     default: return nullptr;
   }
 }
@@ -517,6 +548,10 @@ void clb_solver_get_rays(clb_solver *h, void *host_rays, void *stream)
 void clb_solver_load_density(clb_solver *h, const float *counts_map, float premul, float densmul, float backdens, void *stream)
 {
   Solver *s = &h->s;
+  if (s->staged[s->cur].src) {   // a prefetch is (or was) filling this buffer: let it finish, then drop it
+    CLB_CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, s->dens_ready[s->cur], 0));
+    s->staged[s->cur].src = nullptr;
+  }
   load_density(s, counts_map, s->cur, premul, densmul, backdens, (cudaStream_t)stream);
 }
 
@@ -556,18 +591,54 @@ void clb_solver_ray_update(clb_solver *h, double wpp1, double wp, double wpm1, i
 void clb_solver_set_next(clb_solver *h, const float *next_counts_map, float premul, float densmul, float backdens)
 {
   Solver *s = &h->s;
-  s->next_src = next_counts_map; s->next_scal[0] = premul; s->next_scal[1] = densmul; s->next_scal[2] = backdens;
+  if (s->n_next >= 2) { s->next[0] = s->next[1]; s->n_next = 1; }   // at most two planes ahead: the oldest request goes
+  s->next[s->n_next++].set(next_counts_map, premul, densmul, backdens);
 }
 
-static void prefetch(clb_solver *h, const float *next_counts_map, float premul, float densmul, float backdens)
+void clb_solver_set_pair(clb_solver *h, const float *partner_counts_map, float premul, float densmul, float backdens)
 {
   Solver *s = &h->s;
-  const int k = 1 - s->cur;
-  if (s->dens_free_valid[k]) CLB_CUDA_CHECK(cudaStreamWaitEvent(s->copy_stream, s->dens_free[k], 0));
-  load_density(s, next_counts_map, k, premul, densmul, backdens, s->copy_stream);
-  CLB_CUDA_CHECK(cudaEventRecord(s->dens_ready[k], s->copy_stream));
-  s->staged_src = next_counts_map; s->staged_scal[0] = premul; s->staged_scal[1] = densmul; s->staged_scal[2] = backdens;
-  s->staged_buf = k;
+  if (s->shells < 2) die("clb_solver_set_pair: the solver was created for one shell per pass (clb_set_tuning(11, 2))");
+  s->pair.set(partner_counts_map, premul, densmul, backdens);
+}
+
+// density buffer that holds plane (src, scalings): the staged one if the plane was prefetched, else a buffer loaded now
+// (never `avoid`, the buffer of the other plane of this pass)
+static int acquire_density(Solver *s, const float *src, float premul, float densmul, float backdens, int avoid, cudaStream_t st)
+{
+  for (int k = 0; k < 2; ++k)
+    if (k != avoid && s->staged[k].is(src, premul, densmul, backdens)) {
+      CLB_CUDA_CHECK(cudaStreamWaitEvent(st, s->dens_ready[k], 0));     // prefetched: nothing crosses PCIe now
+      s->staged[k].src = nullptr;
+      return k;
+    }
+  int k = -1;
+  for (int c = 0; c < 2; ++c) if (c != avoid && !s->staged[c].src) { k = c; break; }   // leave a pending prefetch alone
+  if (k < 0) {       // both hold other prefetched planes: the stale one is overwritten once its load has finished
+    k = (avoid == 0) ? 1 : 0;
+    CLB_CUDA_CHECK(cudaStreamWaitEvent(st, s->dens_ready[k], 0));
+    s->staged[k].src = nullptr;
+  }
+  load_density(s, src, k, premul, densmul, backdens, st);
+  return k;
+}
+
+static void prefetch_queued(Solver *s)
+{
+  for (int i = 0; i < s->n_next; ++i) {
+    const Solver::PlaneKey &n = s->next[i];
+    bool have = false;
+    for (int k = 0; k < 2; ++k) have |= s->staged[k].is(n.src, n.scal[0], n.scal[1], n.scal[2]);
+    if (have) continue;
+    int k = -1;
+    for (int c = 0; c < 2; ++c) if (!s->staged[c].src) { k = c; break; }
+    if (k < 0) break;     // both buffers already hold planes to come
+    if (s->dens_free_valid[k]) CLB_CUDA_CHECK(cudaStreamWaitEvent(s->copy_stream, s->dens_free[k], 0));
+    load_density(s, reinterpret_cast<const float *>(n.src), k, n.scal[0], n.scal[1], n.scal[2], s->copy_stream);
+    CLB_CUDA_CHECK(cudaEventRecord(s->dens_ready[k], s->copy_stream));
+    s->staged[k] = n;
+  }
+  s->n_next = 0;
 }
 
 int clb_solver_check(clb_solver *h, void *stream)
@@ -585,24 +656,28 @@ int clb_solver_step(clb_solver *h, const float *counts_map, float premul, float 
   Solver *s = &h->s;
   cudaStream_t st = (cudaStream_t)stream;
   mark(s, 0, st);
-  if (s->staged_buf >= 0 && s->staged_src == counts_map && s->staged_scal[0] == premul && s->staged_scal[1] == densmul &&
-      s->staged_scal[2] == backdens) {
-    s->cur = s->staged_buf;                        // the prefetched plane: wait for its load, nothing crosses PCIe now
-    CLB_CUDA_CHECK(cudaStreamWaitEvent(st, s->dens_ready[s->cur], 0));
+  if (s->cached.is(counts_map, premul, densmul, backdens)) {
+    // this plane was solved together with the previous one: its six maps wait in map set 1, only the rays are left
+    s->cached.src = nullptr;
+    for (int k = 1; k <= 8; ++k) mark(s, k, st);
+    ray_update(s, wpp1, wp, wpm1, 1 | 2 | 4, sum6 != nullptr, st, 1);
   } else {
-    if (s->staged_buf >= 0) s->cur = 1 - s->staged_buf;   // leave a pending prefetch alone
-    load_density(s, counts_map, s->cur, premul, densmul, backdens, st);
+    s->cached.src = nullptr;
+    int buf[2] = {-1, -1};
+    buf[0] = acquire_density(s, counts_map, premul, densmul, backdens, -1, st);
+    int nshell = 1;
+    if (s->pair.src) {
+      buf[1] = acquire_density(s, reinterpret_cast<const float *>(s->pair.src), s->pair.scal[0], s->pair.scal[1], s->pair.scal[2], buf[0], st);
+      nshell = 2;
+    }
+    s->cur = buf[0];
+    mark(s, 1, st);
+    const float *dens[2] = {s->dens[buf[0]], nshell == 2 ? s->dens[buf[1]] : nullptr};
+    solve(s, dens, nshell, buf, st);
+    if (nshell == 2) { s->cached = s->pair; s->pair.src = nullptr; }
+    ray_update(s, wpp1, wp, wpm1, 1 | 2 | 4, sum6 != nullptr, st, 0);
   }
-  s->staged_buf = -1; s->staged_src = nullptr;
-  mark(s, 1, st);
-  solve(s, s->dens[s->cur], st);
-  CLB_CUDA_CHECK(cudaEventRecord(s->dens_free[s->cur], st));
-  s->dens_free_valid[s->cur] = true;
-  ray_update(s, wpp1, wp, wpm1, 1 | 2 | 4, sum6 != nullptr, st);
-  if (s->next_src) {   // the next plane's map starts streaming in behind this plane's kernels
-    prefetch(h, reinterpret_cast<const float *>(s->next_src), s->next_scal[0], s->next_scal[1], s->next_scal[2]);
-    s->next_src = nullptr;
-  }
+  prefetch_queued(s);   // the next planes' maps start streaming in behind this plane's kernels
   if (!sum6) return 0;
   CLB_CUDA_CHECK(cudaMemcpyAsync(s->h_sum6, s->d_sum6, sizeof(double) * 6, cudaMemcpyDeviceToHost, st));
   const int err = clb_solver_check(h, stream);

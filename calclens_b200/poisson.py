@@ -168,6 +168,8 @@ class LensPlaneSolver:
             self.fused = bool(q(2))
             self.plan = _SolverPlan(self.lib, ptr(4), self.order, self.lmax, self.nranks, self.rank, self.device)
             self.maps = self._dev_view(ptr(0), (6, self.npix), torch.float32)
+            self.shells = int(q(8))
+            self.maps2 = self._dev_view(ptr(9), (6, self.npix), torch.float32) if self.shells >= 2 else None
             self.alm_re = self._dev_view(ptr(2), (max(self.plan.Nlm, 1),), torch.float64)
             self.alm_im = self._dev_view(ptr(3), (max(self.plan.Nlm, 1),), torch.float64)
             self.summary = self._dev_view(ptr(8), (6,), torch.float64)
@@ -204,7 +206,7 @@ class LensPlaneSolver:
         """Release the solver (collective on multi-rank solvers: every rank must call it)."""
         if self._cs:
             torch.cuda.synchronize()
-            self.maps = self.alm_re = self.alm_im = self.summary = self._need = self.rays = None
+            self.maps = self.maps2 = self.alm_re = self.alm_im = self.summary = self._need = self.rays = None
             self.plan.destroy()
             self.lib.clb_solver_destroy(self._cs)
             self._cs = None
@@ -315,17 +317,26 @@ class LensPlaneSolver:
         if err & 1:
             raise RuntimeError("calclens_b200: a ray left its domain + halo (%.2f deg); raise halo_deg" % self.halo_deg)
 
-    def step(self, counts_map, premul, densmul, backdens, wpp1, wp, wpm1, read_summary=True, prefetch=None):
+    def step(self, counts_map, premul, densmul, backdens, wpp1, wp, wpm1, read_summary=True, prefetch=None, pair=None):
         """One lens plane.  ``counts_map``: RING float32 full-sky map, a device tensor or a (pinned) host tensor.
-        ``prefetch`` = (next_counts_map, premul, densmul, backdens) starts the next plane's load behind this plane's
-        kernels; a later step() given that same map picks the staged density up instead of loading again.
+        ``prefetch`` = (next_counts_map, premul, densmul, backdens), or a list of up to two of them, starts the load of the
+        planes to come behind this plane's kernels; a later step() given that same map picks the staged density up
+        instead of loading again.
+        ``pair`` = (partner_counts_map, premul, densmul, backdens): the plane AFTER this one.  Both go through one pass of
+        each Legendre kernel (two shells per pass); the next step(), given the partner map, only updates the rays.
         Returns the six ray sums over all ranks (read_summary) or None."""
         assert counts_map.dtype == torch.float32 and counts_map.numel() == self.npix and counts_map.is_contiguous()
         if self._cs:
+            if pair is not None:
+                nm, a, b, c = pair
+                self._pair = nm
+                self.lib.clb_solver_set_pair(self._cs, nm.data_ptr(), float(a), float(b), float(c))
             if prefetch is not None:
-                nm, a, b, c = prefetch
-                self._next = nm    # keep the tensor alive until its load has run
-                self.lib.clb_solver_set_next(self._cs, nm.data_ptr(), float(a), float(b), float(c))
+                if isinstance(prefetch, tuple):
+                    prefetch = [prefetch]
+                self._next = [x[0] for x in prefetch]    # keep the tensors alive until their loads have run
+                for nm, a, b, c in prefetch:
+                    self.lib.clb_solver_set_next(self._cs, nm.data_ptr(), float(a), float(b), float(c))
             out = (C.c_double * 6)() if read_summary else None
             err = self.lib.clb_solver_step(self._cs, counts_map.data_ptr(), float(premul), float(densmul), float(backdens),
                                            float(wpp1), float(wp), float(wpm1), out, self._stream())
@@ -338,6 +349,7 @@ class LensPlaneSolver:
                 self.dist.all_reduce(t, group=self.group)
                 res = t.cpu().numpy()
             return res
+        assert pair is None, "two shells per pass need the fused C solver"
         self.load_density(counts_map, premul, densmul, backdens)
         self.solve()
         self.ray_update(wpp1, wp, wpm1, with_summary=read_summary)

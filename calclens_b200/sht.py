@@ -154,20 +154,26 @@ class HEALPixSHTPlan:
         self.lib.clb_ring_analysis_dev(self._h, map_dev.data_ptr(), g_send.data_ptr(), self._stream())
         return g_send
 
-    def legendre_analysis(self, g_recv, alm_re=None, alm_im=None, poisson_filter=False):
-        assert g_recv.dtype == torch.float64 and g_recv.is_cuda and g_recv.numel() >= 2 * self.g_recv_total
+    def legendre_analysis(self, g_recv, alm_re=None, alm_im=None, poisson_filter=False, nshell=1):
+        """nshell = 2: two shells in one pass (g_recv holds them back to back, g_recv_total complex values apart; the alm
+        come back the same way, Nlm apart)."""
+        assert g_recv.dtype == torch.float64 and g_recv.is_cuda and g_recv.numel() >= 2 * nshell * self.g_recv_total
         if alm_re is None:
-            alm_re = torch.empty(max(self.Nlm, 1), dtype=torch.float64, device=self.device)
-            alm_im = torch.empty(max(self.Nlm, 1), dtype=torch.float64, device=self.device)
-        self.lib.clb_legendre_analysis_dev(self._h, g_recv.data_ptr(), alm_re.data_ptr(), alm_im.data_ptr(),
-                                           1 if poisson_filter else 0, self._stream())
+            alm_re = torch.empty(nshell * max(self.Nlm, 1), dtype=torch.float64, device=self.device)
+            alm_im = torch.empty(nshell * max(self.Nlm, 1), dtype=torch.float64, device=self.device)
+        assert alm_re.numel() >= nshell * self.Nlm and alm_im.numel() >= nshell * self.Nlm
+        self.lib.clb_legendre_analysis_shells_dev(self._h, g_recv.data_ptr(), alm_re.data_ptr(), alm_im.data_ptr(),
+                                                  1 if poisson_filter else 0, int(nshell), self._stream())
         return alm_re, alm_im
 
-    def legendre_synthesis(self, alm_re, alm_im, b_send=None):
+    def legendre_synthesis(self, alm_re, alm_im, b_send=None, nshell=1):
         assert alm_re.dtype == torch.float64 and alm_re.is_cuda and alm_im.is_cuda
+        assert alm_re.numel() >= nshell * self.Nlm and alm_im.numel() >= nshell * self.Nlm
         if b_send is None:
-            b_send = torch.empty(2 * max(self.b_send_total, 1), dtype=torch.float64, device=self.device)
-        self.lib.clb_legendre_synthesis_dev(self._h, alm_re.data_ptr(), alm_im.data_ptr(), b_send.data_ptr(), self._stream())
+            b_send = torch.empty(2 * nshell * max(self.b_send_total, 1), dtype=torch.float64, device=self.device)
+        assert b_send.numel() >= 2 * nshell * self.b_send_total
+        self.lib.clb_legendre_synthesis_shells_dev(self._h, alm_re.data_ptr(), alm_im.data_ptr(), b_send.data_ptr(), int(nshell),
+                                                   self._stream())
         return b_send
 
     def ring_synthesis(self, b_recv, maps=None):

@@ -59,6 +59,16 @@ int clb_legendre_analysis_dev(clb_sht_plan *plan, const double *g_recv, double *
 /* ---- stages of alm2allmaps_mpi (alm2allmaps_transpose_mpi.c:53-1240) ---- */
 /* Legendre synthesis of the six fields :272-595.  b_send: clb_sht_plan_query(7) complex doubles */
 int clb_legendre_synthesis_dev(clb_sht_plan *plan, const double *alm_re, const double *alm_im, double *b_send, void *stream);
+/* ---- two shells (lens planes) per Legendre pass -- SURVEY.md section 8f-4; the reference has no counterpart (it solves
+ * plane by plane, shtpoissonsolve.c:517-570, although plane p+1's solve does not depend on the rays).  The lambda_lm
+ * recurrence is generated once and applied to both shells: 3 instead of 4 FP64 instructions per (m, ring pair, l, shell) in
+ * the analysis, 7 instead of 8 in the synthesis.  nshell = 1 or 2; shell s reads g at g_recv + s * query(6) complex doubles
+ * and delivers alm at alm_re/alm_im + s * query(2); the synthesis reads alm the same way and writes b at
+ * b_send + s * query(7).  Every shell's result is bit-identical to what the one-shell call gives for it. ---- */
+int clb_legendre_analysis_shells_dev(clb_sht_plan *plan, const double *g_recv, double *alm_re, double *alm_im,
+                                     int apply_poisson_filter, int nshell, void *stream);
+int clb_legendre_synthesis_shells_dev(clb_sht_plan *plan, const double *alm_re, const double *alm_im, double *b_send,
+                                      int nshell, void *stream);
 /* unpack/alias fold + phase + c2r + 1/sin scalings + cot terms :818-1147 */
 int clb_ring_synthesis_dev(const clb_sht_plan *plan, const double *b_recv, float *const maps[6], void *stream);
 
@@ -87,6 +97,9 @@ void clb_peer_export(void *p, void *handle64);
 void *clb_peer_import(const void *handle64);
 void clb_peer_release(void *p);
 void clb_sht_plan_set_peers(clb_sht_plan *plan, void *const *g_send_ptrs, void *const *b_recv_ptrs);
+/* the same with peer buffers that hold nshell (1 or 2) shells back to back: rank q's second shell starts at
+ * + its query(5) (g) / query(8) (b) complex doubles */
+void clb_sht_plan_set_peers_shells(clb_sht_plan *plan, void *const *g_send_ptrs, void *const *b_recv_ptrs, int nshell);
 int clb_maps_broadcast_dev(const clb_sht_plan *plan, float *const local_maps[6], float *const *peer_maps,
                            const unsigned char *need, long coarse_order, void *stream);
 void clb_domain_masks(long ray_order, int nranks, long coarse_order, double margin_rad, unsigned char *mask);
@@ -185,10 +198,11 @@ clb_solver *clb_solver_create(long sht_order, long lmax, long ray_order, const d
                               double halo_deg);
 void clb_solver_destroy(clb_solver *s);   /* collective on multi-rank solvers */
 /* what: 0 rays on this rank, 1 first NEST index, 2 fused exchange active, 3 kernels launched, 4 halo mask in use,
- * 5 mean fraction of the sky a rank receives x 1e6, 6 host barriers in use (ranks time-share a GPU), 7 Npix */
+ * 5 mean fraction of the sky a rank receives x 1e6, 6 host barriers in use (ranks time-share a GPU), 7 Npix,
+ * 8 shells per pass the solver is provisioned for */
 long clb_solver_query(const clb_solver *s, int what);
 /* device pointers owned by the solver: 0 six maps [6][Npix], 1 rays, 2/3 alm re/im, 4 the clb_sht_plan, 5 halo mask,
- * 6/7 the two density buffers, 8 the six ray sums */
+ * 6/7 the two density buffers, 8 the six ray sums, 9 the second map set (the partner plane of a two-shell pass) */
 void *clb_solver_ptr(clb_solver *s, int what);
 /* alloc_rays + init_rays (raytrace_utils.c:265-347) for this rank's NEST range; returns the number of rays */
 long clb_solver_init_rays(clb_solver *s, double binL_2, void *stream);
@@ -207,6 +221,12 @@ int clb_solver_step(clb_solver *s, const float *counts_map, float premul, float 
 /* register the NEXT plane's map: the following clb_solver_step starts loading it on a side stream behind its own
  * kernels, and the step after that, given the same pointer and scalings, finds its density already on the device */
 void clb_solver_set_next(clb_solver *s, const float *next_counts_map, float premul, float densmul, float backdens);
+/* (up to two planes may be registered between steps; they are loaded in that order into the two density buffers)
+ * Two planes per SHT pass: register the plane AFTER the one the next clb_solver_step will be given.  That step then runs
+ * both planes through one pass of each Legendre kernel (clb_legendre_*_shells_dev), updates the rays with its own plane
+ * and keeps the partner's six maps; the following clb_solver_step, given the partner's pointer and scalings, finds them
+ * and only updates the rays.  Rays, maps and sums are bit-identical to two ordinary steps. */
+void clb_solver_set_pair(clb_solver *s, const float *partner_counts_map, float premul, float densmul, float backdens);
 /* synchronise and return the error bits of clb_solver_step */
 int clb_solver_check(clb_solver *s, void *stream);
 /* the pieces of a step, for callers that interleave their own work: density load into the current buffer, the SHT
