@@ -4,7 +4,7 @@
 #include <string.h>
 
 namespace clb {
-extern int g_syn_rings_per_thread, g_ana_rings_per_thread, g_fft_threads_big, g_leg_warps_per_cta, g_fft_force_scratch, g_ana_rows, g_syn2_rings_per_thread, g_ana2_rings_per_thread, g_fft_field_groups, g_fft_prefetch, g_fft_debug, g_solver_shells;
+extern int g_syn_rings_per_thread, g_ana_rings_per_thread, g_fft_threads_big, g_leg_warps_per_cta, g_fft_force_scratch, g_ana_rows, g_syn2_rings_per_thread, g_ana2_rings_per_thread, g_fft_field_groups, g_fft_debug, g_solver_shells;
 
 // safe[c] = AND of mask[d] over every cell d whose centre lies within neighbour_rad of c's centre (c included): a ray whose
 // stencil starts in a "safe" cell cannot touch an undelivered pixel, so the ray kernel skips the per-pixel mask check there
@@ -120,7 +120,6 @@ void clb_set_tuning(int what, int value)
   if (what == 9 && value >= 1 && value <= 4) g_syn2_rings_per_thread = value;
   if (what == 10 && (value == 1 || value == 2 || value == 4 || value == 6 || value == 8)) g_ana2_rings_per_thread = value;
   if (what == 6 && (value == 0 || value == 1 || value == 3)) g_fft_field_groups = value;
-  if (what == 7) g_fft_prefetch = value ? 1 : 0;
   if (what == 8) g_fft_debug = value;   // development aid: skip phases of the ring synthesis (wrong results)
   if (what == 3 && (value == 1 || value == 2 || value == 4)) g_leg_warps_per_cta = value;
   if (what == 2 && (value == 256 || value == 512 || value == 768 || value == 1024)) g_fft_threads_big = value;   // read at plan creation

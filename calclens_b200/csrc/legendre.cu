@@ -56,8 +56,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // per-thread partial sums are reduced over the warp through shared memory and land in the warp's partial-sum row.
 // A warp walks several chunks one after the other (chunk = row, row + rows, ...: every warp gets the same mix of polar and
 // equatorial rings, so the warps of a CTA finish together) and accumulates them into the same row, which it alone owns:
-// the first chunk stores, the later ones read-modify-write (same thread, same address: program order).  alm_finish_kernel
-// adds the `rows` rows of an m in a fixed order, so the result is deterministic.
+// the first chunk stores, the later ones add with red.global (same thread, same address: program order, so the sum is
+// deterministic).  alm_finish_kernel adds the `rows` rows of an m in a fixed order.
 template <int R, int NS, int NB>
 __global__ void __launch_bounds__(kLegThreads, NB)
 legendre_analysis_kernel(const double2 *__restrict__ g_recv, long g_shell, const double2 *const *__restrict__ rp_gsrc,
@@ -74,6 +74,7 @@ legendre_analysis_kernel(const double2 *__restrict__ g_recv, long g_shell, const
   constexpr int NP = (R + 1) / 2;
   __shared__ __align__(16) double s_A[kLegWarps][2][kAnaTile];
   __shared__ double s_red[kLegWarps][16 * 33];
+  __shared__ __align__(16) double2 s_seed[kLegWarps][R][32];   // the chunk's seeds, copied in with the first coefficient tile
 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int row = blockIdx.x * (blockDim.x >> 5) + w, mi = blockIdx.y;
@@ -122,6 +123,10 @@ legendre_analysis_kernel(const double2 *__restrict__ g_recv, long g_shell, const
       lsmax = max(lsmax, __shfl_xor_sync(0xffffffffu, lsmax, o));
     }
     if (lsw == kNoStart) continue;   // every ring of this chunk is cut for this m
+    // (a global load at the moment a ring starts would stall the whole warp on HBM latency in the middle of the FP64 work)
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+      if (rp0 + j * 32 < nrp) cp_async16(&s_seed[w][j][lane], &seed_tab[(size_t)mi * nrp + rp0 + j * 32]);
     const bool rmw = !first;
     if (first) {                     // degrees below the first active block get exact zeros
       for (int l = m + lane; l < lsw; l += 32)
@@ -148,14 +153,12 @@ legendre_analysis_kernel(const double2 *__restrict__ g_recv, long g_shell, const
         const int l0 = lt + b * KB;
         if (l0 > lmax) break;
         double2 *dst = out + osh * part_shell + (l0 - m + oi);
-        double2 old = make_double2(0.0, 0.0);
-        if (rmw && writer && l0 + oi <= lmax) old = *dst;   // issued early: arrives behind the block's FP64 work
         if ((b * KB) % kSeedAlign == 0 && l0 <= lsmax) {   // start-up phase of this warp: inject the seeds of rings starting here
           const unsigned blk = (unsigned)(l0 - m) / kSeedAlign;
 #pragma unroll
           for (int j = 0; j < R; ++j)
             if (((sb[j / 2] >> (16 * (j & 1))) & 0xffffu) == blk) {
-              const double2 sd = seed_tab[(size_t)mi * nrp + rp0 + j * 32];
+              const double2 sd = s_seed[w][j][lane];
               mp[j] = sd.x; mc[j] = sd.y;
             }
         }
@@ -191,13 +194,19 @@ legendre_analysis_kernel(const double2 *__restrict__ g_recv, long g_shell, const
         double t = (t0 + t1) + (t2 + t3);
         t += __shfl_xor_sync(0xffffffffu, t, 16);
         const double ti = __shfl_down_sync(0xffffffffu, t, KB);   // imaginary part lives KB lanes up
-        if (writer && l0 + oi <= lmax) *dst = make_double2(old.x + t, old.y + ti);
+        if (writer && l0 + oi <= lmax) {
+          if (!rmw) *dst = make_double2(t, ti);
+          else {   // a later chunk of the same row: fire-and-forget adds in L2 (this thread alone touches the address, in program order)
+            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(&dst->x), "d"(t) : "memory");
+            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(&dst->y), "d"(ti) : "memory");
+          }
+        }
         __syncwarp();   // the parked sums are consumed before the next block overwrites them
       }
       __syncwarp();   // everyone is done with this tile before the next iteration's copy overwrites it
     }
     cp_async_wait<0>();
-    __syncwarp();
+    __syncwarp();   // (also: every lane has read its seeds before the next chunk's copies overwrite them)
   }
   if (first) {   // no ring of this warp is active for this m: the row is all zeros
     for (int l = m + lane; l <= lmax; l += 32)
@@ -306,11 +315,12 @@ legendre_synthesis_kernel(const double *__restrict__ coef, const long *__restric
                           const int *__restrict__ ls_tab, const double2 *__restrict__ seed_tab,
                           const double *__restrict__ cth_rp, const double *__restrict__ sth_rp,
                           const int *__restrict__ m_loc, const long *__restrict__ b_off,
-                          const int *__restrict__ b_stride, double2 *__restrict__ b_send, long b_shell,
+                          long b_fs, double2 *__restrict__ b_send, long b_shell,
                           double2 *const *__restrict__ rp_bptr, int nrp, int lmax)
 {
   constexpr int RW = 8 * NS;     // doubles per coefficient record
   __shared__ __align__(16) double s_tile[kLegWarps][2][kLB * RW];
+  __shared__ __align__(16) double2 s_seed[kLegWarps][R][32];   // the warp's seeds, copied in with the first coefficient tile
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int c = blockIdx.x, mi = blockIdx.y;
   const int m = m_loc[mi];
@@ -341,6 +351,9 @@ legendre_synthesis_kernel(const double *__restrict__ coef, const long *__restric
     // lane moves bytes [32*NS*lane, 32*NS*(lane+1)) of the tile
 #pragma unroll
     for (int q = 0; q < 2 * NS; ++q) cp_async16(tile + 4 * NS * lane + 2 * q, crow + 4 * NS * lane + 2 * q);
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+      if (rp0 + j * 32 < nrp) cp_async16(&s_seed[w][j][lane], &seed_tab[(size_t)mi * nrp + rp0 + j * 32]);
     cp_async_commit();
     int buf = 0;
     for (int l0 = lsmin; l0 <= lmax + 1; l0 += kLB, buf ^= 1) {
@@ -349,14 +362,14 @@ legendre_synthesis_kernel(const double *__restrict__ coef, const long *__restric
 #pragma unroll
       for (int q = 0; q < 2 * NS; ++q) cp_async16(nxt + 4 * NS * lane + 2 * q, crow + 4 * NS * lane + 2 * q);
       cp_async_commit();
+      cp_async_wait<1>();
+      __syncwarp();
 #pragma unroll
       for (int j = 0; j < R; ++j)
         if (ls[j] == l0) {
-          const double2 sd = seed_tab[(size_t)mi * nrp + rp0 + j * 32];
+          const double2 sd = s_seed[w][j][lane];
           mp[j] = sd.x; mc[j] = sd.y;
         }
-      cp_async_wait<1>();
-      __syncwarp();
       const double *t = &s_tile[w][buf][0];
 #pragma unroll
       for (int i = 0; i < kLB; ++i) {
@@ -425,8 +438,9 @@ legendre_synthesis_kernel(const double *__restrict__ coef, const long *__restric
     const double sth = sth_rp[rp], cth = cth_rp[rp];
     const double isth = 1.0 / sth, cot = cth * isth, m2s2 = m2 * isth * isth;
     // destination: this rank's send buffer, or (fused exchange) the ring owner's receive buffer over NVLink
-    double2 *o = (rp_bptr ? rp_bptr[rp + s * nrp] : b_send + s * b_shell + b_off[rp]) + (long)mi * 6 * b_stride[rp];
-    const long fs = b_stride[rp];
+    // (blocks are ordered [ring pair][field][m][hemisphere]: field stride = 2 * number of local m)
+    double2 *o = (rp_bptr ? rp_bptr[rp + s * nrp] : b_send + s * b_shell + b_off[rp]) + 2L * mi;
+    const long fs = b_fs;
     double2 q[6][2];   // [field][hemisphere]
 #pragma unroll
     for (int hemi = 0; hemi < 2; ++hemi) {
@@ -443,8 +457,8 @@ legendre_synthesis_kernel(const double *__restrict__ coef, const long *__restric
       q[4][hemi] = make_double2(-dm * q1i, dm * q1r);          // i m d_theta    (.. / sin)
       q[5][hemi] = make_double2(-m2 * Pr, -m2 * Pi);           // -m^2 P         (.. / sin^2)
     }
-    // the (north, south) pair of a field is 32 contiguous, 32-byte aligned bytes: one 256-bit store each (full sectors
-    // on the local path, full packets over NVLink)
+    // the (north, south) pair of a field is 32 contiguous, 32-byte aligned bytes: one 256-bit store each (a full sector;
+    // the neighbouring m of the same ring arrive from the CTAs next door and the L2 merges them into full lines)
 #pragma unroll
     for (int f = 0; f < 6; ++f)
       asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(o + f * fs), "d"(q[f][0].x), "d"(q[f][0].y),
@@ -497,11 +511,11 @@ int launch_legendre_analysis(ShtPlan *p, const double2 *d_g_recv, double *d_alm_
   int rows = g_ana_rows;
   if (rows <= 0) {
     const long want_warps = 16L * 3 * sm_count() * g_leg_warps_per_cta;
-    rows = (int)std::min<long>(nchunk, std::max<long>(8, (want_warps + p->nm_loc - 1) / p->nm_loc));
+    rows = (int)std::min<long>(nchunk, std::max<long>(16, (want_warps + p->nm_loc - 1) / p->nm_loc));
   }
   rows = std::max(1, std::min(rows, nchunk));
   rows = (nchunk + (nchunk / rows) - 1) / (nchunk / rows);     // chunks per warp = floor(nchunk / rows); rows = what that needs
-  if (!p->d_part || p->ana_nchunk != rows * nshell) {
+  if (!p->d_part || p->ana_nchunk < rows * nshell) {   // grow only: one- and two-shell passes alternate in a run of planes
     if (p->d_part) cudaFree(p->d_part);
     CLB_CUDA_CHECK(cudaMalloc(&p->d_part, sizeof(double2) * (size_t)rows * nshell * p->alm_total));
     p->ana_nchunk = rows * nshell;
@@ -562,7 +576,7 @@ int launch_legendre_synthesis(ShtPlan *p, const double *d_alm_re, const double *
   dim3 grid(nchunk, p->nm_loc);
 #define CLB_SYN_LAUNCH(RR, NS)                                                                                          \
   legendre_synthesis_kernel<RR, NS><<<grid, 32 * warps, 0, st>>>(p->d_coef, p->d_row_off, p->d_ls_syn, p->d_seed, p->d_cth, \
-                                                                  p->d_sth, p->d_m_loc, p->d_b_off, p->d_b_stride, d_b_send, \
+                                                                  p->d_sth, p->d_m_loc, p->d_b_off, 2L * p->nm_loc, d_b_send, \
                                                                   p->b_send_total, bptr, p->nrp, (int)p->lmax)
   if (nshell == 1) {
     switch (R) {

@@ -555,8 +555,12 @@ __global__ void __launch_bounds__(512) ring_analysis_scratch_kernel(AnaArgs A, d
 // ---------------------------------------------------------------------------------------------------------------
 // float half-complex bin k of one ring, accumulated exactly like the reference's unpack loop
 // (ascending m; positive-m contribution before the negative-m one; one float rounding per contribution).
-__device__ __forceinline__ float2 fold_bin(const double2 *__restrict__ b_recv, const long *__restrict__ m_boff,
-                                           long fslot, int k, int n, int lmax, int shifted)
+// b of (m, row = local ring pair * 6 + field, hemisphere): blocks are ordered [ring pair][field][m][hemisphere]
+struct BAddr {
+  const double2 *b; const long *off; const int *str; long row; int hemi;
+  __device__ __forceinline__ double2 operator()(long m) const { return __ldg(&b[off[m] + row * str[m] + hemi]); }
+};
+__device__ __forceinline__ float2 fold_bin(const BAddr &B, int k, int n, int lmax, int shifted)
 {
   // The contributions to bin k come from m = k, n-k, n+k, 2n-k, 2n+k, ... (k > 0) or m = 0, n, n, 2n, 2n, ...
   // (k = 0): term t >= 0 has m_t = (t+1)/2 * n + (t odd ? -k : +k) for k > 0; positive-m terms (t even) add b,
@@ -566,7 +570,7 @@ __device__ __forceinline__ float2 fold_bin(const double2 *__restrict__ b_recv, c
   // common case (every ring with more than lmax pixels, except near its Nyquist bin): only m = k lands in this bin
   if (n - k > lmax && (k > 0 || n > lmax)) {
     if (k > lmax) return make_float2(0.f, 0.f);
-    const double2 b = __ldg(&b_recv[m_boff[k] + fslot]);
+    const double2 b = B(k);
     return make_float2(__double2float_rn(__dadd_rn(0.0, b.x)), __double2float_rn(__dadd_rn(0.0, b.y)));
   }
   auto term_m = [&](int t) -> long {
@@ -583,13 +587,13 @@ __device__ __forceinline__ float2 fold_bin(const double2 *__restrict__ b_recv, c
   // k = 0 visits m = 0 once (positive term only), every later multiple of n twice (positive, then negative)
   int t = 0;
   if (k == 0) {
-    apply(0, __ldg(&b_recv[m_boff[0] + fslot]));
+    apply(0, B(0));
     for (long j = 1; j * n <= lmax; j += 4) {
       double2 b[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const long m = (j + u) * n;
-        b[u] = (m <= lmax) ? __ldg(&b_recv[m_boff[m] + fslot]) : make_double2(0.0, 0.0);
+        b[u] = (m <= lmax) ? B(m) : make_double2(0.0, 0.0);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -611,7 +615,7 @@ __device__ __forceinline__ float2 fold_bin(const double2 *__restrict__ b_recv, c
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const long m = term_m(t + u);
-      b[u] = (m <= lmax) ? __ldg(&b_recv[m_boff[m] + fslot]) : make_double2(0.0, 0.0);
+      b[u] = (m <= lmax) ? B(m) : make_double2(0.0, 0.0);
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -628,29 +632,27 @@ struct MapPtrs { float *p[6]; };
 // reused as park).  On the Bluestein path the bins Y overlay bufA[M/2..M), which is unused until the zero fill.
 struct SynArgs {
   const double2 *b_recv; MapPtrs maps; RingGeomDev geo;
-  const int *class_rp, *rp_to_local; const long *m_boff; int nslot_loc, lmax;
+  const int *class_rp, *rp_to_local; const long *m_boff; const int *m_bstr; int lmax;
   const signed char *rp_logM, *rp_blu; int Mmax, rmax;
   const long *chirp_off, *bhat_off; const double2 *chirp_all, *bhat_all, *tw; int logTW;
   const double2 *phase_all; const long *phase_off;
   int dbg;            // development aid (clb_set_tuning(8, bits)): 1 no b loads, 2 no transforms, 4 no stores -- wrong results, phase costs
-  int nfg, prefetch;   // field groups per ring (1: all six in one CTA; 3: {0,3},{1,5},{2,4}), L2 prefetch of the next field
+  int nfg;             // field groups per ring (1: all six in one CTA; 3: {0,3},{1,5},{2,4})
 };
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 
 
 // One CTA synthesises two (or all six) fields of one ring, one after the other: work = 2 * (index into the class list) +
 // hemisphere, group = which fields.  Field 1 is always done before 5 and 2 before 4 by the same threads, so the
 // cot(theta) cross terms (alm2allmaps_transpose_mpi.c:1097-1147) are applied on the way out of fields 4 and 5 -- no second
-// kernel, no second pass over the maps.  (An L2 prefetch of the next field's b_m during the transform of the current
-// one was measured and lost 15 %: prefetch.global.L2 moves more than the 16 bytes per 1.5 MB stride this gather needs;
-// it stays behind clb_set_tuning(7, 1).)
+// kernel, no second pass over the maps.  The b_m of a (ring, field) are one contiguous run in m (hemispheres interleaved):
+// streaming reads; the CTA of the other hemisphere, next in line, finds the other half of every sector in L2.
 __device__ __forceinline__ void ring_synthesis_body(const SynArgs &A, double2 *smem, int work, int group)
 {
   const double2 *__restrict__ b_recv = A.b_recv; const MapPtrs &maps = A.maps; const RingGeomDev &geo = A.geo;
   const int *__restrict__ class_rp = A.class_rp, *__restrict__ rp_to_local = A.rp_to_local;
-  const long *__restrict__ m_boff = A.m_boff; const int nslot_loc = A.nslot_loc, lmax = A.lmax;
+  const int lmax = A.lmax;
   const signed char *__restrict__ rp_logM = A.rp_logM, *__restrict__ rp_blu = A.rp_blu;
   const int Mmax = A.Mmax, rmax = A.rmax;
   const long *__restrict__ chirp_off = A.chirp_off, *__restrict__ bhat_off = A.bhat_off;
@@ -667,7 +669,7 @@ __device__ __forceinline__ void ring_synthesis_body(const SynArgs &A, double2 *s
   const int M = 1 << logM;
   const double2 *PT = phase_all + phase_off[rp];
   const int shifted = geo.shifted[rp];
-  const long slot = 2 * rp_to_local[rp] + hemi;
+  const long rpl = rp_to_local[rp];
   double2 *bufA = smem;
   double2 *bufB = smem + Mmax;
   float2 *tailbuf = reinterpret_cast<float2 *>(smem + Mmax + rmax + 1);
@@ -697,8 +699,7 @@ __device__ __forceinline__ void ring_synthesis_body(const SynArgs &A, double2 *s
 #pragma unroll 1
   for (int fi = 0; fi < nf; ++fi) {
     const int field = (A.nfg == 1) ? fi : (fi == 0 ? group : (group == 0 ? 3 : group == 1 ? 5 : 4));
-    const int field_next = (A.nfg == 1) ? fi + 1 : (group == 0 ? 3 : group == 1 ? 5 : 4);
-    const long fslot = (long)field * nslot_loc + slot;
+    const BAddr B{b_recv, A.m_boff, A.m_bstr, rpl * 6 + field, hemi};
     // S1: folded, phased float bins.  U bins per thread and trip, the global loads of both terms of all U bins (and of
     // the phase table) issued together: this loop is otherwise bound by one exposed memory round trip per bin
     constexpr int U = 4;
@@ -711,8 +712,8 @@ __device__ __forceinline__ void ring_synthesis_body(const SynArgs &A, double2 *s
         valid[u] = k <= 2 * r;
         two[u] = valid[u] && !deep && k > 0 && (n - k <= lmax);     // the conjugated term m = n - k lands here too
         b0[u] = make_double2(0.0, 0.0); b1[u] = make_double2(0.0, 0.0); ph[u] = make_double2(1.0, 0.0);
-        if (valid[u] && !deep && k <= lmax && !(A.dbg & 1)) b0[u] = __ldg(&b_recv[m_boff[k] + fslot]);
-        if (two[u] && !(A.dbg & 1)) b1[u] = __ldg(&b_recv[m_boff[n - k] + fslot]);
+        if (valid[u] && !deep && k <= lmax && !(A.dbg & 1)) b0[u] = B(k);
+        if (two[u] && !(A.dbg & 1)) b1[u] = B(n - k);
         if (valid[u] && shifted) ph[u] = __ldg(&PT[k]);               // (cos, sin)(k pi / n), tabulated at plan time
       }
 #pragma unroll
@@ -720,7 +721,7 @@ __device__ __forceinline__ void ring_synthesis_body(const SynArgs &A, double2 *s
         if (!valid[u]) continue;
         const int k = kb + u * blockDim.x;
         float2 y;
-        if (deep) y = (A.dbg & 1) ? make_float2(1.f, 0.f) : fold_bin(b_recv, m_boff, fslot, k, n, lmax, shifted);
+        if (deep) y = (A.dbg & 1) ? make_float2(1.f, 0.f) : fold_bin(B, k, n, lmax, shifted);
         else {
           // exactly the reference's float accumulation (ascending m; alm2allmaps_transpose_mpi.c:836-881): term 0 has
           // wrap count 0 (sign +1), term 1 wrap count 1 (sign -1 on shifted rings) and enters conjugated
@@ -738,14 +739,6 @@ __device__ __forceinline__ void ring_synthesis_body(const SynArgs &A, double2 *s
           y.y = __double2float_rn(__dadd_rn(__dmul_rn(t1, c), __dmul_rn(t0, s)));
         }
         Y[k] = y;
-      }
-    }
-    // the next field's b_m start their trip from HBM into L2 now and arrive while this field is transformed
-    if (A.prefetch && fi + 1 < nf && !deep) {
-      const long fnext = (long)field_next * nslot_loc + slot;
-      for (int k = threadIdx.x; k <= 2 * r; k += blockDim.x) {
-        if (k <= lmax) prefetch_l2(&b_recv[m_boff[k] + fnext]);
-        if (k > 0 && n - k <= lmax && n - k > 2 * r) prefetch_l2(&b_recv[m_boff[n - k] + fnext]);
       }
     }
     __syncthreads();
@@ -882,7 +875,6 @@ __global__ void __launch_bounds__(512) ring_synthesis_scratch_kernel(SynArgs A, 
 constexpr size_t kMaxSmem = 227 * 1024;
 int g_fft_field_groups = 0;     // clb_set_tuning(6, 0|1|3): CTAs per ring and hemisphere; 0 = default (3: fields {0,3}, {1,5}, {2,4})
 int g_fft_debug = 0;
-int g_fft_prefetch = 0;         // clb_set_tuning(7, 0|1): L2 prefetch of the next field's b_m
 int g_fft_force_scratch = 0;    // clb_set_tuning(4, 1): run every ring FFT from global scratch (tests the large-ring path at small Nside)
 int g_fft_threads_big = 512;   // threads per CTA for work lengths >= 4096 (clb_set_tuning(2, .))
 
@@ -1095,9 +1087,9 @@ int launch_ring_synthesis(const ShtPlan *p, const double2 *d_b_recv, float *cons
   for (int k = 0; k < 6; ++k) mp.p[k] = d_maps[k];
   int launches = 0;
   for (const auto &c : t->classes) {
-    SynArgs A{d_b_recv, mp, geom_of(p), c.d_rp, plan_rp_to_local(p), p->d_m_boff, 2 * p->nrp_loc, (int)p->lmax, t->d_rp_logM,
+    SynArgs A{d_b_recv, mp, geom_of(p), c.d_rp, plan_rp_to_local(p), p->d_m_boff, p->d_m_bstr, (int)p->lmax, t->d_rp_logM,
               t->d_rp_blu, 1 << c.logM, c.rmax, t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat, t->d_tw, t->logTW,
-              t->d_phase, t->d_phase_off, g_fft_debug, 1, g_fft_prefetch};
+              t->d_phase, t->d_phase_off, g_fft_debug, 1};
     A.nfg = g_fft_field_groups ? g_fft_field_groups : 3;
     if (c.smem_syn <= kMaxSmem && !g_fft_force_scratch) {
       dim3 grid(2 * c.count, A.nfg);

@@ -58,11 +58,13 @@ struct ShtPlan {
   // exchange layouts (in double2 elements)
   //  analysis:  FFT side writes  g_send[m_goff[m] + slot_loc]             (slot_loc = 2*rp_local + hemi)
   //             Legendre side reads g_recv[g_off[rp] + m_idx*g_stride[rp] + hemi]
-  //  synthesis: Legendre side writes b_send[b_off[rp] + (m_idx*6+f)*b_stride[rp] + hemi]
-  //             FFT side reads   b_recv[m_boff[m] + f*nslot_loc + slot_loc]
+  //  synthesis: blocks ordered [ring pair][field][m][hemisphere] (a ring's b_m are one contiguous run for its FFT)
+  //             Legendre side writes b_send[b_off[rp] + (f*nm_loc + m_idx)*2 + hemi]
+  //             FFT side reads   b_recv[m_boff[m] + (rp_local*6 + f)*m_bstr[m] + hemi]
   long *d_m_goff = nullptr, *d_m_boff = nullptr;   // [lmax+1]
   long *d_g_off = nullptr, *d_b_off = nullptr;     // [nrp]
-  int *d_g_stride = nullptr, *d_b_stride = nullptr;  // [nrp]
+  int *d_g_stride = nullptr;                       // [nrp]
+  int *d_m_bstr = nullptr;                         // [lmax+1]
   std::vector<long> g_send_count, g_recv_count, b_send_count, b_recv_count;  // per peer, in double2 elements
   long g_send_total = 0, g_recv_total = 0, b_send_total = 0, b_recv_total = 0;
   // recurrence tables for the local m rows: row(m_idx) starts at row_off[m_idx], index l-m, length row_len

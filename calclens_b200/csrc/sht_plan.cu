@@ -193,17 +193,18 @@ ShtPlan *sht_plan_create(long order, long lmax, const double *ring_weights, int 
   }
   p->g_send_total = a; p->g_recv_total = b; p->b_send_total = c; p->b_recv_total = d;
   std::vector<long> m_goff(lmax + 1), m_boff(lmax + 1), g_off(nrp), b_off(nrp);
-  std::vector<int> g_stride(nrp), b_stride(nrp);
+  std::vector<int> g_stride(nrp), m_bstr(lmax + 1);
   for (long m = 0; m <= lmax; ++m) {
     int q = p->m_owner[m];
     m_goff[m] = g_sbase[q] + (long)m_local_idx[m] * nslot_mine;
-    m_boff[m] = b_rbase[q] + (long)m_local_idx[m] * 6L * nslot_mine;
+    // b blocks are ordered [ring pair][field][m][hemisphere]: the block from rank q holds its nm_of_rank[q] values of m
+    m_boff[m] = b_rbase[q] + 2L * m_local_idx[m]; m_bstr[m] = 2 * p->nm_of_rank[q];
   }
   for (int rp = 0; rp < nrp; ++rp) {
     int q = p->rp_owner[rp];
     int ns = 2 * p->nrp_of_rank[q];
     g_off[rp] = g_rbase[q] + 2L * rp_local_idx[rp]; g_stride[rp] = ns;
-    b_off[rp] = b_sbase[q] + 2L * rp_local_idx[rp]; b_stride[rp] = ns;
+    b_off[rp] = b_sbase[q] + (long)rp_local_idx[rp] * 6L * p->nm_loc * 2L;
   }
   // upload geometry and layouts
   p->d_cth = to_device(p->h_cth); p->d_sth = to_device(p->h_sth); p->d_logsth = to_device(logsth);
@@ -212,7 +213,7 @@ ShtPlan *sht_plan_create(long order, long lmax, const double *ring_weights, int 
   p->d_rp_loc = to_device(p->rp_loc); p->d_m_loc = to_device(p->m_loc);
   p->d_m_goff = to_device(m_goff); p->d_m_boff = to_device(m_boff);
   p->d_g_off = to_device(g_off); p->d_b_off = to_device(b_off);
-  p->d_g_stride = to_device(g_stride); p->d_b_stride = to_device(b_stride);
+  p->d_g_stride = to_device(g_stride); p->d_m_bstr = to_device(m_bstr);
   {
     std::vector<int> r2l(nrp, -1);
     for (int i = 0; i < p->nrp_loc; ++i) r2l[p->rp_loc[i]] = i;
@@ -271,7 +272,7 @@ void sht_plan_destroy(ShtPlan *p)
   fft_tables_destroy(p);
   void *ptrs[] = {p->d_cth, p->d_sth, p->d_logsth, p->d_weight, p->d_nphi, p->d_shifted, p->d_startN, p->d_startS,
                   p->d_rp_loc, p->d_m_loc, p->d_m_goff, p->d_m_boff, p->d_g_off, p->d_b_off, p->d_g_stride,
-                  p->d_b_stride, p->d_rp_to_local, p->d_row_off, p->d_alm_off, p->d_A, p->d_c, p->d_coef,
+                  p->d_m_bstr, p->d_rp_to_local, p->d_row_off, p->d_alm_off, p->d_A, p->d_c, p->d_coef,
                   p->d_ls_ana, p->d_ls_syn, p->d_seed, p->d_part, (void *)p->d_rp_gsrc, p->d_rp_bptr};
   for (void *q : ptrs) if (q) cudaFree(q);
   delete p;
@@ -282,7 +283,7 @@ int *plan_rp_to_local(const ShtPlan *p) { return p->d_rp_to_local; }
 // Fused exchange over peer memory.  g (analysis): every rank's ring FFT fills its own send buffer with coalesced
 // local stores, and the Legendre stage of the m owner READS the (north, south) pairs of 32 adjacent ring pairs -- 1 KB
 // contiguous per warp -- straight out of the ring owner's buffer over NVLink.  b (synthesis): the Legendre epilogue
-// WRITES its 128-byte runs straight into the ring owner's receive buffer.  g_send_ptrs[q] / b_recv_ptrs[q] are the
+// WRITES its 32-byte (north, south) pairs straight into the ring owner's receive buffer.  g_send_ptrs[q] / b_recv_ptrs[q] are the
 // base addresses of rank q's buffers as seen from this process (peer mappings; this rank's own buffers for q == rank).
 void sht_plan_set_peers(ShtPlan *p, void *const *g_send_ptrs, void *const *b_recv_ptrs, int nshell)
 {
@@ -302,7 +303,7 @@ void sht_plan_set_peers(ShtPlan *p, void *const *g_send_ptrs, void *const *b_rec
       rbase += (long)p->nm_of_rank[r] * 6L * nslot_q;   // q's receive block from rank r
     }
     gsrc[rp] = reinterpret_cast<const double2 *>(g_send_ptrs[q]) + sbase + 2L * rp_local_idx[rp];
-    bptr[rp] = reinterpret_cast<double2 *>(b_recv_ptrs[q]) + rbase + 2L * rp_local_idx[rp];
+    bptr[rp] = reinterpret_cast<double2 *>(b_recv_ptrs[q]) + rbase + (long)rp_local_idx[rp] * 6L * p->nm_loc * 2L;
     if (nshell >= 2) {
       gsrc[nrp + rp] = gsrc[rp] + (p->lmax + 1) * nslot_q;          // rank q's g_send_total
       bptr[nrp + rp] = bptr[rp] + (p->lmax + 1) * 6L * nslot_q;     // rank q's b_recv_total

@@ -51,13 +51,18 @@ class ExchangeLayout:
         return int(self.g_rbase[q] + self.m_local[m] * 2 * self.nrp_of[q] + 2 * self.rp_local[rp] + hemi)
 
     # synthesis transpose -------------------------------------------------------------------------------------
+    # Inside a peer block the order is [ring pair][field][m][hemisphere]: the ring FFT of a (ring, field) then reads its
+    # b_m as one contiguous run in m (streaming HBM reads instead of one 16-byte gather per m at a stride of megabytes),
+    # and the scatter sits on the Legendre side, whose 32-byte (north, south) stores the L2 merges into full lines.
     def b_send_index(self, m, field, rp, hemi):
+        """where the Legendre stage of the owner of m (this rank) puts b of (field, rp, hemi)"""
         q = self.rp_owner[rp]
-        return int(self.b_sbase[q] + (self.m_local[m] * 6 + field) * 2 * self.nrp_of[q] + 2 * self.rp_local[rp] + hemi)
+        return int(self.b_sbase[q] + ((self.rp_local[rp] * 6 + field) * self.my_m.size + self.m_local[m]) * 2 + hemi)
 
     def b_recv_index(self, m, field, rp, hemi):
+        """where the FFT stage of the owner of ring pair rp (this rank) finds b_m of (field, rp, hemi)"""
         q = self.m_owner[m]
-        return int(self.b_rbase[q] + (self.m_local[m] * 6 + field) * self.nslot_mine + 2 * self.rp_local[rp] + hemi)
+        return int(self.b_rbase[q] + ((self.rp_local[rp] * 6 + field) * int(self.nm_of[q]) + self.m_local[m]) * 2 + hemi)
 
 
     # fused exchange over peer memory (csrc/sht_plan.cu:sht_plan_set_peers) -------------------------------------
@@ -75,7 +80,7 @@ class ExchangeLayout:
         q = self.rp_owner[rp]
         nslot_q = 2 * int(self.nrp_of[q])
         rbase = sum(int(self.nm_of[r]) * 6 * nslot_q for r in range(self.rank))
-        return int(q), int(rbase + (m_idx * 6 + field) * nslot_q + 2 * self.rp_local[rp] + hemi)
+        return int(q), int(rbase + ((self.rp_local[rp] * 6 + field) * self.my_m.size + m_idx) * 2 + hemi)
 
 
 def ray_ranges(ray_order, nranks):

@@ -1,5 +1,5 @@
 #!/bin/bash
-# per-class ring FFT durations for a list of tuning settings: tools/fft_classes.sh "fg=1 pf=0" "fg=3 pf=1" ...
+# per-class ring FFT durations for a list of tuning settings: tools/fft_classes.sh "fg=1" "fg=3 dbg=1" ...
 for cfg in "$@"; do
   tag=$(echo $cfg | tr ' =' '__')
   ncu --metrics gpu__time_duration.sum --clock-control none -k regex:ring_synthesis -c 4 --csv --log-file gpurun_out/fftc_$tag.csv python tools/stage_bench.py 12 8192 1 $cfg > /dev/null 2>&1

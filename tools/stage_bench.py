@@ -16,7 +16,6 @@ for a in sys.argv[3:]:
     elif a.startswith("scratch="): _lib.load().clb_set_tuning(4, int(a[8:]))
     elif a.startswith("sr="): _lib.load().clb_set_tuning(5, int(a[3:]))
     elif a.startswith("fg="): _lib.load().clb_set_tuning(6, int(a[3:]))
-    elif a.startswith("pf="): _lib.load().clb_set_tuning(7, int(a[3:]))
     elif a.startswith("dbg="): _lib.load().clb_set_tuning(8, int(a[4:]))
     else: reps = int(a)
 L = _lib.load()
@@ -59,7 +58,7 @@ t, maps = timeit(lambda: plan.ring_synthesis(bref, maps_b))
 print("ring_synthesis       %8.3f ms" % t)
 # ray stage on the maps just synthesised (scaled to lensing-like amplitudes)
 import ctypes as C
-maps = maps_b * (1e-3 / float(maps_b[3].abs().max()))
+maps = maps_b * (1e-3 / max(float(maps_b[3].abs().max()), 1e-30))
 nrays = plan.npix
 rays = torch.empty(nrays * 176, dtype=torch.uint8, device="cuda")
 L.clb_ray_init_dev(rays.data_ptr(), nrays, 0, order, 15.0, None)
