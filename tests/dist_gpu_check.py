@@ -32,8 +32,16 @@ def main():
     if fused and not solver.fused:
         print("WARNING: fused exchange requested but peer mapping failed")
     solver.init_rays(15.0)
-    planes = [(45.0, 15.0, 0.0), (75.0, 45.0, 15.0), (105.0, 75.0, 45.0)]
-    sums = [solver.step(counts, premul, densmul, backdens, *pl) for pl in planes]
+    planes = [(45.0, 15.0, 0.0), (75.0, 45.0, 15.0), (105.0, 75.0, 45.0), (135.0, 105.0, 75.0), (165.0, 135.0, 105.0)]
+    pm = [np.float32(premul * (1.0 + 0.25 * k)) for k in range(len(planes))]     # a different shell per plane
+    # two planes per SHT pass (CLB_PAIR=1, fused solver only): planes (0,1) and (2,3) share their Legendre passes
+    pairs = solver.fused and os.environ.get("CLB_PAIR", "1") != "0"
+    sums = []
+    for k, pl in enumerate(planes):
+        pair = (counts, pm[k + 1], densmul, backdens) if (pairs and k in (0, 2)) else None
+        sums.append(solver.step(counts, pm[k], densmul, backdens, *pl, pair=pair))
+    if rank == 0:
+        print("two planes per SHT pass:", bool(pairs))
     maps_d = solver.maps.cpu().numpy()
     rays_d = solver.rays_host().copy()
     gathered = [None] * world
@@ -42,7 +50,7 @@ def main():
     if rank == 0:
         single = poisson.LensPlaneSolver(order, lmax, ray_order, device=local_rank)
         single.init_rays(15.0)
-        sums1 = [single.step(counts, premul, densmul, backdens, *pl) for pl in planes]
+        sums1 = [single.step(counts, pm[k], densmul, backdens, *pl) for k, pl in enumerate(planes)]
         maps_s = single.maps.cpu().numpy()
         rays_s = single.rays_host()
         if solver._need is None:
