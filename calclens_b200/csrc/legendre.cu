@@ -58,7 +58,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // equatorial rings, so the warps of a CTA finish together) and accumulates them into the same row, which it alone owns:
 // the first chunk stores, the later ones add with red.global (same thread, same address: program order, so the sum is
 // deterministic).  alm_finish_kernel adds the `rows` rows of an m in a fixed order.
-template <int R, int NS, int NB>
+template <int R, int NS, int NB, bool PIPE>
 __global__ void __launch_bounds__(kLegThreads, NB)
 legendre_analysis_kernel(const double2 *__restrict__ g_recv, long g_shell, const double2 *const *__restrict__ rp_gsrc,
                          const long *__restrict__ g_off, const int *__restrict__ g_stride, const double *__restrict__ Atab,
@@ -72,17 +72,21 @@ legendre_analysis_kernel(const double2 *__restrict__ g_recv, long g_shell, const
   constexpr int KB = 8 / NS;  // degrees per block: 2 * KB * NS = 16 partial sums per thread either way
   constexpr int V = 16;       // v[s*2*KB + i] = re(shell s, l0+i), v[s*2*KB + KB + i] = im(shell s, l0+i)
   constexpr int NP = (R + 1) / 2;
-  __shared__ __align__(16) double s_A[kLegWarps][2][kAnaTile];
-  __shared__ double s_red[kLegWarps][16 * 33];
-  __shared__ __align__(16) double2 s_seed[kLegWarps][R][32];   // the chunk's seeds, copied in with the first coefficient tile
+  // dynamic shared memory (more than the 48 KB static limit for the larger variants), per warp:
+  //   A tiles [2][kAnaTile] | parked partial sums [PIPE ? 2 : 1][16 * 33] | the chunk's seeds [R][32] (double2), copied in
+  //   with the first coefficient tile
+  extern __shared__ __align__(16) double s_dyn[];
+  constexpr int kRedBufs = PIPE ? 2 : 1;
+  constexpr int kWarpDoubles = 2 * kAnaTile + kRedBufs * 16 * 33 + 2 * R * 32;
 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int row = blockIdx.x * (blockDim.x >> 5) + w, mi = blockIdx.y;
   if (row >= rows) return;     // (no block barriers in this kernel)
   const int m = m_loc[mi];
   double2 *out = part + (size_t)row * alm_total + alm_off[mi];   // index l - m; shell s at + s * part_shell
-  double *sA = &s_A[w][0][0];
-  double *red = &s_red[w][0];
+  double *sA = s_dyn + (size_t)w * kWarpDoubles;
+  double *red = sA + 2 * kAnaTile;
+  double2 *seeds = reinterpret_cast<double2 *>(red + kRedBufs * 16 * 33);   // [R][32]; 16-byte aligned: all counts are even
   // which (shell, degree) pair of a block this lane delivers after the reduction
   const int osh = lane / (2 * KB), oi = lane % (2 * KB);
   const bool writer = lane < V && oi < KB;
@@ -126,7 +130,7 @@ legendre_analysis_kernel(const double2 *__restrict__ g_recv, long g_shell, const
     // (a global load at the moment a ring starts would stall the whole warp on HBM latency in the middle of the FP64 work)
 #pragma unroll
     for (int j = 0; j < R; ++j)
-      if (rp0 + j * 32 < nrp) cp_async16(&s_seed[w][j][lane], &seed_tab[(size_t)mi * nrp + rp0 + j * 32]);
+      if (rp0 + j * 32 < nrp) cp_async16(&seeds[j * 32 + lane], &seed_tab[(size_t)mi * nrp + rp0 + j * 32]);
     const bool rmw = !first;
     if (first) {                     // degrees below the first active block get exact zeros
       for (int l = m + lane; l < lsw; l += 32)
@@ -140,6 +144,20 @@ legendre_analysis_kernel(const double2 *__restrict__ g_recv, long g_shell, const
     const double *Arow = Atab + row_off[mi] + (lsw - m);
     if (lane < kAnaTile / 2) cp_async16(sA + 2 * lane, Arow + 2 * lane);
     cp_async_commit();
+    // PIPE: the warp sum of block b is taken while block b+1 is computed -- the block's partial sums wait in one of two
+    // shared-memory buffers, a quarter of the column sum rides on every (second) degree of the next block, and the result
+    // leaves at the end of that block: the FP64 pipe has work during the whole reduction.  Same values, same order of adds.
+    auto deliver = [&](double2 *dst, double t, double ti) {
+      if (!rmw) *dst = make_double2(t, ti);
+      else {   // a later chunk of the same row: fire-and-forget adds in L2 (this thread alone touches the address, in program order)
+        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(&dst->x), "d"(t) : "memory");
+        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(&dst->y), "d"(ti) : "memory");
+      }
+    };
+    bool pend = false;          // a parked block is waiting for its warp sum
+    int pbuf = 0;               // buffer the next block parks in
+    double2 *pdst = out;        // destination of the waiting block (valid when pok)
+    bool pok = false;
     int cur = 0;
     for (int lt = lsw; lt <= lmax; lt += kAnaTile, cur ^= 1) {
       Arow += kAnaTile;
@@ -158,15 +176,23 @@ legendre_analysis_kernel(const double2 *__restrict__ g_recv, long g_shell, const
 #pragma unroll
           for (int j = 0; j < R; ++j)
             if (((sb[j / 2] >> (16 * (j & 1))) & 0xffffu) == blk) {
-              const double2 sd = s_seed[w][j][lane];
+              const double2 sd = seeds[j * 32 + lane];
               mp[j] = sd.x; mc[j] = sd.y;
             }
         }
+        // columns of the waiting block (PIPE; stale data when nothing waits -- computed, never delivered)
+        const double *pcol = red + (pbuf ^ 1) * (16 * 33) + (lane & 15) * 33 + (lane >> 4) * 16;
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
         double v[V];
 #pragma unroll
         for (int i = 0; i < V; ++i) v[i] = 0.0;
 #pragma unroll
         for (int i = 0; i < KB; ++i) {
+          if (PIPE && i % (KB / 4) == 0) {
+            const int k = 4 * (i / (KB / 4));
+            if (k == 0) { t0 = pcol[0]; t1 = pcol[1]; t2 = pcol[2]; t3 = pcol[3]; }
+            else { t0 += pcol[k]; t1 += pcol[k + 1]; t2 += pcol[k + 2]; t3 += pcol[k + 3]; }
+          }
           const double a = sa[b * KB + i];
 #pragma unroll
           for (int j = 0; j < R; ++j) {
@@ -181,29 +207,45 @@ legendre_analysis_kernel(const double2 *__restrict__ g_recv, long g_shell, const
           }
         }
         // warp reduction through shared memory: every lane parks its 16 partial sums ([value][lane], rows padded to 33 so
-        // that the column reads below spread over all banks), then lane L adds 16 lanes' worth of value L % 16 and one
+        // that the column reads spread over all banks), then lane L adds 16 lanes' worth of value L % 16 and one
         // shuffle joins the two halves -- ~3x fewer instructions than a shuffle transpose-reduce, which matters because
         // the reduction shares the issue slots of the warps that feed the FP64 pipe
+        if (PIPE) {
+          double t = (t0 + t1) + (t2 + t3);
+          t += __shfl_xor_sync(0xffffffffu, t, 16);
+          const double ti = __shfl_down_sync(0xffffffffu, t, KB);   // imaginary part lives KB lanes up
+          if (pend && pok) deliver(pdst, t, ti);
+          double *park = red + pbuf * (16 * 33);
 #pragma unroll
-        for (int i = 0; i < V; ++i) red[i * 33 + lane] = v[i];
-        __syncwarp();
-        const double *col = red + (lane & 15) * 33 + (lane >> 4) * 16;
-        double t0 = col[0], t1 = col[1], t2 = col[2], t3 = col[3];
+          for (int i = 0; i < V; ++i) park[i * 33 + lane] = v[i];
+          __syncwarp();   // parked for the next block to sum; and every lane is done reading the other buffer
+          pend = true; pdst = dst; pok = writer && l0 + oi <= lmax; pbuf ^= 1;
+        } else {
 #pragma unroll
-        for (int k = 4; k < 16; k += 4) { t0 += col[k]; t1 += col[k + 1]; t2 += col[k + 2]; t3 += col[k + 3]; }
-        double t = (t0 + t1) + (t2 + t3);
-        t += __shfl_xor_sync(0xffffffffu, t, 16);
-        const double ti = __shfl_down_sync(0xffffffffu, t, KB);   // imaginary part lives KB lanes up
-        if (writer && l0 + oi <= lmax) {
-          if (!rmw) *dst = make_double2(t, ti);
-          else {   // a later chunk of the same row: fire-and-forget adds in L2 (this thread alone touches the address, in program order)
-            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(&dst->x), "d"(t) : "memory");
-            asm volatile("red.global.add.f64 [%0], %1;" ::"l"(&dst->y), "d"(ti) : "memory");
-          }
+          for (int i = 0; i < V; ++i) red[i * 33 + lane] = v[i];
+          __syncwarp();
+          const double *col = red + (lane & 15) * 33 + (lane >> 4) * 16;
+          t0 = col[0]; t1 = col[1]; t2 = col[2]; t3 = col[3];
+#pragma unroll
+          for (int k = 4; k < 16; k += 4) { t0 += col[k]; t1 += col[k + 1]; t2 += col[k + 2]; t3 += col[k + 3]; }
+          double t = (t0 + t1) + (t2 + t3);
+          t += __shfl_xor_sync(0xffffffffu, t, 16);
+          const double ti = __shfl_down_sync(0xffffffffu, t, KB);   // imaginary part lives KB lanes up
+          if (writer && l0 + oi <= lmax) deliver(dst, t, ti);
+          __syncwarp();   // the parked sums are consumed before the next block overwrites them
         }
-        __syncwarp();   // the parked sums are consumed before the next block overwrites them
       }
       __syncwarp();   // everyone is done with this tile before the next iteration's copy overwrites it
+    }
+    if (PIPE && pend) {   // the last block of the chunk
+      const double *col = red + (pbuf ^ 1) * (16 * 33) + (lane & 15) * 33 + (lane >> 4) * 16;
+      double t0 = col[0], t1 = col[1], t2 = col[2], t3 = col[3];
+#pragma unroll
+      for (int k = 4; k < 16; k += 4) { t0 += col[k]; t1 += col[k + 1]; t2 += col[k + 2]; t3 += col[k + 3]; }
+      double t = (t0 + t1) + (t2 + t3);
+      t += __shfl_xor_sync(0xffffffffu, t, 16);
+      const double ti = __shfl_down_sync(0xffffffffu, t, KB);
+      if (pok) deliver(pdst, t, ti);
     }
     cp_async_wait<0>();
     __syncwarp();   // (also: every lane has read its seeds before the next chunk's copies overwrite them)
@@ -310,7 +352,7 @@ __global__ void synthesis_coef_kernel(const double *__restrict__ alm_re, const d
 // tile (cp.async, 1 KB per 16 degrees and shell) and reads them back as broadcast LDS.128.  Per degree and ring pair:
 // the recurrence (DMUL + DFMA, shared by the NS shells of a batched pass) and six DFMA per shell.
 template <int R, int NS>
-__global__ void __launch_bounds__(kLegThreads, (NS == 2) ? 2 : ((R >= 4) ? 3 : 4))
+__global__ void __launch_bounds__(kLegThreads, (NS == 2) ? ((R <= 2) ? 3 : 2) : ((R >= 4) ? 3 : 4))
 legendre_synthesis_kernel(const double *__restrict__ coef, const long *__restrict__ row_off,
                           const int *__restrict__ ls_tab, const double2 *__restrict__ seed_tab,
                           const double *__restrict__ cth_rp, const double *__restrict__ sth_rp,
@@ -474,18 +516,32 @@ int g_leg_warps_per_cta = 4;      // warps are independent in both Legendre kern
 int g_syn_rings_per_thread = 4;   // tunable through clb_set_tuning(0, .)
 int g_ana_rings_per_thread = 8;   // tunable through clb_set_tuning(1, .): 8, 4, 2 or 1
 int g_ana_rows = 0;               // clb_set_tuning(5, n): partial-sum rows per m (0 = automatic)
-int g_syn2_rings_per_thread = 4;  // clb_set_tuning(9, .): rings per thread of the two-shell synthesis kernel
+int g_syn2_rings_per_thread = 3;  // clb_set_tuning(9, .): rings per thread of the two-shell synthesis kernel (3: 244 registers, no spills)
 int g_ana2_rings_per_thread = 8;  // clb_set_tuning(10, .): rings per thread of the two-shell analysis kernel
+
+int g_ana_pipeline = 1;           // clb_set_tuning(12, 0|1|2): warp sum of a block overlapped with the next block's FP64 work: never,
+                                  // in one-shell passes only (measured: 71.1 -> 70.1 ms there, 56.7 -> 61.0 ms with two shells at the
+                                  // 255-register cap), always
 
 template <int R, int NS, int NB>
 static void launch_ana_t(const ShtPlan *p, const double2 *g_recv, const double2 *const *gsrc, int rows, int nchunk, cudaStream_t st)
 {
   const int warps = g_leg_warps_per_cta;
   dim3 grid((rows + warps - 1) / warps, p->nm_loc);
-  legendre_analysis_kernel<R, NS, NB><<<grid, 32 * warps, 0, st>>>(
-      g_recv, p->g_recv_total, gsrc, p->d_g_off, p->d_g_stride, p->d_A, p->d_row_off, p->d_ls_ana, p->d_seed, p->d_cth,
-      p->d_m_loc, p->d_alm_off, reinterpret_cast<double2 *>(p->d_part), (long)rows * p->alm_total, p->alm_total, p->nrp,
-      (int)p->lmax, rows, nchunk);
+#define CLB_ANA_ARGS g_recv, p->g_recv_total, gsrc, p->d_g_off, p->d_g_stride, p->d_A, p->d_row_off, p->d_ls_ana, p->d_seed, p->d_cth, \
+      p->d_m_loc, p->d_alm_off, reinterpret_cast<double2 *>(p->d_part), (long)rows * p->alm_total, p->alm_total, p->nrp,           \
+      (int)p->lmax, rows, nchunk
+  auto smem_of = [&](int bufs) { return sizeof(double) * (size_t)warps * (2 * kAnaTile + bufs * 16 * 33 + 2 * R * 32); };
+  if (g_ana_pipeline == 2 || (g_ana_pipeline == 1 && NS == 1)) {
+    static bool attr = false;   // (per instantiation)
+    if (!attr) { CLB_CUDA_CHECK(cudaFuncSetAttribute(legendre_analysis_kernel<R, NS, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(2) * 4 / warps)); attr = true; }
+    legendre_analysis_kernel<R, NS, NB, true><<<grid, 32 * warps, smem_of(2), st>>>(CLB_ANA_ARGS);
+  } else {
+    static bool attr = false;
+    if (!attr) { CLB_CUDA_CHECK(cudaFuncSetAttribute(legendre_analysis_kernel<R, NS, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(1) * 4 / warps)); attr = true; }
+    legendre_analysis_kernel<R, NS, NB, false><<<grid, 32 * warps, smem_of(1), st>>>(CLB_ANA_ARGS);
+  }
+#undef CLB_ANA_ARGS
 }
 
 // nshell = 1: one plane.  nshell = 2: two planes in one pass: shell s reads g at

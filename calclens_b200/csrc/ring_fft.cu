@@ -926,7 +926,8 @@ void fft_tables_create(ShtPlan *p)
   const long nside = p->nside;
   // classes over the local ring pairs
   struct Key { int logM, blu; };
-  constexpr int kSmallLogM = 11;   // every ring with M <= 2048 goes into one launch (they are latency bound one by one)
+  constexpr int kSmallLogM = 11;   // rings with M <= 2048 mix the power-of-two and Bluestein paths in one class per work length
+  constexpr int kTinyLogM = 8;     // ... and everything up to M = 256 shares one launch
   std::vector<std::vector<int>> members;
   std::vector<Key> keys;
   int maxLogM = 1;
@@ -945,7 +946,9 @@ void fft_tables_create(ShtPlan *p)
     int pow2 = !rp_blu[rp];
     int logM = rp_logM[rp];
     maxLogM = std::max(maxLogM, logM);
-    Key key = (logM <= kSmallLogM) ? Key{kSmallLogM, 2} : Key{logM, !pow2};
+    // small rings are latency bound one by one: classes of their own (by work length) keep their shared-memory footprint and
+    // CTA size small, so that many of them share an SM
+    Key key = (logM <= kTinyLogM) ? Key{kTinyLogM, 2} : (logM <= kSmallLogM) ? Key{logM, 2} : Key{logM, !pow2};
     size_t k = 0;
     for (; k < keys.size(); ++k) if (keys[k].logM == key.logM && keys[k].blu == key.blu) break;
     if (k == keys.size()) { keys.push_back(key); members.emplace_back(); }

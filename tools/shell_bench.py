@@ -7,11 +7,12 @@ import calclens_b200 as clb
 from calclens_b200 import _lib
 
 order, lmax = int(sys.argv[1]), int(sys.argv[2])
-ana2 = [8]; syn2 = [4]; rows = [0]; reps = 3
+ana2 = [8]; syn2 = [4]; rows = [0]; reps = 3; pipes = [1]
 for a in sys.argv[3:]:
     if a.startswith("ana2="): ana2 = [int(x) for x in a[5:].split(",")]
     elif a.startswith("syn2="): syn2 = [int(x) for x in a[5:].split(",")]
     elif a.startswith("rows="): rows = [int(x) for x in a[5:].split(",")]
+    elif a.startswith("pipe="): pipes = [int(x) for x in a[5:].split(",")]
     else: reps = int(a)
 L = _lib.load()
 plan = clb.HEALPixSHTPlan(order, lmax)
@@ -34,19 +35,19 @@ def timeit(fn):
     return e0.elapsed_time(e1) / reps
 
 
-for r in rows:
-    L.clb_set_tuning(5, r)
-    t = timeit(lambda: plan.legendre_analysis(g, are, aim, poisson_filter=True))
-    print("analysis  1 shell  rows=%d           %8.3f ms per shell" % (r, t))
-ref = (are[:n].clone(), aim[:n].clone())
-for r in rows:
-    L.clb_set_tuning(5, r)
-    for R in ana2:
-        L.clb_set_tuning(10, R)
-        t = timeit(lambda: plan.legendre_analysis(g, are, aim, poisson_filter=True, nshell=2))
-        print("analysis  2 shells rows=%d R=%d       %8.3f ms per shell   shell 0 identical to one-shell: %s" % (
-            r, R, t / 2, bool(torch.equal(are[:n], ref[0]) and torch.equal(aim[:n], ref[1]))))
-L.clb_set_tuning(5, 0); L.clb_set_tuning(10, 8)
+for pipe in pipes:
+    L.clb_set_tuning(12, 2 * pipe)
+    for r in rows:
+        L.clb_set_tuning(5, r)
+        t = timeit(lambda: plan.legendre_analysis(g, are, aim, poisson_filter=True))
+        print("analysis  1 shell  pipe=%d rows=%d           %8.3f ms per shell" % (pipe, r, t))
+        ref = (are[:n].clone(), aim[:n].clone())
+        for R in ana2:
+            L.clb_set_tuning(10, R)
+            t = timeit(lambda: plan.legendre_analysis(g, are, aim, poisson_filter=True, nshell=2))
+            print("analysis  2 shells pipe=%d rows=%d R=%d       %8.3f ms per shell   shell 0 identical to one-shell: %s" % (
+                pipe, r, R, t / 2, bool(torch.equal(are[:n], ref[0]) and torch.equal(aim[:n], ref[1]))))
+L.clb_set_tuning(5, 0); L.clb_set_tuning(10, 8); L.clb_set_tuning(12, 1)
 plan.legendre_analysis(g, are, aim, poisson_filter=True, nshell=2)
 t = timeit(lambda: plan.legendre_synthesis(are, aim, b))
 print("synthesis 1 shell                    %8.3f ms per shell" % t)
