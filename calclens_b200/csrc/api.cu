@@ -4,7 +4,7 @@
 #include <string.h>
 
 namespace clb {
-extern int g_syn_rings_per_thread, g_ana_rings_per_thread, g_fft_threads_big, g_leg_warps_per_cta, g_fft_force_scratch, g_ana_rows, g_syn2_rings_per_thread, g_ana2_rings_per_thread, g_fft_field_groups, g_fft_debug, g_solver_shells, g_ana_pipeline;
+extern int g_syn_rings_per_thread, g_ana_rings_per_thread, g_fft_threads_big, g_leg_warps_per_cta, g_fft_force_scratch, g_ana_rows, g_syn2_rings_per_thread, g_ana2_rings_per_thread, g_fft_field_groups, g_fft_debug, g_solver_shells, g_ana_pipeline, g_fft_streams;
 
 // safe[c] = AND of mask[d] over every cell d whose centre lies within neighbour_rad of c's centre (c included): a ray whose
 // stencil starts in a "safe" cell cannot touch an undelivered pixel, so the ray kernel skips the per-pixel mask check there
@@ -116,6 +116,7 @@ void clb_set_tuning(int what, int value)
   if (what == 0 && value >= 1 && value <= 4) g_syn_rings_per_thread = value;
   if (what == 4) g_fft_force_scratch = value ? 1 : 0;
   if (what == 5 && value >= 0) g_ana_rows = value;   // partial-sum rows per m of the Legendre analysis (0 = automatic)
+  if (what == 7) g_fft_streams = value ? 1 : 0;
   if (what == 12 && value >= 0 && value <= 2) g_ana_pipeline = value;
   if (what == 11 && (value == 1 || value == 2)) g_solver_shells = value;   // read by clb_solver_create
   if (what == 9 && value >= 1 && value <= 4) g_syn2_rings_per_thread = value;

@@ -11,6 +11,8 @@ void sht_plan_destroy(ShtPlan *p);
 void sht_plan_set_peers(ShtPlan *p, void *const *g_send_ptrs, void *const *b_recv_ptrs, int nshell = 1);
 int launch_ring_analysis(const ShtPlan *p, const float *d_map, double2 *d_g_send, cudaStream_t st);
 int launch_ring_synthesis(const ShtPlan *p, const double2 *d_b_recv, float *const d_maps[6], cudaStream_t st);
+void fft_fork(const ShtPlan *p, cudaStream_t st);   // the ring-FFT class launches up to fft_join may run on parallel streams
+void fft_join(const ShtPlan *p, cudaStream_t st);
 int launch_legendre_analysis(ShtPlan *p, const double2 *d_g_recv, double *d_alm_re, double *d_alm_im, int apply_filter,
                              cudaStream_t st, int nshell = 1);
 int launch_legendre_synthesis(ShtPlan *p, const double *d_alm_re, const double *d_alm_im, double2 *d_b_send, cudaStream_t st,

@@ -28,11 +28,14 @@
 
 namespace clb {
 
+constexpr int kFoldTile = 1024;   // degrees per shared-memory tile of the streamed alias fold (classes of short rings)
+
 struct FftClass {   // one launch group: ring pairs that share a shared-memory footprint
   int logM;          // largest work length in the group, Mmax = 1 << logM
   int bluestein;     // group key only (groups with logM <= kSmallLogM mix both paths)
   int rmax;          // largest r in the group (sizes shared memory)
-  int tail;          // float2 entries behind bufB
+  int tail;          // float2 entries behind bufB (even)
+  int tileT;         // degrees per tile of the streamed alias fold, stored behind the tail (0: class of long rings)
   int count;         // ring pairs in the class (local ones only)
   int *d_rp = nullptr;   // [count] global ring-pair indices
   int threads;
@@ -57,6 +60,11 @@ struct FftTables {
   // rings whose work buffers exceed an SM's shared memory (r > 4095) run from a global scratch buffer
   double2 *d_scratch = nullptr;
   size_t scratch_bytes = 0;
+  // the class launches of a stage are independent: they go round-robin to the caller's stream and three side streams, so that
+  // the CTAs of the next class fill the SMs the tail of the previous one leaves idle (fft_fork / fft_join)
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  int depth = 0, rr = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -638,6 +646,7 @@ struct SynArgs {
   const double2 *phase_all; const long *phase_off;
   int dbg;            // development aid (clb_set_tuning(8, bits)): 1 no b loads, 2 no transforms, 4 no stores -- wrong results, phase costs
   int nfg;             // field groups per ring (1: all six in one CTA; 3: {0,3},{1,5},{2,4})
+  int tail, tileT;     // float2 entries of the tail buffer; degrees per tile of the streamed alias fold behind it (0: none)
 };
 
 
@@ -700,6 +709,57 @@ __device__ __forceinline__ void ring_synthesis_body(const SynArgs &A, double2 *s
   for (int fi = 0; fi < nf; ++fi) {
     const int field = (A.nfg == 1) ? fi : (fi == 0 ? group : (group == 0 ? 3 : group == 1 ? 5 : 4));
     const BAddr B{b_recv, A.m_boff, A.m_bstr, rpl * 6 + field, hemi};
+    // S1 for short rings (n <= lmax, classes that carry a tile buffer): a bin of a ring with n pixels collects ~2 lmax / n
+    // values of m -- thousands for the rings next to the poles -- and the reference adds them in ascending m with one float
+    // rounding each (alm2allmaps_transpose_mpi.c:836-881), a serial chain.  Gathering them one memory round trip at a time
+    // made the ring of FOUR pixels the critical path of the whole stage (3.5 ms, whatever the number of GPUs); instead the
+    // CTA streams the ring's b_m (contiguous in m) through a shared-memory tile and every bin walks its own terms there.
+    if (deep && A.tileT > 0 && !(A.dbg & 1)) {
+      double2 *tile = reinterpret_cast<double2 *>(tailbuf + A.tail);
+      const int T = A.tileT;
+      for (int k = threadIdx.x; k <= 2 * r; k += blockDim.x) Y[k] = make_float2(0.f, 0.f);
+      for (int m0 = 0; m0 <= lmax; m0 += T) {
+        const int mend = min(m0 + T, lmax + 1);
+        for (int t = threadIdx.x; m0 + t < mend; t += blockDim.x) tile[t] = B(m0 + t);
+        __syncthreads();
+        for (int k = threadIdx.x; k <= 2 * r; k += blockDim.x) {
+          float2 y = Y[k];
+          auto apply = [&](int t, double2 b) {                          // term t of the bin: see fold_bin
+            const int wraps = (t + 1) >> 1;
+            const double sk = (shifted && (wraps & 1)) ? -1.0 : 1.0;
+            y.x = __double2float_rn(__dadd_rn((double)y.x, __dmul_rn(b.x, sk)));
+            if (t & 1) y.y = __double2float_rn(__dsub_rn((double)y.y, __dmul_rn(b.y, sk)));
+            else y.y = __double2float_rn(__dadd_rn((double)y.y, __dmul_rn(b.y, sk)));
+          };
+          if (k == 0) {   // m = 0 once, then every multiple of n twice: its positive term, then its negative one
+            for (long j = (m0 + n - 1) / n; j * n < mend; ++j) {
+              const double2 b = tile[j * n - m0];
+              if (j == 0) apply(0, b);
+              else { apply((int)(2 * j), b); apply((int)(2 * j - 1), b); }
+            }
+          } else {
+            // terms below m0 are done: P positive ones (m = j n + k < m0) and Q negative ones (m = j n - k < m0, j >= 1)
+            const int P = (m0 > k) ? (m0 - k + n - 1) / n : 0;
+            const int Q = (m0 + k - 1) / n;
+            for (int t = P + Q;; ++t) {
+              const long mm = (long)((t + 1) >> 1) * n + ((t & 1) ? -k : k);
+              if (mm >= mend) break;
+              apply(t, tile[mm - m0]);
+            }
+          }
+          Y[k] = y;
+        }
+        __syncthreads();
+      }
+      if (shifted)
+        for (int k = threadIdx.x; k <= 2 * r; k += blockDim.x) {        // [healpix_shtrans.c:186-197]
+          const double2 ph = __ldg(&PT[k]);
+          const float2 y = Y[k];
+          const double t0 = (double)y.x, t1 = (double)y.y;
+          Y[k] = make_float2(__double2float_rn(__dsub_rn(__dmul_rn(t0, ph.x), __dmul_rn(t1, ph.y))),
+                             __double2float_rn(__dadd_rn(__dmul_rn(t1, ph.x), __dmul_rn(t0, ph.y))));
+        }
+    } else {
     // S1: folded, phased float bins.  U bins per thread and trip, the global loads of both terms of all U bins (and of
     // the phase table) issued together: this loop is otherwise bound by one exposed memory round trip per bin
     constexpr int U = 4;
@@ -740,6 +800,7 @@ __device__ __forceinline__ void ring_synthesis_body(const SynArgs &A, double2 *s
         }
         Y[k] = y;
       }
+    }
     }
     __syncthreads();
     // c2r samples 0, n/4, n/2, 3n/4 have rational twiddles: exact sums of the float bins (same reason and same
@@ -877,6 +938,33 @@ int g_fft_field_groups = 0;     // clb_set_tuning(6, 0|1|3): CTAs per ring and h
 int g_fft_debug = 0;
 int g_fft_force_scratch = 0;    // clb_set_tuning(4, 1): run every ring FFT from global scratch (tests the large-ring path at small Nside)
 int g_fft_threads_big = 512;   // threads per CTA for work lengths >= 4096 (clb_set_tuning(2, .))
+int g_fft_streams = 1;         // clb_set_tuning(7, 0|1): class launches of a stage on parallel streams
+
+// Everything enqueued between fft_fork and fft_join through class_stream() runs after what `st` holds at the fork and before
+// what `st` receives after the join.  Calls nest (the solver forks once around the launches of both shells of a pass).
+void fft_fork(const ShtPlan *p, cudaStream_t st)
+{
+  FftTables *t = p->fft;
+  if (t->depth++ > 0 || !g_fft_streams) return;
+  t->rr = 0;
+  CLB_CUDA_CHECK(cudaEventRecord(t->ev_fork, st));
+  for (int i = 0; i < 3; ++i) CLB_CUDA_CHECK(cudaStreamWaitEvent(t->aux[i], t->ev_fork, 0));
+}
+void fft_join(const ShtPlan *p, cudaStream_t st)
+{
+  FftTables *t = p->fft;
+  if (--t->depth > 0 || !g_fft_streams) return;
+  for (int i = 0; i < 3; ++i) {
+    CLB_CUDA_CHECK(cudaEventRecord(t->ev_join[i], t->aux[i]));
+    CLB_CUDA_CHECK(cudaStreamWaitEvent(st, t->ev_join[i], 0));
+  }
+}
+static cudaStream_t class_stream(FftTables *t, cudaStream_t st)
+{
+  if (!g_fft_streams) return st;
+  const int i = t->rr++ & 3;
+  return i == 0 ? st : t->aux[i - 1];
+}
 
 template <typename T>
 static T *to_dev(const std::vector<T> &v)
@@ -913,6 +1001,8 @@ void fft_tables_destroy(ShtPlan *p)
   FftTables *t = p->fft;
   if (!t) return;
   for (auto &c : t->classes) cudaFree(c.d_rp);
+  for (int i = 0; i < 3; ++i) { if (t->aux[i]) cudaStreamDestroy(t->aux[i]); if (t->ev_join[i]) cudaEventDestroy(t->ev_join[i]); }
+  if (t->ev_fork) cudaEventDestroy(t->ev_fork);
   cudaFree(t->d_tw); cudaFree(t->d_chirp_off); cudaFree(t->d_bhat_off); cudaFree(t->d_chirp); cudaFree(t->d_bhat);
   cudaFree(t->d_phase); cudaFree(t->d_phase_off); cudaFree(t->d_rp_logM); cudaFree(t->d_rp_blu); cudaFree(t->d_scratch);
   delete t;
@@ -923,6 +1013,11 @@ void fft_tables_create(ShtPlan *p)
 {
   FftTables *t = new FftTables();
   p->fft = t;
+  CLB_CUDA_CHECK(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < 3; ++i) {
+    CLB_CUDA_CHECK(cudaStreamCreateWithFlags(&t->aux[i], cudaStreamNonBlocking));
+    CLB_CUDA_CHECK(cudaEventCreateWithFlags(&t->ev_join[i], cudaEventDisableTiming));
+  }
   const long nside = p->nside;
   // classes over the local ring pairs
   struct Key { int logM, blu; };
@@ -1031,8 +1126,10 @@ void fft_tables_create(ShtPlan *p)
     const long M = 1L << c.logM;
     c.threads = (int)std::min<long>(256, std::max<long>(32, M / 4));
     if (M >= 4096) c.threads = g_fft_threads_big;
+    c.tail += c.tail & 1;   // the tile behind it holds double2
+    c.tileT = (c.logM <= 10) ? kFoldTile : 0;
     c.smem_ana = sizeof(double2) * (M + c.rmax);
-    c.smem_syn = sizeof(double2) * (M + c.rmax + 1) + sizeof(float2) * c.tail;
+    c.smem_syn = sizeof(double2) * (M + c.rmax + 1) + sizeof(float2) * c.tail + sizeof(double2) * c.tileT;
     max_ana = std::max(max_ana, c.smem_ana); max_syn = std::max(max_syn, c.smem_syn);
     // longest rings first: CTAs are dispatched in order, so the short ones fill the tail of the launch
     std::stable_sort(members[k].begin(), members[k].end(), [&](int x, int y) { return p->h_nphi[x] > p->h_nphi[y]; });
@@ -1040,6 +1137,10 @@ void fft_tables_create(ShtPlan *p)
     CLB_CUDA_CHECK(cudaMemcpy(c.d_rp, members[k].data(), sizeof(int) * c.count, cudaMemcpyHostToDevice));
     t->classes.push_back(c);
   }
+  // most work first: the short classes then fill the gaps the long ones leave (fft_fork)
+  std::stable_sort(t->classes.begin(), t->classes.end(), [](const FftClass &a, const FftClass &b) {
+    return ((long)a.count << a.logM) > ((long)b.count << b.logM);
+  });
   // classes that do not fit an SM's shared memory use the persistent global-scratch kernels instead
   max_ana = max_syn = 0;
   for (const auto &c : t->classes) {
@@ -1066,7 +1167,10 @@ int launch_ring_analysis(const ShtPlan *p, const float *d_map, double2 *d_g_send
 {
   FftTables *t = p->fft;
   int launches = 0;
+  fft_fork(p, st);
+  const cudaStream_t st0 = st;
   for (const auto &c : t->classes) {
+    st = class_stream(t, st0);
     AnaArgs A{d_map, d_g_send, geom_of(p), c.d_rp, plan_rp_to_local(p), p->d_m_goff, (int)p->lmax, t->d_rp_logM, t->d_rp_blu,
               1 << c.logM, t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat, t->d_tw, t->logTW, t->d_phase, t->d_phase_off};
     if (c.smem_ana <= kMaxSmem && !g_fft_force_scratch) {
@@ -1075,11 +1179,12 @@ int launch_ring_analysis(const ShtPlan *p, const float *d_map, double2 *d_g_send
       const int nwork = 2 * c.count, ctas = std::min(nwork, scratch_ctas());
       const long stride = (long)((c.smem_ana + 255) / 256) * 16;   // double2 elements, 256-byte aligned slices
       double2 *scr = fft_scratch(t, (size_t)ctas * stride * sizeof(double2));
-      ring_analysis_scratch_kernel<<<ctas, 512, 0, st>>>(A, scr, stride, nwork);
+      ring_analysis_scratch_kernel<<<ctas, 512, 0, st0>>>(A, scr, stride, nwork);   // (one scratch buffer: these launches stay in line)
     }
     ++launches;
   }
   CLB_CUDA_CHECK(cudaGetLastError());
+  fft_join(p, st0);
   return launches;
 }
 
@@ -1089,10 +1194,13 @@ int launch_ring_synthesis(const ShtPlan *p, const double2 *d_b_recv, float *cons
   MapPtrs mp;
   for (int k = 0; k < 6; ++k) mp.p[k] = d_maps[k];
   int launches = 0;
+  fft_fork(p, st);
+  const cudaStream_t st0 = st;
   for (const auto &c : t->classes) {
+    st = class_stream(t, st0);
     SynArgs A{d_b_recv, mp, geom_of(p), c.d_rp, plan_rp_to_local(p), p->d_m_boff, p->d_m_bstr, (int)p->lmax, t->d_rp_logM,
               t->d_rp_blu, 1 << c.logM, c.rmax, t->d_chirp_off, t->d_bhat_off, t->d_chirp, t->d_bhat, t->d_tw, t->logTW,
-              t->d_phase, t->d_phase_off, g_fft_debug, 1};
+              t->d_phase, t->d_phase_off, g_fft_debug, 1, c.tail, c.tileT};
     A.nfg = g_fft_field_groups ? g_fft_field_groups : 3;
     if (c.smem_syn <= kMaxSmem && !g_fft_force_scratch) {
       dim3 grid(2 * c.count, A.nfg);
@@ -1101,11 +1209,12 @@ int launch_ring_synthesis(const ShtPlan *p, const double2 *d_b_recv, float *cons
       const int nwork = 2 * c.count, ctas = std::min(nwork * A.nfg, scratch_ctas());
       const long stride = (long)((c.smem_syn + 255) / 256) * 16;
       double2 *scr = fft_scratch(t, (size_t)ctas * stride * sizeof(double2));
-      ring_synthesis_scratch_kernel<<<ctas, 512, 0, st>>>(A, scr, stride, nwork);
+      ring_synthesis_scratch_kernel<<<ctas, 512, 0, st0>>>(A, scr, stride, nwork);   // (one scratch buffer: these launches stay in line)
     }
     ++launches;
   }
   CLB_CUDA_CHECK(cudaGetLastError());
+  fft_join(p, st0);
   return launches;
 }
 

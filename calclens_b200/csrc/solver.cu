@@ -276,13 +276,14 @@ static void solve(Solver *s, const float *const dens[2], int nshell, const int d
   for (int q = 0; q < nshell; ++q)
     for (int k = 0; k < 6; ++k) mp[q][k] = s->maps + ((size_t)q * 6 + k) * s->npix;
   if (s->fused) stream_barrier(s, st);          // every rank is done with the previous plane's g, b and maps
-  for (int q = 0; q < nshell; ++q) {
-    LAUNCHED(s) launch_ring_analysis(p, dens[q], s->g_send + (size_t)q * p->g_send_total, st);
+  fft_fork(p, st);                              // the class launches of both shells share the parallel streams
+  for (int q = 0; q < nshell; ++q) LAUNCHED(s) launch_ring_analysis(p, dens[q], s->g_send + (size_t)q * p->g_send_total, st);
+  fft_join(p, st);
+  for (int q = 0; q < nshell; ++q)
     if (dens_buf && dens_buf[q] >= 0) {         // the density buffer is free again: a prefetch may overwrite it
       CLB_CUDA_CHECK(cudaEventRecord(s->dens_free[dens_buf[q]], st));
       s->dens_free_valid[dens_buf[q]] = true;
     }
-  }
   mark(s, 2, st);
   if (s->fused) stream_barrier(s, st);
   mark(s, 3, st);
@@ -290,7 +291,9 @@ static void solve(Solver *s, const float *const dens[2], int nshell, const int d
   LAUNCHED(s) launch_legendre_synthesis(p, s->alm_re, s->alm_im, s->fused ? nullptr : s->b_send, st, nshell); mark(s, 5, st);
   if (s->fused) stream_barrier(s, st);
   mark(s, 6, st);
+  fft_fork(p, st);
   for (int q = 0; q < nshell; ++q) LAUNCHED(s) launch_ring_synthesis(p, s->b_recv + (size_t)q * p->b_recv_total, mp[q], st);
+  fft_join(p, st);
   mark(s, 7, st);
   if (s->fused) {
     for (int q = 0; q < nshell; ++q) {
