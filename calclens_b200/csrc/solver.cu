@@ -110,6 +110,7 @@ struct Solver {
   };
   PlaneKey staged[2];                // density buffer k holds this prefetched plane (src == nullptr: nothing staged)
   float *h_stage[2] = {nullptr, nullptr};   // pinned staging for pageable host maps
+  float *d_raw[2] = {nullptr, nullptr};     // single rank: a host map crosses PCIe whole, on a copy engine (no SM slots), then is scaled
   PlaneKey next[2];                  // planes registered by clb_solver_set_next: prefetched behind the current step's kernels
   int n_next = 0;
   // two planes per SHT pass: the partner registered by clb_solver_set_pair is solved together with
@@ -262,6 +263,19 @@ static const float *device_view(Solver *s, const float *src, int slot, cudaStrea
 static void load_density(Solver *s, const float *src, int k, float premul, float densmul, float backdens, cudaStream_t st)
 {
   const float *v = device_view(s, src, k, st);
+  if (s->nranks == 1) {
+    // One rank needs every ring: a plain asynchronous copy moves the map at full PCIe rate on a copy engine while the SMs
+    // compute (the kernel that reads pinned host memory directly holds SM slots for the ~15 ms the transfer takes; with
+    // several ranks it is still the better choice because every rank then moves only its own rings).
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, v) != cudaSuccess) { cudaGetLastError(); attr.type = cudaMemoryTypeUnregistered; }
+    if (attr.type == cudaMemoryTypeHost) {
+      if (!s->d_raw[k]) CLB_CUDA_CHECK(cudaMalloc(&s->d_raw[k], sizeof(float) * s->npix));
+      const void *hsrc = attr.hostPointer ? attr.hostPointer : (const void *)v;   // (the pinned staging copy for pageable maps)
+      CLB_CUDA_CHECK(cudaMemcpyAsync(s->d_raw[k], hsrc, sizeof(float) * s->npix, cudaMemcpyHostToDevice, st));
+      v = s->d_raw[k];
+    }
+  }
   LAUNCHED(s) launch_load_density(s->plan, v, s->dens[k], premul, densmul, backdens, st);
 }
 
@@ -453,7 +467,7 @@ void clb_solver_destroy(clb_solver *h)
   else if (s->nranks == 1) { cudaFree(s->g_send); cudaFree(s->b_send); cudaFree(s->maps); }
   cudaFree(s->alm_re); cudaFree(s->alm_im); cudaFree(s->dens[0]); cudaFree(s->dens[1]); cudaFree(s->rays);
   cudaFree(s->d_sum6); cudaFree(s->d_err); cudaFree(s->d_need);
-  cudaFreeHost(s->h_sum6); cudaFreeHost(s->h_stage[0]); cudaFreeHost(s->h_stage[1]);
+  cudaFreeHost(s->h_sum6); cudaFreeHost(s->h_stage[0]); cudaFreeHost(s->h_stage[1]); cudaFree(s->d_raw[0]); cudaFree(s->d_raw[1]);
   for (int k = 0; k < 2; ++k) { if (s->dens_ready[k]) cudaEventDestroy(s->dens_ready[k]); if (s->dens_free[k]) cudaEventDestroy(s->dens_free[k]); }
   if (s->ev_tmp) cudaEventDestroy(s->ev_tmp);
   for (int k = 0; k <= kStages; ++k) if (s->ev[k]) cudaEventDestroy(s->ev[k]);
