@@ -326,12 +326,17 @@ def measure(a, L, poisson, torch, dist, world, rank, local_rank, group, order, r
     stage_ms = {k: 0.0 for k in STAGES}
     solver.set_timing(True)
     base = warmup + steps
-    for _ in run_planes(base, steps, dev_maps):
-        for k, v in zip(STAGES, solver.stage_ms()):
+    pass_ms = {1: [], 2: []}     # legendre synthesis launches by shells per pass (the roofline kernel), ms per launch
+    for i, _ in enumerate(run_planes(base, steps, dev_maps)):
+        st = solver.stage_ms()
+        for k, v in zip(STAGES, st):
             stage_ms[k] += v / steps
+        if st[4] > 0.0:     # (the second plane of a pair records no SHT stage)
+            paired = a.shells == 2 and i % 2 == 0 and i + 1 < steps
+            pass_ms[2 if paired else 1].append(st[4])
     solver.set_timing(False)
     base += steps
-    out = {"ms_per_step": ms_per_step, "stage_ms": stage_ms, "launches": launches, "clocks": clocks, "setup_s": t_setup,
+    out = {"ms_per_step": ms_per_step, "stage_ms": stage_ms, "pass_ms": pass_ms, "launches": launches, "clocks": clocks, "setup_s": t_setup,
            "npix": solver.npix, "fused": solver.fused, "host_barriers": getattr(solver, "host_barriers", False)}
     if with_e2e:
         # ---- end to end through the public API with host buffers: H2D of every plane's map (prefetched behind the previous
@@ -493,24 +498,30 @@ def main():
             hbm_peak, hbm_src = float(mp_["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
         except Exception:
             pass
-        ach_syn = wm["flops_synthesis"] / world / (stage_ms["legendre_synthesis"] * 1e-3) / 1e12
+        # the dominant kernel: legendre_synthesis_kernel.  With two shells per pass one launch does two planes' worth of
+        # algorithmic work; its duration is the CUDA-event time of that stage in the steps that ran a two-shell pass
+        nsh = 2 if r["pass_ms"][2] else 1
+        launch_ms = float(np.mean(r["pass_ms"][nsh])) if r["pass_ms"][nsh] else stage_ms["legendre_synthesis"]
+        flops_launch = nsh * wm["flops_synthesis"] / world
+        ach_syn = flops_launch / (launch_ms * 1e-3) / 1e12
         traffic = None
-        for tf in ("r02_traffic.json", "r01_traffic.json"):
-            try:
-                tj = json.load(open(os.path.join(HERE, "profiles", tf)))
-                if world == 1 and a.nside == 4096 and a.lmax == 8192:
-                    traffic = tj.get("legendre_synthesis", {}).get("dram_bytes_per_launch")
-                    break
-            except Exception:
-                pass
-        roofline = {"kernel": "legendre_synthesis_kernel (dominant)", "bound": "fp64", "achieved": ach_syn, "peak": fp64_peak, "unit": "TFLOP/s",
-                    "frac": ach_syn / fp64_peak, "traffic": traffic,
-                    "peak_source": fp64_src, "algorithmic_flops_per_launch": wm["flops_synthesis"] / world,
+        try:
+            tj = json.load(open(os.path.join(HERE, "profiles", "r02_traffic.json")))
+            key = "legendre_synthesis_%dshell" % nsh
+            if world == 1 and a.nside == 4096 and a.lmax == 8192 and key in tj:
+                traffic = tj[key].get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        roofline = {"kernel": "legendre_synthesis_kernel<R,%d> (dominant; %d lens plane%s per launch)" % (nsh, nsh, "s" if nsh > 1 else ""),
+                    "bound": "fp64", "achieved": ach_syn, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": ach_syn / fp64_peak, "traffic": traffic, "launch_ms": launch_ms,
+                    "peak_source": fp64_src, "algorithmic_flops_per_launch": flops_launch,
                     "note": "FP64 FMA-pipe roofline (not tensor: B200's DMMA rate equals its DFMA rate and the recurrence is serial per ring). "
-                            "algorithmic = 16 flop per (m, ring pair, l) triple of the reference's lmin cut: 2-instruction recurrence + three "
-                            "complex sums (DESIGN.md section 4); with SURVEY.md 8d's four-sum count of 20 the same time gives %.2f TFLOP/s. "
-                            "traffic = dram bytes of one launch from profiles/ (ncu --set full)" % (
-                                wm["flops_synthesis_survey"] / world / (stage_ms["legendre_synthesis"] * 1e-3) / 1e12)}
+                            "algorithmic = 16 flop per (m, ring pair, l) triple of the reference's lmin cut and shell: 2-instruction recurrence + three "
+                            "complex sums (DESIGN.md section 4) -- a two-shell pass EXECUTES 14 instead of 16 FP64 instructions per two triple-shells, "
+                            "so a fraction close to 1 is the amortised recurrence, not a faster pipe; with SURVEY.md 8d's four-sum count of 20 the "
+                            "same time gives %.2f TFLOP/s. traffic = dram bytes of one launch (ncu, profiles/r02_traffic.json)" % (
+                                nsh * wm["flops_synthesis_survey"] / world / (launch_ms * 1e-3) / 1e12)}
         stages = {
             "legendre_analysis": {"bound": "fp64", "achieved": wm["flops_analysis"] / world / (stage_ms["legendre_analysis"] * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s"},
             "fft_analysis": {"bound": "hbm", "achieved": wm["bytes_fft_analysis"] / world / (stage_ms["fft_analysis"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"},

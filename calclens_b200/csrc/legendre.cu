@@ -519,6 +519,13 @@ int g_ana_rows = 0;               // clb_set_tuning(5, n): partial-sum rows per 
 int g_syn2_rings_per_thread = 3;  // clb_set_tuning(9, .): rings per thread of the two-shell synthesis kernel (3: 244 registers, no spills)
 int g_ana2_rings_per_thread = 8;  // clb_set_tuning(10, .): rings per thread of the two-shell analysis kernel
 
+static int cur_device()
+{
+  int dev = 0;
+  CLB_CUDA_CHECK(cudaGetDevice(&dev));
+  return dev;
+}
+
 int g_ana_pipeline = 1;           // clb_set_tuning(12, 0|1|2): warp sum of a block overlapped with the next block's FP64 work: never,
                                   // in one-shell passes only (measured: 71.1 -> 70.1 ms there, 56.7 -> 61.0 ms with two shells at the
                                   // 255-register cap), always
@@ -533,11 +540,13 @@ static void launch_ana_t(const ShtPlan *p, const double2 *g_recv, const double2 
       (int)p->lmax, rows, nchunk
   auto smem_of = [&](int bufs) { return sizeof(double) * (size_t)warps * (2 * kAnaTile + bufs * 16 * 33 + 2 * R * 32); };
   if (g_ana_pipeline == 2 || (g_ana_pipeline == 1 && NS == 1)) {
-    static bool attr = false;   // (per instantiation)
+    static bool done[64] = {};   // (per instantiation and device: the attribute belongs to the function in one context)
+    bool &attr = done[cur_device() & 63];
     if (!attr) { CLB_CUDA_CHECK(cudaFuncSetAttribute(legendre_analysis_kernel<R, NS, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(2) * 4 / warps)); attr = true; }
     legendre_analysis_kernel<R, NS, NB, true><<<grid, 32 * warps, smem_of(2), st>>>(CLB_ANA_ARGS);
   } else {
-    static bool attr = false;
+    static bool done[64] = {};
+    bool &attr = done[cur_device() & 63];
     if (!attr) { CLB_CUDA_CHECK(cudaFuncSetAttribute(legendre_analysis_kernel<R, NS, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(1) * 4 / warps)); attr = true; }
     legendre_analysis_kernel<R, NS, NB, false><<<grid, 32 * warps, smem_of(1), st>>>(CLB_ANA_ARGS);
   }

@@ -1094,7 +1094,10 @@ void fft_tables_create(ShtPlan *p)
     CLB_CUDA_CHECK(cudaMemcpy(d_rlist, need_r.data(), sizeof(int) * need_r.size(), cudaMemcpyHostToDevice));
     size_t smem = sizeof(double2) << maxLogM;
     if (smem <= kMaxSmem && !g_fft_force_scratch) {
-      static size_t attr_blu = 0;
+      static size_t attr_blu_dev[64] = {};   // per device: the attribute belongs to the function in one context
+      int dev = 0;
+      CLB_CUDA_CHECK(cudaGetDevice(&dev));
+      size_t &attr_blu = attr_blu_dev[dev & 63];
       if (smem > attr_blu) {
         CLB_CUDA_CHECK(cudaFuncSetAttribute(bluestein_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_blu = smem;
@@ -1147,9 +1150,12 @@ void fft_tables_create(ShtPlan *p)
     if (c.smem_ana <= kMaxSmem) max_ana = std::max(max_ana, c.smem_ana);
     if (c.smem_syn <= kMaxSmem) max_syn = std::max(max_syn, c.smem_syn);
   }
-  // the attribute is per function, not per plan: several plans may be alive (one per emulated rank, or one per
-  // resolution), so it is only ever raised
-  static size_t attr_ana = 0, attr_syn = 0;
+  // the attribute is per function (and device), not per plan: several plans may be alive (one per emulated rank, or one
+  // per resolution), so it is only ever raised
+  static size_t attr_ana_dev[64] = {}, attr_syn_dev[64] = {};
+  int cur_dev = 0;
+  CLB_CUDA_CHECK(cudaGetDevice(&cur_dev));
+  size_t &attr_ana = attr_ana_dev[cur_dev & 63], &attr_syn = attr_syn_dev[cur_dev & 63];
   if (max_ana > attr_ana) {
     CLB_CUDA_CHECK(cudaFuncSetAttribute(ring_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_ana));
     attr_ana = max_ana;

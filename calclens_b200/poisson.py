@@ -5,8 +5,10 @@ the plane's ``rayprop_sphere`` calls (raytrace.c:256-269), on one GPU or sharded
 Sharding follows the reference: the map side of the SHT is split by ring pairs, the alm side
 by m, joined by one transpose per direction (map2alm_transpose_mpi.c:339-381, alm2allmaps_transpose_mpi.c:656-724);
 rays are split into contiguous NEST ranges, i.e. compact sky domains (cf. loadbalance.c:151-181).  Instead of the
-reference's ring->domain shuffle with halo cells (map_shuffle.c) every rank receives the six full derivative maps, so
-rays never miss a map cell however far they have been deflected.
+reference's ring->domain shuffle with halo cells (map_shuffle.c) every rank's rings are stored into the map buffers of
+the ranks whose ray domain + halo (``halo_deg``, default 1 degree) can reach them; with a halo a rank's ``maps`` are
+therefore valid on its own rings and its halo region only (``halo_deg=0`` broadcasts full maps), and the ray kernel
+raises an error if a ray's stencil leaves that region.
 
 The driver itself lives below the C ABI (``clb_solver_*``, csrc/solver.cu): this class is a thin caller of it, so a C
 host (CALCLENS through shim/calclens_b200_shim.c) reaches exactly the same code.  Two exchange back ends:
