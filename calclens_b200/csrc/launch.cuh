@@ -27,7 +27,8 @@ int launch_deposit_ngp(const float *d_pos, const float *d_mass, long nparts, lon
 void launch_healpix_index(int what, long order, long n, const long *in, const double *th, const double *ph, long *out, cudaStream_t st);
 void launch_healpix_interpol(long order, long n, const double *vec, long *pix, double *wgt, int use_table, cudaStream_t st);
 int launch_maps_broadcast(const ShtPlan *p, float *const local_maps[6], float *const *peer_maps,
-                          const unsigned char *d_need, long coarse_order, cudaStream_t st);
+                          const unsigned char *d_need, long coarse_order, cudaStream_t st, const unsigned char *d_gmask = nullptr);
+int launch_group_masks(const ShtPlan *p, const unsigned char *d_need, long coarse_order, unsigned char *d_gmask, cudaStream_t st);
 int launch_load_density(const ShtPlan *p, const float *src, float *dst, float premul, float densmul, float backdens,
                         cudaStream_t st);
 void domain_masks(long ray_order, int nranks, long coarse_order, double margin_rad, unsigned char *mask);

@@ -1269,9 +1269,17 @@ int launch_load_density(const ShtPlan *p, const float *src, float *dst, float pr
 struct PeerMaps { float *p[8][6]; };
 // need[c] (optional): bit q set when rank q's ray domain, grown by the halo margin, touches coarse NEST cell c
 // (clb_domain_masks); a group of four pixels goes only to the ranks whose bit is set for its cell(s).
+// Four consecutive ring pixels can touch up to four coarse cells (corner cuts): OR over all of them.
+__device__ __forceinline__ unsigned group_need(const unsigned char *__restrict__ need, long pix, long order, int coarse_shift)
+{
+  return need[ring2nest(pix, order) >> coarse_shift] | need[ring2nest(pix + 1, order) >> coarse_shift] |
+         need[ring2nest(pix + 2, order) >> coarse_shift] | need[ring2nest(pix + 3, order) >> coarse_shift];
+}
+// gmask[pix / 4] (optional): the same per group of four pixels, tabulated once (the four ring -> nest conversions per group
+// were most of this kernel's time)
 __global__ void ring_broadcast_kernel(MapPtrs local, PeerMaps peers, int nranks, int rank, RingGeomDev geo,
-                                      const int *__restrict__ rp_loc, const unsigned char *__restrict__ need, long order,
-                                      int coarse_shift)
+                                      const int *__restrict__ rp_loc, const unsigned char *__restrict__ need,
+                                      const unsigned char *__restrict__ gmask, long order, int coarse_shift)
 {
   const int rp = rp_loc[blockIdx.x >> 1];
   const int hemi = blockIdx.x & 1;
@@ -1280,12 +1288,8 @@ __global__ void ring_broadcast_kernel(MapPtrs local, PeerMaps peers, int nranks,
   const int n4 = geo.nphi[rp] >> 2;
   for (int i = threadIdx.x; i < n4; i += blockDim.x) {
     unsigned m = 0xffu;
-    if (need) {
-      const long pix = start + 4L * i;
-      // four consecutive ring pixels can touch up to four coarse cells (corner cuts): OR over all of them
-      m = need[ring2nest(pix, order) >> coarse_shift] | need[ring2nest(pix + 1, order) >> coarse_shift] |
-          need[ring2nest(pix + 2, order) >> coarse_shift] | need[ring2nest(pix + 3, order) >> coarse_shift];
-    }
+    if (gmask) m = gmask[(start >> 2) + i];      // (every ring starts at a multiple of four)
+    else if (need) m = group_need(need, start + 4L * i, order, coarse_shift);
     m &= ~(1u << rank);
     if (!m) continue;
 #pragma unroll
@@ -1296,9 +1300,27 @@ __global__ void ring_broadcast_kernel(MapPtrs local, PeerMaps peers, int nranks,
     }
   }
 }
+// the table for this rank's rings (entries of other rings stay untouched)
+__global__ void group_mask_kernel(RingGeomDev geo, const int *__restrict__ rp_loc, const unsigned char *__restrict__ need,
+                                  long order, int coarse_shift, unsigned char *__restrict__ gmask)
+{
+  const int rp = rp_loc[blockIdx.x >> 1];
+  const int hemi = blockIdx.x & 1;
+  const long start = hemi ? geo.startS[rp] : geo.startN[rp];
+  if (start < 0) return;
+  const int n4 = geo.nphi[rp] >> 2;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) gmask[(start >> 2) + i] = (unsigned char)group_need(need, start + 4L * i, order, coarse_shift);
+}
+int launch_group_masks(const ShtPlan *p, const unsigned char *d_need, long coarse_order, unsigned char *d_gmask, cudaStream_t st)
+{
+  if (p->nrp_loc == 0) return 0;
+  group_mask_kernel<<<2 * p->nrp_loc, 256, 0, st>>>(geom_of(p), p->d_rp_loc, d_need, p->order, (int)(2 * (p->order - coarse_order)), d_gmask);
+  CLB_CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
 
 int launch_maps_broadcast(const ShtPlan *p, float *const local_maps[6], float *const *peer_maps,
-                          const unsigned char *d_need, long coarse_order, cudaStream_t st)
+                          const unsigned char *d_need, long coarse_order, cudaStream_t st, const unsigned char *d_gmask)
 {
   if (p->nranks <= 1 || p->nrp_loc == 0) return 0;
   if (p->nranks > 8) { fprintf(stderr, "calclens_b200: map broadcast supports up to 8 ranks per node\n"); abort(); }
@@ -1306,8 +1328,8 @@ int launch_maps_broadcast(const ShtPlan *p, float *const local_maps[6], float *c
   for (int k = 0; k < 6; ++k) loc.p[k] = local_maps[k];
   for (int q = 0; q < 8; ++q)
     for (int k = 0; k < 6; ++k) peers.p[q][k] = (q < p->nranks) ? peer_maps[q * 6 + k] : nullptr;
-  if (d_need && coarse_order > p->order) d_need = nullptr;
-  ring_broadcast_kernel<<<2 * p->nrp_loc, 256, 0, st>>>(loc, peers, p->nranks, p->rank, geom_of(p), p->d_rp_loc, d_need,
+  if (d_need && coarse_order > p->order) { d_need = nullptr; d_gmask = nullptr; }
+  ring_broadcast_kernel<<<2 * p->nrp_loc, 256, 0, st>>>(loc, peers, p->nranks, p->rank, geom_of(p), p->d_rp_loc, d_need, d_gmask,
                                                         p->order, (int)(2 * (p->order - coarse_order)));
   CLB_CUDA_CHECK(cudaGetLastError());
   return 1;

@@ -91,6 +91,7 @@ struct Solver {
   double *d_sum6 = nullptr;
   int *d_err = nullptr;
   unsigned char *d_need = nullptr;
+  unsigned char *d_gmask = nullptr;    // d_need evaluated per group of four ring pixels of this rank's rings (map broadcast)
   double need_fraction = 1.0, halo_deg = 0.0;
   double *h_sum6 = nullptr;   // pinned: 6 sums + err word
   // peers
@@ -314,7 +315,7 @@ static void solve(Solver *s, const float *const dens[2], int nshell, const int d
       float *pm[kMaxPeers * 6];
       for (int r = 0; r < s->nranks; ++r)
         for (int k = 0; k < 6; ++k) pm[r * 6 + k] = reinterpret_cast<float *>(s->peer[r][2]) + ((size_t)q * 6 + k) * s->npix;
-      LAUNCHED(s) launch_maps_broadcast(p, mp[q], pm, s->d_need, kCoarseOrder, st);
+      LAUNCHED(s) launch_maps_broadcast(p, mp[q], pm, s->d_need, kCoarseOrder, st, s->d_gmask);
     }
     stream_barrier(s, st);
   }
@@ -442,6 +443,8 @@ clb_solver *clb_solver_create(long sht_order, long lmax, long ray_order, const d
       s->d_need = (unsigned char *)dmalloc(2 * nc);
       CLB_CUDA_CHECK(cudaMemcpy(s->d_need, mask.data(), nc, cudaMemcpyHostToDevice));
       CLB_CUDA_CHECK(cudaMemcpy(s->d_need + nc, safe.data(), nc, cudaMemcpyHostToDevice));
+      s->d_gmask = (unsigned char *)dmalloc((size_t)(s->npix / 4));
+      LAUNCHED(s) launch_group_masks(p, s->d_need, kCoarseOrder, s->d_gmask, nullptr);
       long bits = 0;
       for (long c = 0; c < nc; ++c) bits += __builtin_popcount(mask[c]);
       s->need_fraction = (double)bits / ((double)nc * nranks);
@@ -466,7 +469,7 @@ void clb_solver_destroy(clb_solver *h)
   if (s->fused) release_peers(s);
   else if (s->nranks == 1) { cudaFree(s->g_send); cudaFree(s->b_send); cudaFree(s->maps); }
   cudaFree(s->alm_re); cudaFree(s->alm_im); cudaFree(s->dens[0]); cudaFree(s->dens[1]); cudaFree(s->rays);
-  cudaFree(s->d_sum6); cudaFree(s->d_err); cudaFree(s->d_need);
+  cudaFree(s->d_sum6); cudaFree(s->d_err); cudaFree(s->d_need); cudaFree(s->d_gmask);
   cudaFreeHost(s->h_sum6); cudaFreeHost(s->h_stage[0]); cudaFreeHost(s->h_stage[1]); cudaFree(s->d_raw[0]); cudaFree(s->d_raw[1]);
   for (int k = 0; k < 2; ++k) { if (s->dens_ready[k]) cudaEventDestroy(s->dens_ready[k]); if (s->dens_free[k]) cudaEventDestroy(s->dens_free[k]); }
   if (s->ev_tmp) cudaEventDestroy(s->ev_tmp);
@@ -595,7 +598,7 @@ void clb_solver_alm2allmaps(clb_solver *h, const double *alm_re, const double *a
     float *pm[kMaxPeers * 6];
     for (int q = 0; q < s->nranks; ++q)
       for (int k = 0; k < 6; ++k) pm[q * 6 + k] = reinterpret_cast<float *>(s->peer[q][2]) + (size_t)k * s->npix;
-    LAUNCHED(s) launch_maps_broadcast(p, mp, pm, s->d_need, kCoarseOrder, st);
+    LAUNCHED(s) launch_maps_broadcast(p, mp, pm, s->d_need, kCoarseOrder, st, s->d_gmask);
     stream_barrier(s, st);
   }
 }
