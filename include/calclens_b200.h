@@ -29,8 +29,15 @@ int clb_device_count(void);
 void clb_set_device(int device);
 /* kernels launched by this library since load (bench.py reports it as gpu_launches) */
 long clb_launch_count(void);
-/* tuning knobs: what = 0 synthesis rings per thread (1..4), 1 analysis rings per thread (1,2,4,6,8,10,12),
- * 2 threads per CTA of the large ring FFTs (256, 512; read at plan creation) */
+/* tuning knobs (development; the defaults are the measured optimum on B200):
+ *   0 Legendre synthesis rings per thread, one-shell pass (1..4; 4)       1 analysis rings per thread, one-shell (1,2,4,6,8; 8)
+ *   2 threads per CTA of the large ring FFTs (256..1024; 512; read at plan creation)
+ *   3 warps per CTA of the Legendre kernels (1,2,4; 4)                    4 run every ring FFT from global scratch (0|1; 0)
+ *   5 partial-sum rows per m of the Legendre analysis (0 = automatic)     6 field groups per ring in the ring synthesis (0|1|3)
+ *   7 ring-FFT class launches on parallel streams (0|1; 1)                8 skip phases of the ring synthesis (timing aid, wrong results)
+ *   9 synthesis rings per thread, two-shell pass (1..4; 3)               10 analysis rings per thread, two-shell pass (1,2,4,6,8; 8)
+ *  11 shells per SHT pass a solver is provisioned for (1|2; 2; read by clb_solver_create)
+ *  12 overlap the analysis warp sum with the next block: 0 never, 1 one-shell passes only (default), 2 always */
 void clb_set_tuning(int what, int value);
 
 /* ---- plan: replaces healpixsht_plan / healpixsht_destroy_plan (healpix_shtrans.c:54-160, :496-516) and
