@@ -242,6 +242,22 @@ def make_count_maps(solver, nmaps, lmax, seed=1234, nbar=8.0, sigma=0.5):
     return maps
 
 
+def plane_schedule(first, n, shells, prefetch=False):
+    """How a run of n consecutive planes starting at `first` is stepped: [(plane, partner or None, planes to prefetch)].
+    Two shells per SHT pass (--shells 2, the default): plane 0 of the run is solved together with plane 1, plane 2 with plane 3,
+    ...; an odd last plane is solved alone -- a run does exactly n planes of work, whatever was solved before or comes after.
+    prefetch (host maps): the planes to come stream in behind the kernels of the step that frees the density buffers."""
+    out = []
+    for i in range(n):
+        s = first + i
+        partner = s + 1 if (shells == 2 and i % 2 == 0 and i + 1 < n) else None
+        ahead = []
+        if prefetch:
+            ahead = [s + 1] if shells == 1 else ([s + 2, s + 3] if i % 2 == 0 else [])
+        out.append((s, partner, ahead))
+    return out
+
+
 STAGES = ["scale", "fft_analysis", "a2a_g", "legendre_analysis", "legendre_synthesis", "a2a_b", "fft_synthesis", "map_allreduce", "rays"]
 
 
@@ -285,19 +301,10 @@ def measure(a, L, poisson, torch, dist, world, rank, local_rank, group, order, r
             return float(t.item())
         return ms
 
-    # Two shells per SHT pass (--shells 2, the default): inside a run of n consecutive planes, plane 0 is solved together with
-    # plane 1, plane 2 with plane 3, ...; an odd last plane is solved alone.  A run therefore does exactly n planes of work.
     def run_planes(first, n, maps, read_summary=False, prefetch=False):
-        summ = None
-        for i in range(n):
-            s = first + i
-            pair = None
-            if a.shells == 2 and i % 2 == 0 and i + 1 < n:
-                pair = (maps[(s + 1) % nmaps],) + tuple(plane_args(s + 1, peek=True)[:3])
-            pre = None
-            if prefetch:   # host maps: the planes to come stream in behind this plane's kernels
-                ahead = [s + 1] if a.shells == 1 else ([s + 2, s + 3] if i % 2 == 0 else [])
-                pre = [(maps[q % nmaps],) + tuple(plane_args(q, peek=True)[:3]) for q in ahead] or None
+        for s, partner, ahead in plane_schedule(first, n, a.shells, prefetch):
+            pair = None if partner is None else (maps[partner % nmaps],) + tuple(plane_args(partner, peek=True)[:3])
+            pre = [(maps[q % nmaps],) + tuple(plane_args(q, peek=True)[:3]) for q in ahead] or None
             summ = solver.step(maps[s % nmaps], *plane_args(s), read_summary=read_summary, prefetch=pre, pair=pair)
             yield s, summ
 

@@ -577,6 +577,9 @@ int launch_legendre_analysis(ShtPlan *p, const double2 *d_g_recv, double *d_alm_
   if (rows <= 0) {
     const long want_warps = 16L * 3 * sm_count() * g_leg_warps_per_cta;
     rows = (int)std::min<long>(nchunk, std::max<long>(16, (want_warps + p->nm_loc - 1) / p->nm_loc));
+    // ... and no more than ~24 GB of partial sums (lmax = 3 Nside - 1 at Nside 4096 would take 39 GB with 16 rows and two shells)
+    const double row_gb = 16e-9 * (double)p->alm_total * nshell;
+    while (rows > 8 && rows * row_gb > 24.0) rows = (rows + 1) / 2;
   }
   rows = std::max(1, std::min(rows, nchunk));
   rows = (nchunk + (nchunk / rows) - 1) / (nchunk / rows);     // chunks per warp = floor(nchunk / rows); rows = what that needs

@@ -174,3 +174,25 @@ def test_fused_exchange_addresses_match_the_all_to_all_layout():
             assert q == rp_owner[rp] and off == lays[q].g_send_index(m, rp, hemi)
             q, off = me.b_push_index(m_idx, f, rp, hemi)
             assert q == rp_owner[rp] and off == lays[q].b_recv_index(m, f, rp, hemi)
+
+
+def test_bench_plane_schedule_does_exactly_n_planes_of_work():
+    """bench.py pairs consecutive planes for the two-shell passes; a timed run of n planes must contain n planes of SHT work:
+    floor(n/2) pair solves + (n mod 2) single solves, never a pair that reaches outside the run"""
+    import bench
+    for first in (0, 3, 8):
+        for n in (1, 2, 5, 6, 20):
+            sch = bench.plane_schedule(first, n, 2, prefetch=True)
+            assert [s for s, _, _ in sch] == list(range(first, first + n))
+            solved = []
+            for s, partner, ahead in sch:
+                if partner is not None:
+                    assert partner == s + 1 and partner < first + n
+                    solved += [s, partner]
+                elif s not in solved:
+                    solved.append(s)
+                assert all(q > s for q in ahead) and len(ahead) <= 2
+            assert solved == list(range(first, first + n))
+            assert sum(1 for _, p, _ in sch if p is not None) == n // 2
+            one = bench.plane_schedule(first, n, 1, prefetch=True)
+            assert all(p is None for _, p, _ in one) and all(a == [s + 1] for s, _, a in one)
