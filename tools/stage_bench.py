@@ -14,7 +14,9 @@ for a in sys.argv[3:]:
     elif a.startswith("warps="): _lib.load().clb_set_tuning(3, int(a[6:]))
     elif a.startswith("fft="): _lib.load().clb_set_tuning(2, int(a[4:]))
     elif a.startswith("scratch="): _lib.load().clb_set_tuning(4, int(a[8:]))
-    elif a.startswith("sr="): _lib.load().clb_set_tuning(5, int(a[3:]))
+    elif a.startswith("rows="): _lib.load().clb_set_tuning(5, int(a[5:]))
+    elif a.startswith("streams="): _lib.load().clb_set_tuning(7, int(a[8:]))
+    elif a.startswith("pipe="): _lib.load().clb_set_tuning(12, int(a[5:]))
     elif a.startswith("fg="): _lib.load().clb_set_tuning(6, int(a[3:]))
     elif a.startswith("dbg="): _lib.load().clb_set_tuning(8, int(a[4:]))
     else: reps = int(a)
