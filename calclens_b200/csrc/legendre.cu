@@ -538,17 +538,26 @@ static void launch_ana_t(const ShtPlan *p, const double2 *g_recv, const double2 
 #define CLB_ANA_ARGS g_recv, p->g_recv_total, gsrc, p->d_g_off, p->d_g_stride, p->d_A, p->d_row_off, p->d_ls_ana, p->d_seed, p->d_cth, \
       p->d_m_loc, p->d_alm_off, reinterpret_cast<double2 *>(p->d_part), (long)rows * p->alm_total, p->alm_total, p->nrp,           \
       (int)p->lmax, rows, nchunk
-  auto smem_of = [&](int bufs) { return sizeof(double) * (size_t)warps * (2 * kAnaTile + bufs * 16 * 33 + 2 * R * 32); };
+  // dynamic shared memory per warp (see the kernel): A tiles, parked partial sums (two buffers when pipelined), seeds
+  auto warp_bytes = [](int bufs) { return sizeof(double) * (size_t)(2 * kAnaTile + bufs * 16 * 33 + 2 * R * 32); };
   if (g_ana_pipeline == 2 || (g_ana_pipeline == 1 && NS == 1)) {
     static bool done[64] = {};   // (per instantiation and device: the attribute belongs to the function in one context)
     bool &attr = done[cur_device() & 63];
-    if (!attr) { CLB_CUDA_CHECK(cudaFuncSetAttribute(legendre_analysis_kernel<R, NS, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(2) * 4 / warps)); attr = true; }
-    legendre_analysis_kernel<R, NS, NB, true><<<grid, 32 * warps, smem_of(2), st>>>(CLB_ANA_ARGS);
+    if (!attr) {
+      CLB_CUDA_CHECK(cudaFuncSetAttribute(legendre_analysis_kernel<R, NS, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(warp_bytes(2) * kLegWarps)));
+      attr = true;
+    }
+    legendre_analysis_kernel<R, NS, NB, true><<<grid, 32 * warps, warp_bytes(2) * warps, st>>>(CLB_ANA_ARGS);
   } else {
     static bool done[64] = {};
     bool &attr = done[cur_device() & 63];
-    if (!attr) { CLB_CUDA_CHECK(cudaFuncSetAttribute(legendre_analysis_kernel<R, NS, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(1) * 4 / warps)); attr = true; }
-    legendre_analysis_kernel<R, NS, NB, false><<<grid, 32 * warps, smem_of(1), st>>>(CLB_ANA_ARGS);
+    if (!attr) {
+      CLB_CUDA_CHECK(cudaFuncSetAttribute(legendre_analysis_kernel<R, NS, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(warp_bytes(1) * kLegWarps)));
+      attr = true;
+    }
+    legendre_analysis_kernel<R, NS, NB, false><<<grid, 32 * warps, warp_bytes(1) * warps, st>>>(CLB_ANA_ARGS);
   }
 #undef CLB_ANA_ARGS
 }
