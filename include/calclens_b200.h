@@ -232,7 +232,9 @@ void clb_solver_set_next(clb_solver *s, const float *next_counts_map, float prem
  * Two planes per SHT pass: register the plane AFTER the one the next clb_solver_step will be given.  That step then runs
  * both planes through one pass of each Legendre kernel (clb_legendre_*_shells_dev), updates the rays with its own plane
  * and keeps the partner's six maps; the following clb_solver_step, given the partner's pointer and scalings, finds them
- * and only updates the rays.  Rays, maps and sums are bit-identical to two ordinary steps. */
+ * and only updates the rays.  Rays, maps and sums are bit-identical to two ordinary steps.  A plane is identified by its
+ * map pointer and the three scalings; the partner's map is read during the step that follows clb_solver_set_pair (and a
+ * map registered with clb_solver_set_next while that step's kernels run), so its contents must be final by then. */
 void clb_solver_set_pair(clb_solver *s, const float *partner_counts_map, float premul, float densmul, float backdens);
 /* synchronise and return the error bits of clb_solver_step */
 int clb_solver_check(clb_solver *s, void *stream);
