@@ -196,3 +196,27 @@ def test_bench_plane_schedule_does_exactly_n_planes_of_work():
             assert sum(1 for _, p, _ in sch if p is not None) == n // 2
             one = bench.plane_schedule(first, n, 1, prefetch=True)
             assert all(p is None for _, p, _ in one) and all(a == [s + 1] for s, _, a in one)
+
+
+def test_b_layout_is_a_contiguous_run_in_m_for_every_ring_and_field():
+    """the property the ring FFT relies on: inside a peer block the b_m of one (ring pair, field) are
+    consecutive in m with the two hemispheres interleaved, so a ring's FFT streams its input instead of gathering it"""
+    order, lmax = 3, 12
+    nside = 1 << order
+    for nranks in (1, 3):
+        rp_owner, m_owner = clb.default_owners(order, lmax, nranks)
+        for r in range(nranks):
+            L = layout.ExchangeLayout(nside, lmax, nranks, r, rp_owner, m_owner)
+            for rp in L.my_rp[:3]:
+                for f in (0, 5):
+                    for q in range(nranks):
+                        ms = [m for m in range(lmax + 1) if m_owner[m] == q]
+                        idx = [L.b_recv_index(m, f, rp, 0) for m in ms]
+                        assert all(b - a == 2 for a, b in zip(idx, idx[1:]))
+                        assert all(L.b_recv_index(m, f, rp, 1) == i + 1 for m, i in zip(ms, idx))
+            # and on the sending side the (north, south) pair of a field is 2 consecutive elements, fields nm_mine * 2 apart
+            for m in L.my_m[:2]:
+                for rp in (0, 2 * nside - 1):
+                    a = L.b_send_index(m, 0, rp, 0)
+                    assert L.b_send_index(m, 0, rp, 1) == a + 1
+                    assert L.b_send_index(m, 1, rp, 0) == a + 2 * L.my_m.size
